@@ -1,0 +1,150 @@
+/*
+ * omc_b200.h -- C ABI of libomc_b200.so, the B200 (sm_100a) bounding engine for
+ * sean-lo/OptimalMatrixCompletion.jl's disjunctive branch-and-bound.
+ *
+ * The reference has no FFI: its seam is the set of Julia functions the main loop calls
+ * (OMC.jl = /root/reference/src/OptimalMatrixCompletion.jl).  Each entry point below names the
+ * reference function whose BODY it replaces; the Julia glue (optimalmatrixcompletion.jl_b200/julia/)
+ * keeps the signatures and result-Dict keys and ccall's these.
+ *
+ * Conventions:
+ *   - every call returns int32: 0 = OK, < 0 = error (message via omc_last_error()); nothing throws
+ *     across the ABI;
+ *   - the caller owns every host buffer; the library copies in/out and keeps no host pointer after
+ *     return; handles are opaque and freed by the matching destroy;
+ *   - matrices are column-major Float64 exactly as Julia stores Matrix{Float64};
+ *     the mask is Julia's BitMatrix.chunks (UInt64 words, column-major bit index, LSB first);
+ *   - indices inside the ABI are 0-based;
+ *   - calls are blocking and made from one host thread per process (the reference is single
+ *     threaded); one process drives one GPU (omc_init(device)), N GPUs = N processes.
+ *   - There is NO CPU fallback: every compute entry fails with OMC_ERR_CUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef OMC_B200_H
+#define OMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMC_OK 0
+#define OMC_ERR_ARG (-1)
+#define OMC_ERR_CUDA (-2)
+#define OMC_ERR_STATE (-3)
+#define OMC_ERR_UNSUPPORTED (-4)
+
+/* per-node solver status; the Julia glue maps them to the MOI codes the host loop branches on
+ * (OMC.jl:780-785, 809-812, 840-842, 1866-1940) */
+#define OMC_STATUS_OPTIMAL 0         /* MOI.OPTIMAL                                              */
+#define OMC_STATUS_ITERATION_LIMIT 1 /* MOI.SLOW_PROGRESS with values -> feasible = true          */
+#define OMC_STATUS_INFEASIBLE 2      /* MOI.INFEASIBLE                    -> feasible = false      */
+#define OMC_STATUS_TIME_LIMIT 3      /* MOI.TIME_LIMIT with values                                */
+#define OMC_STATUS_CUTOFF 4          /* certified lower bound > opts.cutoff: objective := that bound,
+                                        reported as MOI.OPTIMAL; the host prunes it at OMC.jl:797  */
+
+/* disjunctive_cuts_type (OMC.jl:1581,1603,1635) */
+#define OMC_CUT_LINEAR 0
+#define OMC_CUT_LINEAR2 1
+#define OMC_CUT_LINEAR3 2
+
+typedef struct omc_problem omc_problem;   /* (A, indices, gamma, k) resident in HBM + cut pool + state pool */
+typedef struct omc_frontier omc_frontier; /* a batch of open nodes resident in HBM                          */
+
+typedef struct omc_relax_opts {
+  double eps_abs;          /* ADMM residual tolerances (scaled program)                    */
+  double eps_rel;
+  int32_t max_iter;
+  int32_t check_every;     /* residual / termination check period                          */
+  int32_t adapt_every;     /* rho re-balancing period (multiple of check_every)            */
+  int32_t fix_linear3_right; /* 0 = replicate OMC.jl:1675 (reference quirk Q1), 1 = valid secant */
+  double rho0;
+  double sigma;
+  double alpha;            /* over-relaxation                                              */
+  double cutoff;           /* incumbent upper bound; +inf disables early pruning           */
+  double time_limit_s;     /* per call; <= 0 disables                                      */
+  double jacobi_tol;       /* relative off-diagonal tolerance of the eigensolver           */
+  int32_t reortho_every;   /* restart the eigenvector basis from I every this many iterations (0 = never) */
+  int32_t reserved;
+} omc_relax_opts;
+
+/* ---- library / device ------------------------------------------------------------------------ */
+int32_t omc_init(int32_t device);
+int32_t omc_shutdown(void);
+const char* omc_last_error(void);
+int32_t omc_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* free_bytes);
+/* stream the library launches on (a cudaStream_t), so a host can bracket launches with its own events */
+void* omc_stream(void);
+
+/* ---- problem: replaces the per-call (A, indices, gamma) arguments of every function below ---- */
+/* mask_chunks: BitMatrix.chunks, ceil(n*m/64) words.  state_pool_capacity: number of warm-start
+ * records (ADMM state of a relaxed node, reused by its children) the problem can hold.            */
+int32_t omc_problem_create(int32_t n, int32_t m, int32_t k, const double* A, const uint64_t* mask_chunks,
+                           double gamma, int32_t cut_type, int32_t state_pool_capacity, omc_problem** out);
+int32_t omc_problem_destroy(omc_problem* p);
+/* mask compaction (replaces the indices[i,j] loops OMC.jl:2200,2220,1852,2354).  Pass NULL arrays to
+ * query nnz only.  rowptr[n+1]/colidx[nnz] = row-CSR, colptr[m+1]/rowidx[nnz] = column-CSC, ascending. */
+int32_t omc_problem_get_csr(omc_problem* p, int32_t* rowptr, int32_t* colidx, int32_t* colptr, int32_t* rowidx,
+                            int64_t* nnz);
+
+/* ---- cut pool: one entry per (breakpoint_vec x, Uhat) created at OMC.jl:2522; only vhat = Uhat'x
+ * is ever read (OMC.jl:1577, 2053).  A node is a list of (cut id, direction codes[k]).              */
+int32_t omc_cutpool_add(omc_problem* p, const double* x, const double* vhat, int32_t* cut_id);
+int32_t omc_cutpool_size(omc_problem* p, int32_t* size);
+
+/* ---- relaxation: replaces the body of matrix_completion_SDP_relaxation (OMC.jl:1431-1943) and
+ * compute_SDP_relaxation_objective (OMC.jl:1945-1977) for B nodes at once.                         */
+void omc_relax_default_opts(omc_relax_opts* o);
+/* node b owns cut entries node_cut_ptr[b] .. node_cut_ptr[b+1]-1; entry e is pool cut node_cut_ids[e]
+ * with direction codes node_cut_dirs[e*k + j] (index into ["left","right"] / ["left","middle","right"] /
+ * ["left","inner_left","inner_right","right"], OMC.jl:2481-2491).
+ * warm_ids[b]  : state-pool record to start from (-1 = cold start).  May be NULL.
+ * save_ids[b]  : state-pool record that receives node b's final ADMM state (-1 = none).  May be NULL. */
+int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_ptr, const int32_t* node_cut_ids,
+                            const uint8_t* node_cut_dirs, const int32_t* warm_ids, const int32_t* save_ids,
+                            omc_frontier** out);
+/* one pass of the hot path over the resident batch; kernel_ms (may be NULL) = CUDA-event time of the
+ * fused ADMM kernel on the library stream */
+int32_t omc_frontier_relax(omc_frontier* f, const omc_relax_opts* opts, float* kernel_ms);
+/* results: any pointer may be NULL.  X[B*n*m], Y[B*n*n], U[B*n*k], Theta[B*m*m] column-major per node.
+ * res[2*b] / res[2*b+1] = primal / dual residual.                                                       */
+int32_t omc_frontier_fetch(omc_frontier* f, int32_t* status, double* objective, double* lower_bound,
+                           int32_t* iters, double* res, double* X, double* Y, double* U, double* Theta);
+int32_t omc_frontier_destroy(omc_frontier* f);
+/* convenience = create + relax + fetch + destroy (host buffers in, host buffers out) */
+int32_t omc_relax_batch(omc_problem* p, int32_t B, const int32_t* node_cut_ptr, const int32_t* node_cut_ids,
+                        const uint8_t* node_cut_dirs, const int32_t* warm_ids, const int32_t* save_ids,
+                        const omc_relax_opts* opts, int32_t* status, double* objective, double* lower_bound,
+                        int32_t* iters, double* res, double* X, double* Y, double* U, double* Theta,
+                        float* kernel_ms);
+
+/* ---- separation oracle: replaces eigs(Symmetric(U*U' - Y), nev, :SR) at OMC.jl:2466-2477 and the
+ * test at OMC.jl:1272-1277.  Y[B*n*n], U[B*n*k] column-major.  Outputs: lam[B*nev] ascending,
+ * vec[B*n*nev] (unit, largest-|.| component positive), breakpoint[B*n] (the mixed vector of
+ * OMC.jl:2471-2476 when nev == 2), master_feasible[B] (lam_min >= -1e-6).                           */
+int32_t omc_smallest_eigvecs_batch(int32_t n, int32_t k, int32_t B, const double* Y, const double* U, int32_t nev,
+                                   double* lam, double* vec, double* breakpoint, int32_t* master_feasible);
+
+/* ---- alternating minimisation: replaces the body of alternating_minimization (OMC.jl:1979-2279).
+ * cut entries as for a node (ncuts may be 0).  objectives[max_iters].                               */
+int32_t omc_altmin(omc_problem* p, const double* U_initial, int32_t ncuts, const int32_t* cut_ids,
+                   const uint8_t* cut_dirs, double eps, int32_t max_iters, double time_limit_s, double* U,
+                   double* V, int32_t* converged, int32_t* n_iters, double* objectives, double* solve_time);
+
+/* ---- fused objective + MSE: replaces evaluate_objective (OMC.jl:2330-2359) and compute_MSE
+ * (OMC.jl:2373-2409).  X column-major n*m.  out[0] objective, out[1] MSE in, out[2] MSE out, out[3] MSE all */
+int32_t omc_objective_mse(omc_problem* p, const double* X, double* out4);
+
+/* ---- diagnostics used by tests / bench ------------------------------------------------------- */
+/* batched symmetric eigendecomposition + PSD projection of B dense N x N matrices (row-major, symmetric):
+ * P[B*N*N] = projection onto the PSD cone, lam[B*N] = eigenvalues (unordered), sweeps[B] */
+int32_t omc_debug_psd_project_batch(int32_t N, int32_t B, const double* Vin, double* P, double* lam,
+                                    int32_t* sweeps, float* kernel_ms);
+/* measured FP64 peaks of this GPU: out[0] = DFMA TFLOP/s, out[1] = DMMA (mma.m8n8k4.f64) TFLOP/s */
+int32_t omc_measure_fp64_peak(double* out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMC_B200_H */

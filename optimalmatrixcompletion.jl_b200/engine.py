@@ -1,0 +1,295 @@
+"""Host-side mirror of the reference's operator interface over the C ABI.
+
+Function names, argument meaning and result-dict keys follow
+/root/reference/src/OptimalMatrixCompletion.jl (OMC.jl) so the parity tests read like
+tests of the reference; every numerical body is a call into libomc_b200.so (CUDA,
+sm_100a).  NumPy is used for buffers only.  Nothing here imports ``oracle``.
+"""
+import ctypes as C
+import time
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import RelaxOpts, check, CUT_TYPES
+
+LABELS = {
+    "linear": ["left", "right"],                                  # OMC.jl:2482
+    "linear2": ["left", "middle", "right"],                       # OMC.jl:2486
+    "linear3": ["left", "inner_left", "inner_right", "right"],    # OMC.jl:2490
+}
+# status -> the MOI termination status name the Julia glue reports (OMC.jl:1866-1940)
+MOI_STATUS = {0: "OPTIMAL", 1: "SLOW_PROGRESS", 2: "INFEASIBLE", 3: "TIME_LIMIT", 4: "OPTIMAL"}
+
+_initialised = None
+
+
+def init(device: int = 0):
+    """omc_init: one process drives one GPU."""
+    global _initialised
+    lib = _lib.load()
+    if _initialised != device:
+        check(lib.omc_init(device))
+        _initialised = device
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty)) if a is not None else None
+
+
+def bitmatrix_chunks(indices: np.ndarray) -> np.ndarray:
+    """Julia ``BitMatrix.chunks`` of a bool (n, m) array: column-major bit index, LSB first."""
+    n, m = indices.shape
+    flat = np.asarray(indices, dtype=bool).T.reshape(-1)
+    nchunks = (n * m + 63) // 64
+    padded = np.zeros(nchunks * 64, dtype=np.uint8)
+    padded[: n * m] = flat
+    return np.packbits(padded.reshape(nchunks, 64), axis=1, bitorder="little").view(np.uint64).reshape(-1).copy()
+
+
+def default_opts(**kw) -> RelaxOpts:
+    o = RelaxOpts()
+    _lib.load().omc_relax_default_opts(C.byref(o))
+    for key, v in kw.items():
+        if not hasattr(o, key):
+            raise TypeError(f"unknown relaxation option {key}")
+        setattr(o, key, v)
+    return o
+
+
+@dataclass
+class Cut:
+    """One entry of BBNodeDisjunctiveCuts.cuts (OMC.jl:33-35): (breakpoint_vec, Uhat, directions)."""
+    cut_id: int
+    x: np.ndarray
+    Uhat: np.ndarray
+    directions: List[str]
+
+
+class Problem:
+    """(k, A, indices, gamma) resident in HBM, its cut pool and warm-start state pool."""
+
+    def __init__(self, k: int, A: np.ndarray, indices: np.ndarray, gamma: float, disjunctive_cuts_type: str = "linear",
+                 state_pool_capacity: int = 0, device: int = 0):
+        if disjunctive_cuts_type not in CUT_TYPES:
+            raise ValueError('Disjunctive cuts type must be either "linear" or "linear2" or "linear3"; '
+                             f"{disjunctive_cuts_type} supplied instead.")         # OMC.jl:1456-1462
+        if A.shape != indices.shape:
+            raise ValueError("Dimension mismatch. Input matrix A must have size (n, m); "
+                             "Input matrix indices must have size (n, m).")        # OMC.jl:240-246
+        self.lib = init(device)
+        self.k, self.gamma, self.cut_type = int(k), float(gamma), disjunctive_cuts_type
+        self.n, self.m = A.shape
+        self.A = np.asfortranarray(A, dtype=np.float64)
+        self.indices = np.asarray(indices, dtype=bool)
+        self._chunks = bitmatrix_chunks(self.indices)
+        self.handle = C.c_void_p()
+        check(self.lib.omc_problem_create(self.n, self.m, self.k, _ptr(self.A, C.c_double),
+                                          _ptr(self._chunks, C.c_uint64), self.gamma, CUT_TYPES[disjunctive_cuts_type],
+                                          int(state_pool_capacity), C.byref(self.handle)))
+        self.state_pool_capacity = int(state_pool_capacity)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.omc_problem_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mask compaction ------------------------------------------------------------------
+    def csr(self):
+        nnz = C.c_int64()
+        check(self.lib.omc_problem_get_csr(self.handle, None, None, None, None, C.byref(nnz)))
+        rowptr = np.zeros(self.n + 1, np.int32); colptr = np.zeros(self.m + 1, np.int32)
+        colidx = np.zeros(max(nnz.value, 1), np.int32); rowidx = np.zeros(max(nnz.value, 1), np.int32)
+        check(self.lib.omc_problem_get_csr(self.handle, _ptr(rowptr, C.c_int32), _ptr(colidx, C.c_int32),
+                                           _ptr(colptr, C.c_int32), _ptr(rowidx, C.c_int32), C.byref(nnz)))
+        return rowptr, colidx[: nnz.value], colptr, rowidx[: nnz.value]
+
+    # ---- cut pool -------------------------------------------------------------------------
+    def add_cut(self, x: np.ndarray, Uhat: np.ndarray) -> int:
+        """Registers (breakpoint_vec, Uhat) created at OMC.jl:2522; only vhat = Uhat'x is uploaded (OMC.jl:1577)."""
+        x = _f64(x)
+        vhat = _f64(np.asarray(Uhat).T @ x) if np.asarray(Uhat).ndim == 2 else _f64(Uhat)
+        cid = C.c_int32()
+        check(self.lib.omc_cutpool_add(self.handle, _ptr(x, C.c_double), _ptr(vhat, C.c_double), C.byref(cid)))
+        return cid.value
+
+    def _flatten(self, node_cuts: List[List[Cut]]):
+        B = len(node_cuts)
+        ptr = np.zeros(B + 1, np.int32)
+        ids, dirs = [], []
+        lab = LABELS[self.cut_type]
+        for b, cuts in enumerate(node_cuts):
+            ptr[b + 1] = ptr[b] + len(cuts)
+            for c in cuts:
+                ids.append(c.cut_id)
+                dirs.extend(lab.index(d) for d in c.directions)
+        ids = np.asarray(ids if ids else [0], np.int32)
+        dirs = np.asarray(dirs if dirs else [0], np.uint8)
+        return ptr, ids, dirs
+
+    # ---- relaxation -----------------------------------------------------------------------
+    def frontier(self, node_cuts: List[List[Cut]], warm_ids=None, save_ids=None) -> "Frontier":
+        return Frontier(self, node_cuts, warm_ids, save_ids)
+
+    def relax_batch(self, node_cuts: List[List[Cut]], opts: Optional[RelaxOpts] = None, warm_ids=None, save_ids=None):
+        """Bodies of B calls of matrix_completion_SDP_relaxation (OMC.jl:1431-1943) in one launch."""
+        f = Frontier(self, node_cuts, warm_ids, save_ids)
+        try:
+            t0 = time.perf_counter()
+            f.relax(opts)
+            out = f.fetch()
+            dt = time.perf_counter() - t0
+        finally:
+            f.close()
+        for r in out:
+            r["solve_time"] = dt / len(out)
+        return out
+
+    # ---- objective / MSE ------------------------------------------------------------------
+    def objective_mse(self, X: np.ndarray) -> Tuple[float, float, float, float]:
+        if X.shape != (self.n, self.m):
+            raise ValueError("Dimension mismatch. Input matrix X must have size (n, m).")
+        Xf = np.asfortranarray(X, dtype=np.float64)
+        out = np.zeros(4)
+        check(self.lib.omc_objective_mse(self.handle, _ptr(Xf, C.c_double), _ptr(out, C.c_double)))
+        return tuple(float(v) for v in out)
+
+
+class Frontier:
+    """A batch of open nodes resident in HBM (omc_frontier)."""
+
+    def __init__(self, problem: Problem, node_cuts, warm_ids=None, save_ids=None):
+        self.p = problem
+        self.B = len(node_cuts)
+        ptr, ids, dirs = problem._flatten(node_cuts)
+        self._keep = (ptr, ids, dirs)
+        w = np.asarray(warm_ids, np.int32) if warm_ids is not None else None
+        s = np.asarray(save_ids, np.int32) if save_ids is not None else None
+        self.handle = C.c_void_p()
+        check(problem.lib.omc_frontier_create(problem.handle, self.B, _ptr(ptr, C.c_int32), _ptr(ids, C.c_int32),
+                                              _ptr(dirs, C.c_uint8), _ptr(w, C.c_int32), _ptr(s, C.c_int32),
+                                              C.byref(self.handle)))
+        self.kernel_ms = None
+
+    def relax(self, opts: Optional[RelaxOpts] = None) -> float:
+        ms = C.c_float()
+        check(self.p.lib.omc_frontier_relax(self.handle, C.byref(opts) if opts is not None else None, C.byref(ms)))
+        self.kernel_ms = ms.value
+        return ms.value
+
+    def fetch(self, matrices: bool = True):
+        p, B = self.p, self.B
+        status = np.zeros(B, np.int32); iters = np.zeros(B, np.int32)
+        obj = np.zeros(B); lb = np.zeros(B); res = np.zeros(2 * B)
+        X = np.zeros((B, p.m, p.n)) if matrices else None   # column-major (n, m) per node
+        Y = np.zeros((B, p.n, p.n)) if matrices else None
+        U = np.zeros((B, p.k, p.n)) if matrices else None
+        check(p.lib.omc_frontier_fetch(self.handle, _ptr(status, C.c_int32), _ptr(obj, C.c_double),
+                                       _ptr(lb, C.c_double), _ptr(iters, C.c_int32), _ptr(res, C.c_double),
+                                       _ptr(X, C.c_double), _ptr(Y, C.c_double), _ptr(U, C.c_double), None))
+        out = []
+        for b in range(B):
+            r = {
+                "model": None,                                        # OMC.jl:1861 (never read by the host loop)
+                "termination_status": MOI_STATUS[int(status[b])],     # OMC.jl:1863
+                "status_code": int(status[b]),
+                "feasible": int(status[b]) != _lib.STATUS_INFEASIBLE,  # OMC.jl:1879, 1935
+                "objective": float(obj[b]),                           # OMC.jl:1882-1895
+                "lower_bound": float(lb[b]),
+                "iters": int(iters[b]),
+                "res_p": float(res[2 * b]), "res_d": float(res[2 * b + 1]),
+            }
+            if matrices:
+                r["X"] = X[b].T.copy(); r["Y"] = Y[b].T.copy(); r["U"] = U[b].T.copy()
+            out.append(r)
+        return out
+
+    def close(self):
+        if self.handle:
+            self.p.lib.omc_frontier_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- reference-named operators ------------------------------------------------------------------
+
+def matrix_completion_SDP_relaxation(problem: Problem, cuts: List[Cut], opts: Optional[RelaxOpts] = None, **kw):
+    """OMC.jl:1431-1943 for one node (disjunctive path)."""
+    return problem.relax_batch([cuts], opts, **kw)[0]
+
+
+def evaluate_objective(problem: Problem, X: np.ndarray) -> float:
+    """OMC.jl:2330-2359."""
+    return problem.objective_mse(X)[0]
+
+
+def compute_MSE(problem: Problem, X: np.ndarray, kind: str = "out") -> float:
+    """OMC.jl:2373-2409."""
+    o = problem.objective_mse(X)
+    if kind == "in":
+        return o[1]
+    if kind == "out":
+        return o[2]
+    if kind == "all":
+        return o[3]
+    raise ValueError('Input argument `kind` not recognized! Must be one of "out", "in", or "all".')
+
+
+def smallest_eigvecs_batch(Y: np.ndarray, U: np.ndarray, nev: int = 1):
+    """Batched OMC.jl:2466-2477 + 1272-1277.  Y (B,n,n), U (B,n,k) -> lam (B,nev), vec (B,n,nev), breakpoint (B,n), feasible (B,)"""
+    lib = init(_initialised if _initialised is not None else 0)
+    Y = np.asarray(Y, dtype=np.float64); U = np.asarray(U, dtype=np.float64)
+    if Y.ndim == 2:
+        Y = Y[None]; U = U[None]
+    B, n, _ = Y.shape
+    k = U.shape[2]
+    Yc = np.ascontiguousarray(np.transpose(Y, (0, 2, 1)))   # column-major per node
+    Uc = np.ascontiguousarray(np.transpose(U, (0, 2, 1)))
+    lam = np.zeros((B, nev)); vec = np.zeros((B, nev, n)); bp = np.zeros((B, n)); feas = np.zeros(B, np.int32)
+    check(lib.omc_smallest_eigvecs_batch(n, k, B, _ptr(Yc, C.c_double), _ptr(Uc, C.c_double), nev,
+                                         _ptr(lam, C.c_double), _ptr(vec, C.c_double), _ptr(bp, C.c_double),
+                                         _ptr(feas, C.c_int32)))
+    return lam, np.transpose(vec, (0, 2, 1)).copy(), bp, feas.astype(bool)
+
+
+def matrix_completion_master_feasible(Y, U, X=None, Theta=None, use_disjunctive_cuts=True) -> bool:
+    """OMC.jl:1261-1292 (disjunctive path only)."""
+    if not use_disjunctive_cuts:
+        raise NotImplementedError("McCormick path is out of scope (SURVEY.md section 2)")
+    return bool(smallest_eigvecs_batch(Y, U, 1)[3][0])
+
+
+def psd_project_batch(V: np.ndarray):
+    """Eigensolver self-test entry: V (B,N,N) symmetric -> (P, lam, sweeps, kernel_ms)."""
+    lib = init(_initialised if _initialised is not None else 0)
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    B, N, _ = V.shape
+    P = np.zeros_like(V); lam = np.zeros((B, N)); sw = np.zeros(B, np.int32); ms = C.c_float()
+    check(lib.omc_debug_psd_project_batch(N, B, _ptr(V, C.c_double), _ptr(P, C.c_double), _ptr(lam, C.c_double),
+                                          _ptr(sw, C.c_int32), C.byref(ms)))
+    return P, lam, sw, ms.value
+
+
+def measure_fp64_peak():
+    lib = init(_initialised if _initialised is not None else 0)
+    out = np.zeros(2)
+    check(lib.omc_measure_fp64_peak(_ptr(out, C.c_double)))
+    return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1])}
