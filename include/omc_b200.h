@@ -64,7 +64,7 @@ typedef struct omc_relax_opts {
   double alpha;            /* over-relaxation                                              */
   double cutoff;           /* incumbent upper bound; +inf disables early pruning           */
   double time_limit_s;     /* per call; <= 0 disables                                      */
-  double jacobi_tol;       /* relative off-diagonal tolerance of the eigensolver           */
+  double jacobi_tol;       /* cap of the eigensolver's relative off-diagonal tolerance (it tightens with the ADMM residual) */
   int32_t reortho_every;   /* restart the eigenvector basis from I every this many iterations (0 = never) */
   int32_t reserved;
 } omc_relax_opts;
@@ -111,6 +111,11 @@ int32_t omc_frontier_relax(omc_frontier* f, const omc_relax_opts* opts, float* k
  * res[2*b] / res[2*b+1] = primal / dual residual.                                                       */
 int32_t omc_frontier_fetch(omc_frontier* f, int32_t* status, double* objective, double* lower_bound,
                            int32_t* iters, double* res, double* X, double* Y, double* U, double* Theta);
+/* per-node kernel profile: prof[16*b + q], q = 0..5 SM cycles spent in (w-update + dense rows, assembling V,
+ * DMMA pre-rotation, Jacobi sweeps, reconstruction + dual update, residual checks), 6 = Jacobi sweeps,
+ * 7 = iterations, 8..14 = primal residual per constraint family at the last check
+ * (psd1, psd2, psd3, trace, box, cut v rows, cut aggregated rows) */
+int32_t omc_frontier_fetch_profile(omc_frontier* f, double* prof);
 int32_t omc_frontier_destroy(omc_frontier* f);
 /* convenience = create + relax + fetch + destroy (host buffers in, host buffers out) */
 int32_t omc_relax_batch(omc_problem* p, int32_t B, const int32_t* node_cut_ptr, const int32_t* node_cut_ids,

@@ -46,6 +46,7 @@ SIGNATURES = {
     "omc_frontier_create": (_i32, [_vp, _i32, _pi32, _pi32, _pu8, _pi32, _pi32, _p(_vp)]),
     "omc_frontier_relax": (_i32, [_vp, _p(RelaxOpts), _pf32]),
     "omc_frontier_fetch": (_i32, [_vp, _pi32, _pf64, _pf64, _pi32, _pf64, _pf64, _pf64, _pf64, _pf64]),
+    "omc_frontier_fetch_profile": (_i32, [_vp, _pf64]),
     "omc_frontier_destroy": (_i32, [_vp]),
     "omc_relax_batch": (_i32, [_vp, _i32, _pi32, _pi32, _pu8, _pi32, _pi32, _p(RelaxOpts), _pi32, _pf64, _pf64,
                                _pi32, _pf64, _pf64, _pf64, _pf64, _pf64, _pf32]),

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdarg.h>
+#include <cstdio>
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
@@ -88,7 +89,7 @@ struct omc_frontier {
   int B, E, Lmax, rmax, grid;
   DevBuf<int> cut_ptr, cut_ids, warm, save, status, iters, queue;
   DevBuf<uint8_t> cut_dirs;
-  DevBuf<double> objective, lower_bound, res, X, Y, U, T, scratch;
+  DevBuf<double> objective, lower_bound, res, X, Y, U, T, scratch, prof;
   omc::ScratchLayout SC;
   bool has_warm = false, has_save = false, want_T = false;
   size_t smem = 0;
@@ -500,7 +501,7 @@ void omc_relax_default_opts(omc_relax_opts* o) {
   o->alpha = 1.6;
   o->cutoff = INFINITY;
   o->time_limit_s = 0.0;
-  o->jacobi_tol = 1e-7;
+  o->jacobi_tol = 1e-5;
   o->reortho_every = 0;
 }
 
@@ -561,6 +562,7 @@ int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_p
   FC(f->Y.alloc((size_t)B * p->n * p->n));
   FC(f->U.alloc((size_t)B * p->n * p->k));
   FC(f->scratch.alloc((size_t)f->grid * f->SC.total));
+  FC(f->prof.alloc((size_t)B * 16));
   FC(cudaMemcpyAsync(f->cut_ptr.p, node_cut_ptr, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, g_stream));
   if (E > 0) {
     FC(cudaMemcpyAsync(f->cut_ids.p, node_cut_ids, E * sizeof(int), cudaMemcpyHostToDevice, g_stream));
@@ -604,6 +606,7 @@ int32_t omc_frontier_relax(omc_frontier* f, const omc_relax_opts* opts, float* k
   a.save_ids = f->has_save ? f->save.p : nullptr;
   a.pool_state = p->pool_state.p; a.scratch = f->scratch.p; a.queue = f->queue.p;
   a.status = f->status.p; a.objective = f->objective.p; a.lower_bound = f->lower_bound.p; a.iters = f->iters.p;
+  a.prof = f->prof.p;
   a.res = f->res.p; a.outX = f->X.p; a.outY = f->Y.p; a.outU = f->U.p; a.outT = f->T.p;
   a.o = o; a.Lcap = p->Lcap; a.rmax = f->rmax; a.SL = p->SL; a.SC = f->SC;
   CU(cudaMemsetAsync(f->queue.p, 0, sizeof(int), g_stream));
@@ -643,6 +646,14 @@ int32_t omc_frontier_fetch(omc_frontier* f, int32_t* status, double* objective, 
   if (X) CU(cudaMemcpyAsync(X, f->X.p, B * p->n * p->m * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   if (Y) CU(cudaMemcpyAsync(Y, f->Y.p, B * p->n * p->n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   if (U) CU(cudaMemcpyAsync(U, f->U.p, B * p->n * p->k * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CU(cudaStreamSynchronize(g_stream));
+  return OMC_OK;
+}
+
+int32_t omc_frontier_fetch_profile(omc_frontier* f, double* prof) {
+  NEED_INIT();
+  if (!f || !prof) return fail(OMC_ERR_ARG, "null argument");
+  CU(cudaMemcpyAsync(prof, f->prof.p, (size_t)f->B * 16 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CU(cudaStreamSynchronize(g_stream));
   return OMC_OK;
 }
@@ -692,7 +703,7 @@ int32_t omc_debug_psd_project_batch(int32_t N, int32_t B, const double* Vin, dou
   DevBuf<int> dS;
   CU(dV.alloc((size_t)B * N * N)); CU(dP.alloc((size_t)B * N * N)); CU(dL.alloc((size_t)B * N)); CU(dS.alloc(B));
   CU(cudaMemcpyAsync(dV.p, Vin, (size_t)B * N * N * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-  const size_t smem = ((size_t)2 * g.NP * g.ld + 2 * g.NP + 32) * 8 + (size_t)g.NP * 4 + 128;
+  const size_t smem = ((size_t)2 * g.NP * g.ld + 2 * g.NP + 32) * 8 + (size_t)g.NP * 8 + 128;
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   const int grid = B < g_sm_count ? B : g_sm_count;
@@ -700,15 +711,15 @@ int32_t omc_debug_psd_project_batch(int32_t N, int32_t B, const double* Vin, dou
   if (g.NP <= 32) {
     auto kern = omc::psd_project_debug_kernel<128, 8>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 128, smem, g_stream>>>(N, B, dV.p, dP.p, dL.p, dS.p, 1e-7);
+    kern<<<grid, 128, smem, g_stream>>>(N, B, dV.p, dP.p, dL.p, dS.p, 1e-13);
   } else if (g.NP <= 64) {
     auto kern = omc::psd_project_debug_kernel<256, 16>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 256, smem, g_stream>>>(N, B, dV.p, dP.p, dL.p, dS.p, 1e-7);
+    kern<<<grid, 256, smem, g_stream>>>(N, B, dV.p, dP.p, dL.p, dS.p, 1e-13);
   } else {
     auto kern = omc::psd_project_debug_kernel<512, 26>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, 512, smem, g_stream>>>(N, B, dV.p, dP.p, dL.p, dS.p, 1e-7);
+    kern<<<grid, 512, smem, g_stream>>>(N, B, dV.p, dP.p, dL.p, dS.p, 1e-13);
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(e1, g_stream));
@@ -791,9 +802,52 @@ int32_t omc_altmin(omc_problem* p, const double* U_initial, int32_t ncuts, const
                    const uint8_t* cut_dirs, double eps, int32_t max_iters, double time_limit_s, double* U, double* V,
                    int32_t* converged, int32_t* n_iters, double* objectives, double* solve_time) {
   NEED_INIT();
-  (void)p; (void)U_initial; (void)ncuts; (void)cut_ids; (void)cut_dirs; (void)eps; (void)max_iters; (void)time_limit_s;
-  (void)U; (void)V; (void)converged; (void)n_iters; (void)objectives; (void)solve_time;
-  return fail(OMC_ERR_UNSUPPORTED, "omc_altmin: not built yet");
+  if (!p || !U_initial || !U || !V || !converged || !n_iters || !objectives) return fail(OMC_ERR_ARG, "null argument");
+  if (ncuts < 0 || (ncuts > 0 && (!cut_ids || !cut_dirs))) return fail(OMC_ERR_ARG, "bad cut list");
+  if (max_iters <= 0) return fail(OMC_ERR_ARG, "max_iters must be positive");
+  if (p->k > omc::ALT_MAXK) return fail(OMC_ERR_UNSUPPORTED, "k = %d > %d", p->k, omc::ALT_MAXK);
+  const int n = p->n, m = p->m, k = p->k, L = ncuts;
+  for (int l = 0; l < L; ++l)
+    if (cut_ids[l] < 0 || cut_ids[l] >= p->pool_size) return fail(OMC_ERR_ARG, "cut id out of range");
+  const omc::AltminWs W = omc::make_altmin_ws(n, m, k, L);
+  DevBuf<double> dU, dV, dws, dobj;
+  DevBuf<int> dids, dout;
+  DevBuf<uint8_t> ddirs;
+  CU(dU.alloc((size_t)n * k)); CU(dV.alloc((size_t)k * m)); CU(dws.alloc(W.total)); CU(dobj.alloc(max_iters));
+  CU(dids.alloc(L > 0 ? L : 1)); CU(ddirs.alloc(L > 0 ? (size_t)L * k : 1)); CU(dout.alloc(4));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, g_stream));
+  CU(cudaMemcpyAsync(dU.p, U_initial, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  if (L > 0) {
+    CU(cudaMemcpyAsync(dids.p, cut_ids, L * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMemcpyAsync(ddirs.p, cut_dirs, (size_t)L * k, cudaMemcpyHostToDevice, g_stream));
+  }
+  CU(cudaMemsetAsync(dobj.p, 0, max_iters * sizeof(double), g_stream));
+  omc::AltminArgs a;
+  memset(&a, 0, sizeof a);
+  a.n = n; a.m = m; a.k = k; a.L = L; a.cut_type = p->cut_type; a.fix3 = 0;
+  a.gamma = p->gamma; a.eps = eps; a.inner_eps = 1e-9; a.sigma = 1e-6; a.alpha = 1.6; a.time_limit_s = time_limit_s;
+  a.max_iters = max_iters; a.inner_max = 20000;
+  a.A = p->A.p; a.rowptr = p->rowptr.p; a.colidx = p->colidx.p; a.colptr = p->colptr.p; a.rowidx = p->rowidx.p;
+  a.pool_x = p->pool_x.p; a.pool_vhat = p->pool_vhat.p; a.cut_ids = dids.p; a.cut_dirs = ddirs.p;
+  a.U = dU.p; a.V = dV.p; a.ws = dws.p; a.objectives = dobj.p; a.out_int = dout.p;
+  omc::altmin_kernel<1024><<<1, 1024, 0, g_stream>>>(a);
+  CU(cudaGetLastError());
+  int oi[4] = {0, 0, 0, 0};
+  CU(cudaMemcpyAsync(U, dU.p, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CU(cudaMemcpyAsync(V, dV.p, (size_t)k * m * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CU(cudaMemcpyAsync(objectives, dobj.p, max_iters * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CU(cudaMemcpyAsync(oi, dout.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  CU(cudaEventRecord(e1, g_stream));
+  CU(cudaStreamSynchronize(g_stream));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *converged = oi[0];
+  *n_iters = oi[1];
+  if (solve_time) *solve_time = ms * 1e-3;
+  return OMC_OK;
 }
 
 }  // extern "C"

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(NT, 1) eigsep_kernel(int n, int k, int B, cons
   double* red = jsn + NP / 2;
   double* wsm = red + 32;  // [2] mixing weights
   int* jrot = reinterpret_cast<int*>(wsm + 2);
-  int* sel = jrot + NP / 2;  // [4]: index of smallest, second smallest, sign flips
+  int* sel = jrot + 3 * (NP / 2);  // [4]: index of smallest, second smallest, sign flips
   for (int node = blockIdx.x; node < B; node += gridDim.x) {
     const double* Yn = Y + (size_t)node * n * n;  // column-major
     const double* Un = U + (size_t)node * n * k;  // column-major
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(NT, 1) eigsep_kernel(int n, int k, int B, cons
       Q[(size_t)r * ld + c] = (r == c) ? 1.0 : 0.0;
     }
     __syncthreads();
-    jacobi_sym(S, Q, NP, ld, 1e-8, 60, jcs, jsn, jrot, red);
+    jacobi_sym(S, Q, NP, ld, 1e-13, 60, jcs, jsn, jrot, red);
     for (int i = tid; i < NP; i += NT) lam[i] = S[(size_t)i * ld + i];
     __syncthreads();
     if (tid == 0) {
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NT, 1) eigsep_kernel(int n, int k, int B, cons
 
 inline size_t eigsep_smem_bytes(int n) {
   const Geo g = make_geo(n);
-  return ((size_t)2 * g.NP * g.ld + 2 * g.NP + 32 + 2) * 8 + ((size_t)g.NP / 2 + 4) * 4 + 128;
+  return ((size_t)2 * g.NP * g.ld + 2 * g.NP + 32 + 2) * 8 + (3 * ((size_t)g.NP / 2) + 4) * 4 + 128;
 }
 
 }  // namespace omc

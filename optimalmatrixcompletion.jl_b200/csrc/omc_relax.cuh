@@ -92,6 +92,7 @@ struct RelaxArgs {
   double* outY;
   double* outU;
   double* outT;
+  double* prof;  // [B][16]: [8..14] = primal residual components at the last check; cycles in phase1+2, build V, gemm, jacobi, reconstruct, residual; sweeps; iterations
   omc_relax_opts o;
   int Lcap, rmax;
   StateLayout SL;
@@ -164,11 +165,12 @@ __device__ __forceinline__ double w_entry(const NodeCtx& c, int b, int r, int co
 }
 
 // ---- dense rows R (trace row, cut rows) applied to (Yt, Ut): rhs = R [Yt; Ut] ------------------
-__device__ inline void dense_rows_apply(const NodeCtx& c, double* out, double* scratch) {
+__device__ __noinline__ void dense_rows_apply(const NodeCtx& c, const double* Yp, const double* Up, double* out,
+                                              double* scratch) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int n = c.n, k = c.k, L = c.L;
   double tr = 0.0;
-  for (int i = tid; i < n; i += nt) tr += c.Yt[(size_t)i * n + i];
+  for (int i = tid; i < n; i += nt) tr += Yp[(size_t)i * n + i];
   tr = block_sum(tr, scratch);
   if (tid == 0) out[0] = tr;
   // one warp per cut: xv[l,j] = x_l' Ut[:,j], q_l = x_l' Yt x_l (lower triangle, doubled off-diagonal)
@@ -178,7 +180,7 @@ __device__ inline void dense_rows_apply(const NodeCtx& c, double* out, double* s
     for (int e = lane; e < n * n; e += 32) {
       const int i = e / n, j = e - i * n;
       if (j <= i) {
-        const double y = c.Yt[(size_t)i * n + j];
+        const double y = Yp[(size_t)i * n + j];
         q += ((i == j) ? 1.0 : 2.0) * x[i] * x[j] * y;
       }
     }
@@ -186,7 +188,7 @@ __device__ inline void dense_rows_apply(const NodeCtx& c, double* out, double* s
     double agg = 0.0;
     for (int j = 0; j < k; ++j) {
       double v = 0.0;
-      for (int i = lane; i < n; i += 32) v += x[i] * c.Ut[(size_t)i + (size_t)n * j];
+      for (int i = lane; i < n; i += 32) v += x[i] * Up[(size_t)i + (size_t)n * j];
       v = warp_sum(v);
       if (lane == 0) out[1 + l * k + j] = -v;
       agg += c.al[l * k + j] * v;
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
   double* cbe = cal + P.Lcap * k;          // [Lcap]
   const double** cxp = reinterpret_cast<const double**>(cbe + P.Lcap);  // [Lcap]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(cxp + P.Lcap);           // [1]
-  int* jrot = reinterpret_cast<int*>(mbar + 1);                         // [NP1/2]
-  int* idx = jrot + g1.NP / 2;                                          // [NP1]
+  int* jrot = reinterpret_cast<int*>(mbar + 1);                         // [3*NP1/2]
+  int* idx = jrot + 3 * (g1.NP / 2);                                    // [NP1]
   int* ish = idx + g1.NP;                                               // [8] misc ints
 
   double* scr = P.scratch + (size_t)blockIdx.x * P.SC.total;
@@ -405,6 +407,18 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
     }
 
     bool have_basis[3] = {false, false, false};
+    // Eigensolver tolerance follows the ADMM residual: off(S) <= jtol ||S||_F with jtol two orders below the
+    // current relative residual, inside [1e-13, jacobi_tol].
+    double jtol = P.o.jacobi_tol;
+    long long pc[6] = {0, 0, 0, 0, 0, 0};
+    long long nsweeps = 0;
+    long long tk = clock64();
+#define OMC_TICK(slot)                 \
+  {                                    \
+    const long long now_ = clock64();  \
+    pc[slot] += now_ - tk;             \
+    tk = now_;                         \
+  }
     int status = OMC_STATUS_ITERATION_LIMIT;
     double res_p = 1e300, res_d = 1e300, obj_p = 0.0, obj_d = -1e300, lbound = -1e300;
     int it = 0;
@@ -457,7 +471,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
       }
       __syncthreads();
       // ------------------------------------------------ phase 2: Woodbury correction for the dense rows
-      dense_rows_apply(c, rhs, red);
+      dense_rows_apply(c, c.Yt, c.Ut, rhs, red);
       for (int i = tid; i < r; i += NT) {
         double v = 0.0;
         for (int j = 0; j < r; ++j) v += c.Minv[(size_t)i * r + j] * rhs[j];
@@ -523,6 +537,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
       }
       __syncthreads();
 
+      OMC_TICK(0)
       // ------------------------------------------------ phase 3: the three PSD projections
       const bool reortho = (P.o.reortho_every > 0) && (it % P.o.reortho_every == 0);
       for (int b = 0; b < 3; ++b) {
@@ -553,6 +568,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           buf0[(size_t)rr * ld + cc] = v;
           buf0[(size_t)cc * ld + rr] = v;
         }
+        OMC_TICK(1)
         if (warmQ) {
 #if OMC_USE_TMA
           mbar_wait(mbar, mbar_phase);
@@ -570,8 +586,10 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           }
           __syncthreads();
         }
-        jacobi_sym(buf0, buf1, NP, ld, P.o.jacobi_tol, 40, jcs, jsn, jrot, red);
+        OMC_TICK(2)
+        nsweeps += jacobi_sym(buf0, buf1, NP, ld, jtol, 40, jcs, jsn, jrot, red);
         have_basis[b] = true;
+        OMC_TICK(3)
         // eigenvalues, the smaller spectral side, compacted index list (warp 0)
         for (int i = tid; i < NP; i += NT) lam[i] = buf0[(size_t)i * ld + i];
         __syncthreads();
@@ -662,11 +680,14 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         if (tid == 0) bulk_wait_all();
 #endif
         __syncthreads();
+        OMC_TICK(4)
       }
 
       // ------------------------------------------------ phase 4: residuals / termination / rho
       if (it % P.o.check_every == 0 || it == P.o.max_iter) {
+        tk = clock64();
         double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0, sxx = 0.0, sfit = 0.0;
+        double rpc[7] = {0, 0, 0, 0, 0, 0, 0};  // components: psd1, psd2, psd3, trace, box, v rows, aggregated rows
         // PSD rows
         for (int b = 0; b < 3; ++b) {
           const int N = gb[b].N;
@@ -675,7 +696,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
             const int rr = e / N, cc = e - rr * N;
             if (cc > rr) continue;
             const double s_ = sB[e];
-            rp = fmax(rp, fabs(w_entry(c, b, rr, cc) - s_));
+            rpc[b] = fmax(rpc[b], fabs(w_entry(c, b, rr, cc) - s_));
             np_ = fmax(np_, fabs(s_));
           }
         }
@@ -713,7 +734,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           for (int l = 0; l < L; ++l) gU -= cxp[l][i] * (c.mv[l * k + j] + c.mg[l] * cal[l * k + j]);
           rd = fmax(rd, fabs(gU));
           nd_ = fmax(nd_, fabs(gU));
-          rp = fmax(rp, fabs(c.U[e] - c.s5[e]));
+          rpc[4] = fmax(rpc[4], fabs(c.U[e] - c.s5[e]));
           np_ = fmax(np_, fabs(c.s5[e]));
           const double lo5 = (i >= n - k + j) ? 0.0 : -c.sa;
           const double m5 = c.m5[e];
@@ -721,33 +742,41 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         }
         // dense rows with the relaxed w: R [Y; U] needs a reduction -> reuse dense_rows_apply on (Y, U)
         __syncthreads();
-        {
-          NodeCtx cwv = c;
-          cwv.Yt = c.Y;
-          cwv.Ut = c.U;
-          dense_rows_apply(cwv, rhs, red);  // rhs = R w
-        }
+        dense_rows_apply(c, c.Y, c.U, rhs, red);  // rhs = R w
         double dual_rows = 0.0;
+#ifdef OMC_DEBUG_PRINT
+        if (tid == 0 && L > 0 && it <= 3) {
+          double xu = 0.0;
+          for (int i = 0; i < n; ++i) xu += cxp[0][i] * c.U[i];
+          printf("[dbg] it %d L %d cL %d rhs %g %g %g  xU_serial %g sv %g sg %g cbe %g nw %d\n", it, L, c.L, rhs[0], rhs[1], rhs[2], xu,
+                 c.sv[0], c.sg[0], cbe[0], (int)(blockDim.x >> 5));
+        }
+#endif
         if (tid == 0) {
-          rp = fmax(rp, fabs((c.ktr - rhs[0]) - c.scal[0]));
+          rpc[3] = fabs((c.ktr - rhs[0]) - c.scal[0]);
           np_ = fmax(np_, fmax(fabs(c.scal[0]), fmax(c.ktr, c.a)));
           nd_ = fmax(nd_, c.cT);
           dual_rows += c.ktr * c.scal[1];
         }
         for (int e = tid; e < L * k; e += NT) {
-          rp = fmax(rp, fabs(-rhs[1 + e] - c.sv[e]));
+          rpc[5] = fmax(rpc[5], fabs(-rhs[1 + e] - c.sv[e]));
           np_ = fmax(np_, fabs(c.sv[e]));
           const double mv_ = c.mv[e];
           dual_rows -= (mv_ < 0.0) ? mv_ * clb[e] : mv_ * cub[e];
         }
         for (int l = tid; l < L; l += NT) {
-          rp = fmax(rp, fabs((cbe[l] - rhs[1 + L * k + l]) - c.sg[l]));
+          rpc[6] = fmax(rpc[6], fabs((cbe[l] - rhs[1 + L * k + l]) - c.sg[l]));
           np_ = fmax(np_, fmax(fabs(c.sg[l]), fabs(cbe[l])));
           dual_rows += cbe[l] * c.mg[l];
         }
         for (int i = tid; i < k; i += NT) dual_rows += c.m2[(size_t)(n + i) * SL.N2 + (n + i)];
         for (int i = tid; i < n; i += NT) dual_rows += c.a * c.m3[(size_t)i * n + i];
-        rp = block_max(rp, red);
+        for (int q = 0; q < 7; ++q) {
+          rpc[q] = block_max(rpc[q], red);
+          rp = fmax(rp, rpc[q]);
+        }
+        if (P.prof && tid == 0)
+          for (int q = 0; q < 7; ++q) P.prof[(size_t)node * 16 + 8 + q] = rpc[q];
         rd = block_max(rd, red);
         np_ = block_max(np_, red);
         nd_ = block_max(nd_, red);
@@ -787,6 +816,10 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           }
         }
         if (stop) break;
+        {
+          const double rel = fmax(rp / fmax(np_, 1.0), rd / fmax(nd_, 1.0));
+          jtol = fmin(P.o.jacobi_tol, fmax(1e-13, 1e-2 * rel));
+        }
         if (P.o.adapt_every > 0 && it % P.o.adapt_every == 0) {
           const double ratio = sqrt((rp / fmax(np_, 1e-12)) / fmax(rd / fmax(nd_, 1e-12), 1e-30));
           if (ratio > 5.0 || ratio < 0.2) {
@@ -797,6 +830,12 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
       }
     }
     if (it > P.o.max_iter) it = P.o.max_iter;
+    OMC_TICK(5)
+    if (P.prof && tid == 0) {
+      for (int q = 0; q < 6; ++q) P.prof[(size_t)node * 16 + q] = (double)pc[q];
+      P.prof[(size_t)node * 16 + 6] = (double)nsweeps;
+      P.prof[(size_t)node * 16 + 7] = (double)it;
+    }
 
     // ---------------------------------------------------------------- outputs (original units)
     if (tid == 0) {
@@ -848,7 +887,7 @@ inline size_t relax_smem_bytes(int n, int m, int k, int Lcap, int rmax) {
   d += (size_t)Lcap;                     // cxp (pointers, 8 bytes)
   d += 1;                                // mbar
   size_t bytes = d * 8;
-  bytes += sizeof(int) * ((size_t)g1.NP / 2 + g1.NP + 8);
+  bytes += sizeof(int) * (3 * ((size_t)g1.NP / 2) + g1.NP + 8);
   return (bytes + 127) & ~(size_t)127;
 }
 

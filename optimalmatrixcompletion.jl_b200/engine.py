@@ -217,6 +217,12 @@ class Frontier:
             out.append(r)
         return out
 
+    def profile(self) -> np.ndarray:
+        """(B, 16): SM cycles per phase (w-update, build V, DMMA pre-rotation, Jacobi, reconstruction, residuals), sweeps, iterations."""
+        prof = np.zeros((self.B, 16))
+        check(self.p.lib.omc_frontier_fetch_profile(self.handle, _ptr(prof, C.c_double)))
+        return prof
+
     def close(self):
         if self.handle:
             self.p.lib.omc_frontier_destroy(self.handle)
@@ -275,6 +281,25 @@ def matrix_completion_master_feasible(Y, U, X=None, Theta=None, use_disjunctive_
     if not use_disjunctive_cuts:
         raise NotImplementedError("McCormick path is out of scope (SURVEY.md section 2)")
     return bool(smallest_eigvecs_batch(Y, U, 1)[3][0])
+
+
+def alternating_minimization(problem: Problem, U_initial: np.ndarray, disjunctive_cuts: Optional[List[Cut]] = None,
+                             eps: float = 1e-5, max_iters: int = 100, time_limit: float = 3600.0):
+    """OMC.jl:1979-2279 (disjunctive path); returns the reference's result dict (OMC.jl:2249-2278)."""
+    cuts = disjunctive_cuts or []
+    if U_initial.shape != (problem.n, problem.k):
+        raise ValueError("U_initial must have size (n, k)")
+    Ui = np.asfortranarray(U_initial, dtype=np.float64)
+    lab = LABELS[problem.cut_type]
+    ids = np.asarray([c.cut_id for c in cuts] or [0], np.int32)
+    dirs = np.asarray([lab.index(d) for c in cuts for d in c.directions] or [0], np.uint8)
+    U = np.zeros((problem.k, problem.n)); V = np.zeros((problem.m, problem.k)); obj = np.zeros(max_iters)
+    conv = C.c_int32(); nit = C.c_int32(); st = C.c_double()
+    check(problem.lib.omc_altmin(problem.handle, _ptr(Ui, C.c_double), len(cuts), _ptr(ids, C.c_int32), _ptr(dirs, C.c_uint8),
+                                 float(eps), int(max_iters), float(time_limit), _ptr(U, C.c_double), _ptr(V, C.c_double),
+                                 C.byref(conv), C.byref(nit), _ptr(obj, C.c_double), C.byref(st)))
+    return {"converged": bool(conv.value), "U": U.T.copy(), "V": V.T.copy(), "solve_time": st.value,
+            "n_iters": nit.value, "max_iters": max_iters, "objectives": [float(v) for v in obj[: nit.value]]}
 
 
 def psd_project_batch(V: np.ndarray):

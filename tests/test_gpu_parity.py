@@ -1,0 +1,191 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle, the committed golden
+vectors and size-independent properties.  Bit-exact for integer work; 1e-6 relative on relaxation bounds
+(north_star), 1e-13 relative on objective/MSE reductions (summation order differs)."""
+import numpy as np
+import pytest
+
+from conftest import golden_instance
+
+pytestmark = pytest.mark.gpu
+REL_BOUND = 1e-6
+
+
+@pytest.fixture(scope="module")
+def omc():
+    import omc_b200
+    omc_b200.init(0)
+    return omc_b200
+
+
+def _cuts_for(omc, p, cuts):
+    return [omc.Cut(p.add_cut(x, U), x, U, d) for x, U, d in cuts]
+
+
+def test_eigensolver_psd_projection(omc):
+    rng = np.random.default_rng(0)
+    for N, B in [(1, 2), (2, 3), (11, 4), (20, 8), (51, 8), (64, 4), (100, 16), (104, 2)]:
+        V = rng.standard_normal((B, N, N)); V = V + np.transpose(V, (0, 2, 1))
+        V[0] = 0.0                                          # zero matrix
+        if B > 1:
+            V[1] = np.diag(rng.standard_normal(N))          # already diagonal
+        P, lam, sw, _ = omc.psd_project_batch(V)
+        for b in range(B):
+            l, Q = np.linalg.eigh(V[b])
+            assert np.abs(P[b] - (Q * np.maximum(l, 0)) @ Q.T).max() <= 1e-12 * max(1.0, np.abs(V[b]).max())
+            assert np.abs(np.sort(lam[b]) - l).max() <= 1e-12 * max(1.0, np.abs(l).max())
+    # idempotence and clustered spectra
+    B, N = 4, 60
+    Q, _ = np.linalg.qr(rng.standard_normal((N, N)))
+    lam0 = np.concatenate([np.full(20, 3.0), np.full(20, -2.0), np.zeros(10), rng.standard_normal(10) * 1e-9])
+    V = np.stack([(Q * lam0) @ Q.T] * B)
+    P, _, _, _ = omc.psd_project_batch(V)
+    P2, _, _, _ = omc.psd_project_batch(P)
+    assert np.abs(P2 - P).max() <= 1e-12 and np.abs(P[0] - (Q * np.maximum(lam0, 0)) @ Q.T).max() <= 1e-12
+
+
+def test_mask_compaction_bit_exact(omc):
+    from oracle import mask as M
+    rng = np.random.default_rng(1)
+    for n, m, dens in [(1, 1, 1.0), (3, 70, 0.3), (10, 10, 0.5), (13, 29, 0.1), (50, 50, 0.5), (64, 64, 0.9), (40, 97, 0.0)]:
+        mask = rng.random((n, m)) < dens
+        p = omc.Problem(1, rng.standard_normal((n, m)), mask, 80.0)
+        rp, ci, cp, ri = p.csr()
+        orp, oci = M.mask_to_csr(mask); ocp, ori = M.mask_to_csc(mask)
+        assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(cp, ocp) and np.array_equal(ri, ori)
+        p.close()
+
+
+def test_objective_mse_fused_reduction(omc):
+    from oracle import objective as O
+    rng = np.random.default_rng(2)
+    for n, m, dens in [(1, 1, 1.0), (10, 10, 0.5), (50, 50, 0.5), (33, 77, 0.2), (20, 20, 1.0), (20, 20, 0.0), (1000, 1000, 0.2)]:
+        A = rng.standard_normal((n, m)); X = rng.standard_normal((n, m)); mask = rng.random((n, m)) < dens
+        p = omc.Problem(1, A, mask, 80.0)
+        got = p.objective_mse(X)
+        want = (O.evaluate_objective(X, A, mask, X[:, :1], 80.0), O.compute_MSE(X, A, mask, "in"),
+                O.compute_MSE(X, A, mask, "out"), O.compute_MSE(X, A, mask, "all"))
+        for g, w in zip(got, want):
+            assert abs(g - w) <= 1e-13 * max(1.0, abs(w))
+        assert omc.evaluate_objective(p, X) == got[0] and omc.compute_MSE(p, X, "in") == got[1]
+        with pytest.raises(ValueError):
+            omc.compute_MSE(p, X, "bogus")
+        p.close()
+
+
+def test_relaxation_matches_golden_vectors(omc, golden):
+    for case in golden:
+        A, mask, cuts = golden_instance(case)
+        p = omc.Problem(case["k"], A, mask, case["gamma"], case["cut_type"])
+        r = omc.matrix_completion_SDP_relaxation(p, _cuts_for(omc, p, cuts), omc.default_opts(eps_abs=1e-9, eps_rel=1e-9, max_iter=200000))
+        assert r["termination_status"] == "OPTIMAL" and r["feasible"], case["name"]
+        assert abs(r["objective"] - case["objective"]) <= REL_BOUND * abs(case["objective"]), (case["name"], r["objective"], case["objective"])
+        assert r["lower_bound"] <= case["objective"] * (1 + 1e-6) + 1e-9      # certified bound never above the optimum
+        # returned point is primal feasible for the reference's program (OMC.jl:1554-1561)
+        n, k = case["n"], case["k"]
+        X, Y, U = r["X"], r["Y"], r["U"]
+        assert np.abs(Y - Y.T).max() <= 1e-12
+        assert np.linalg.eigvalsh(np.eye(n) - Y).min() >= -1e-6 and np.trace(Y) <= k + 1e-6
+        assert np.linalg.eigvalsh(np.block([[Y, U], [U.T, np.eye(k)]])).min() >= -1e-6
+        assert np.sqrt((U * U).sum(axis=0)).max() <= 1 + 1e-6                  # OMC.jl:1831-1835 holds although not imposed
+        p.close()
+
+
+def test_relaxation_matches_oracle_iterate_for_iterate(omc):
+    """Same algorithm, same iteration count: the GPU trajectory equals the oracle's to rounding."""
+    from oracle import relaxation as R
+    from oracle.datagen import config_instance
+    from oracle.cuts import child_directions
+    k, A, mask, g = config_instance("C1", 0)
+    p = omc.Problem(k, A, mask, g, "linear")
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(10); x /= np.linalg.norm(x); Uh = 0.3 * rng.standard_normal((10, 1))
+    cid = p.add_cut(x, Uh)
+    for dirs in (["left"], ["right"]):
+        for mi in (1, 7, 60):
+            r = p.relax_batch([[omc.Cut(cid, x, Uh, dirs)]], omc.default_opts(eps_abs=1e-30, eps_rel=1e-30, max_iter=mi, adapt_every=0, jacobi_tol=1e-13))[0]
+            ro = R.solve_relaxation(A, mask, g, k, "linear", [(x, Uh, dirs)], opts=R.Options(eps_abs=1e-30, eps_rel=1e-30, max_iter=mi, adaptive_rho=False))
+            assert np.abs(r["X"] - ro["X"]).max() < 1e-9 and np.abs(r["Y"] - ro["Y"]).max() < 1e-9 and np.abs(r["U"] - ro["U"]).max() < 1e-9
+            assert abs(r["res_p"] - ro["res_p"]) <= 1e-7 * max(1.0, ro["res_p"]) and abs(r["res_d"] - ro["res_d"]) <= 1e-7 * max(1.0, ro["res_d"])
+    p.close()
+
+
+def test_relaxation_batch_c2_against_oracle_and_properties(omc):
+    """BASELINE config 2 (k=1, 50x50): root + both children, compared with the oracle at full size, and the
+    domain properties child bound >= parent bound, x -> -x symmetry, batch == singles, warm == cold."""
+    from oracle import relaxation as R
+    from oracle.datagen import config_instance
+    k, A, mask, g = config_instance("C2", 0)
+    p = omc.Problem(k, A, mask, g, "linear", state_pool_capacity=4)
+    opts = omc.default_opts()
+    root = p.relax_batch([[]], opts, save_ids=[0])[0]
+    ro = R.solve_relaxation(A, mask, g, k, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8))
+    assert abs(root["objective"] - ro["objective"]) <= REL_BOUND * ro["objective"]
+    lam, vec, bp, feas = omc.smallest_eigvecs_batch(root["Y"], root["U"], 1)
+    assert not feas[0] and lam[0, 0] < -0.5
+    x = bp[0]
+    c = p.add_cut(x, root["U"]); cneg = p.add_cut(-x, root["U"])
+    kids = [[omc.Cut(c, x, root["U"], ["left"])], [omc.Cut(c, x, root["U"], ["right"])]]
+    batch = p.relax_batch(kids, opts)
+    singles = [p.relax_batch([kid], opts)[0] for kid in kids]
+    warm = p.relax_batch(kids, opts, warm_ids=[0, 0])
+    flipped = p.relax_batch([[omc.Cut(cneg, -x, root["U"], ["right"])], [omc.Cut(cneg, -x, root["U"], ["left"])]], opts)
+    for b in range(2):
+        assert batch[b]["termination_status"] == "OPTIMAL"
+        assert batch[b]["objective"] >= root["objective"] * (1 - 1e-6)
+        assert batch[b]["objective"] == singles[b]["objective"]                       # deterministic
+        assert abs(batch[b]["objective"] - warm[b]["objective"]) <= REL_BOUND * batch[b]["objective"]
+        assert abs(batch[b]["objective"] - flipped[b]["objective"]) <= REL_BOUND * batch[b]["objective"]
+    oc = R.solve_relaxation(A, mask, g, k, "linear", [(x, root["U"], ["right"])], opts=R.Options(eps_abs=1e-8, eps_rel=1e-8))
+    assert abs(batch[1]["objective"] - oc["objective"]) <= REL_BOUND * oc["objective"]
+    # any feasible rank-k point bounds the relaxation from above
+    u, s, vt = np.linalg.svd(np.where(mask, A, 0.0)); Xr = (u[:, :k] * s[:k]) @ vt[:k]
+    assert root["objective"] <= p.objective_mse(Xr)[0]
+    p.close()
+
+
+def test_cutoff_prunes_dominated_node_early(omc):
+    from oracle.datagen import config_instance
+    k, A, mask, g = config_instance("C1", 0)
+    p = omc.Problem(k, A, mask, g, "linear")
+    root = p.relax_batch([[]])[0]
+    x = omc.smallest_eigvecs_batch(root["Y"], root["U"], 1)[2][0]
+    c = p.add_cut(x, root["U"])
+    kid = [[omc.Cut(c, x, root["U"], ["left"])]]
+    full = p.relax_batch(kid)[0]
+    assert full["objective"] > root["objective"] * 1.05
+    cut = p.relax_batch(kid, omc.default_opts(cutoff=root["objective"] * 1.01))[0]
+    assert cut["status_code"] == 4 and cut["termination_status"] == "OPTIMAL"
+    assert cut["objective"] > root["objective"] * 1.01 and cut["objective"] <= full["objective"] * (1 + 1e-6)
+    assert cut["iters"] <= full["iters"]
+    p.close()
+
+
+def test_separation_oracle_matches_dense_eigh(omc):
+    from oracle import eigsep as E
+    rng = np.random.default_rng(7)
+    for n, k in [(10, 1), (30, 2), (50, 1), (100, 3)]:
+        B = 5
+        Y = np.stack([(lambda M: M @ M.T / n)(rng.standard_normal((n, n))) for _ in range(B)])
+        U = rng.standard_normal((B, n, k)) / np.sqrt(n)
+        Y[0] = U[0] @ U[0].T + 1e-9 * np.eye(n)               # master-feasible node
+        for nev in (1, 2):
+            lam, vec, bp, feas = omc.smallest_eigvecs_batch(Y, U, nev)
+            for b in range(B):
+                lo, vo = E.smallest_eigpairs(Y[b], U[b], nev)
+                assert np.abs(lam[b] - lo).max() <= 1e-10
+                assert feas[b] == E.master_feasible(Y[b], U[b])
+                if b > 0:
+                    xo, _ = E.breakpoint_vector(Y[b], U[b], "smallest_1_eigvec" if nev == 1 else "smallest_2_eigvec")
+                    assert np.abs(bp[b] - xo).max() <= 1e-8
+                    assert abs(np.linalg.norm(vec[b, :, 0]) - 1) < 1e-12
+
+
+def test_argument_validation_mirrors_reference_errors(omc):
+    rng = np.random.default_rng(8)
+    A = rng.standard_normal((6, 5)); mask = rng.random((6, 5)) < 0.5
+    with pytest.raises(Exception, match="n <= m"):
+        omc.Problem(1, A, mask, 80.0)                         # OMC.jl:249-254
+    with pytest.raises(ValueError, match="Disjunctive cuts type"):
+        omc.Problem(1, A.T, mask.T, 80.0, "linear4")          # OMC.jl:218-224
+    with pytest.raises(ValueError, match="Dimension mismatch"):
+        omc.Problem(1, A.T, mask, 80.0)                       # OMC.jl:240-246

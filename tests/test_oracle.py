@@ -1,0 +1,207 @@
+"""CPU tests: the oracle against analytic known answers, an independent second algorithm, KKT
+certificates and brute-force restatements (the reference ships no golden vectors)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from conftest import golden_instance
+from oracle import cuts as C
+from oracle import eigsep as E
+from oracle import kat
+from oracle import mask as M
+from oracle import objective as O
+from oracle import relaxation as R
+from oracle import shor as S
+from oracle.datagen import config_instance, generate_matrix_completion_data
+
+REL = 1e-6  # north_star: ~1e-6 relative on bounds at matched solver tolerance
+
+
+def test_datagen_mask_has_exact_count_and_full_support():
+    for seed in range(3):
+        A, mask = generate_matrix_completion_data(1, 10, 10, 50, seed)
+        assert mask.sum() == 50 and mask.any(axis=0).all() and mask.any(axis=1).all()
+        assert A.shape == (10, 10)
+    with pytest.raises(ValueError):
+        generate_matrix_completion_data(1, 12, 10, 50, 0)   # n <= m, utils.jl:80-85
+
+
+def test_objective_and_mse_against_loops():
+    rng = np.random.default_rng(0)
+    n, m, g = 7, 9, 80.0
+    A = rng.standard_normal((n, m)); X = rng.standard_normal((n, m)); mask = rng.random((n, m)) < 0.5
+    obj = sum(0.5 * (X[i, j] - A[i, j]) ** 2 for i in range(n) for j in range(m) if mask[i, j]) + (X ** 2).sum() / (2 * g)
+    assert abs(O.evaluate_objective(X, A, mask, X[:, :2], g) - obj) <= 1e-13 * abs(obj)
+    se = (X - A) ** 2
+    assert abs(O.compute_MSE(X, A, mask, "in") - se[mask].mean()) < 1e-13
+    assert abs(O.compute_MSE(X, A, mask, "out") - se[~mask].mean()) < 1e-13
+    assert abs(O.compute_MSE(X, A, mask, "all") - se.mean()) < 1e-13
+    # empty denominators return 0.0 (OMC.jl:2381-2382, 2390-2391)
+    assert O.compute_MSE(X, A, np.ones_like(mask), "out") == 0.0
+    assert O.compute_MSE(X, A, np.zeros_like(mask), "in") == 0.0
+    with pytest.raises(ValueError):
+        O.compute_MSE(X, A, mask, "bogus")
+    T = rng.standard_normal((m, m))
+    rel = O.compute_SDP_relaxation_objective(X, None, T, None, A, mask, g)
+    assert abs(rel - (0.5 * ((A - X)[mask] ** 2).sum() + np.trace(T) / (2 * g))) < 1e-12
+
+
+def test_bitmatrix_chunks_and_compaction_bit_exact():
+    rng = np.random.default_rng(1)
+    for n, m in [(1, 1), (3, 70), (10, 10), (13, 29), (64, 64)]:
+        mask = rng.random((n, m)) < 0.4
+        ch = M.bitmatrix_chunks(mask)
+        assert ch.dtype == np.uint64 and ch.size == (n * m + 63) // 64
+        for i, j in itertools.product(range(n), range(m)):
+            b = i + n * j
+            assert bool((int(ch[b >> 6]) >> (b & 63)) & 1) == bool(mask[i, j])
+        assert np.array_equal(M.chunks_to_mask(ch, n, m), mask)
+        rp, ci = M.mask_to_csr(mask); cp, ri = M.mask_to_csc(mask)
+        assert rp[-1] == cp[-1] == mask.sum()
+        for i in range(n):
+            assert list(ci[rp[i]:rp[i + 1]]) == [j for j in range(m) if mask[i, j]]
+        for j in range(m):
+            assert list(ri[cp[j]:cp[j + 1]]) == [i for i in range(n) if mask[i, j]]
+
+
+def test_cut_table_matches_reference_rows():
+    """SURVEY appendix B / OMC.jl:1581-1676: every alpha v + beta is the secant of v^2 on [lb, ub],
+    except linear3/right which reproduces the reference's expression |vhat| v (quirk Q1)."""
+    for h in (-0.7, -0.2, 0.0, 0.35, 0.9):
+        for t in C.LABELS:
+            for d in C.LABELS[t]:
+                lb, ub, al, be = C.cut_row(t, d, h)
+                assert -1.0 <= lb <= ub <= 1.0
+                if t == "linear2" and d == "middle":
+                    assert al == 0.0 and be == h * h       # constant vhat^2, OMC.jl:1623
+                    continue
+                if t == "linear3" and d == "right":
+                    assert (al, be) == (abs(h), 0.0)        # OMC.jl:1675
+                    lb2, ub2, al2, be2 = C.cut_row(t, d, h, fix_linear3_right=True)
+                    assert abs(al2 * lb2 + be2 - lb2 ** 2) < 1e-15 and abs(al2 * ub2 + be2 - ub2 ** 2) < 1e-15
+                    continue
+                assert abs(al * lb + be - lb * lb) < 1e-15 and abs(al * ub + be - ub * ub) < 1e-15
+
+
+def test_child_enumeration_order_first_factor_fastest():
+    """OMC.jl:2481-2491 + 2524: ind = 1 + sum_j code(dir_j) P^(j-1)."""
+    for t, k in [("linear", 1), ("linear", 3), ("linear2", 2), ("linear3", 2)]:
+        lab = C.LABELS[t]; P = len(lab)
+        ch = C.child_directions(t, k)
+        assert len(ch) == P ** k
+        for ind, dirs in ch:
+            assert ind == 1 + sum(lab.index(d) * P ** j for j, d in enumerate(dirs))
+    assert C.child_directions("linear", 2) == [(1, ["left", "left"]), (2, ["right", "left"]),
+                                               (3, ["left", "right"]), (4, ["right", "right"])]
+
+
+def test_shor_indexes_against_brute_force_and_order():
+    rng = np.random.default_rng(2)
+    ind = rng.random((6, 7)) < 0.5
+    for p in range(5):
+        got = S.shor_constraint_indexes(ind, [p])
+        assert len(got) == len(set(got)) and set(got) == S.shor_brute_force(ind, p)
+        assert all(t[0] < t[1] and t[2] < t[3] for t in got)
+    # the list follows the ORDER of num_entries_present_list (OMC.jl:2554)
+    a = S.shor_constraint_indexes(ind, [4, 1]); b = S.shor_constraint_indexes(ind, [1, 4])
+    n4 = len(S.shor_constraint_indexes(ind, [4]))
+    assert a[:n4] == b[-n4:] and a[n4:] == b[:-n4]
+
+
+def test_root_bound_closed_form_fully_observed():
+    """KAT-root-full: closed-form water-filling value vs the ADMM oracle."""
+    rng = np.random.default_rng(3)
+    for (n, m, k) in [(6, 6, 1), (5, 8, 2), (10, 10, 1)]:
+        A = rng.standard_normal((n, m))
+        full = np.ones((n, m), bool)
+        r = R.solve_relaxation(A, full, 80.0, k, opts=R.Options(eps_abs=1e-9, eps_rel=1e-9, max_iter=100000))
+        want = kat.root_bound_full(A, 80.0, k)
+        assert r["status"] == R.STATUS_OPTIMAL
+        assert abs(r["objective"] - want) <= REL * want
+
+
+def test_rank_k_optimum_pins_evaluate_objective():
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((7, 9)); full = np.ones_like(A, bool)
+    for k in (1, 2, 3):
+        X, obj = kat.rank_k_optimum_full(A, 80.0, k)
+        assert abs(O.evaluate_objective(X, A, full, X[:, :k], 80.0) - obj) <= 1e-12 * obj
+        assert kat.root_bound_full(A, 80.0, k) <= obj + 1e-12    # relaxation bound <= rank-k optimum
+
+
+def test_root_bound_independent_projected_gradient():
+    """Second algorithm (no cones, no ADMM) on PARTIALLY observed roots."""
+    k, A, mask, g = config_instance("C1", 0)
+    v, _ = kat.root_bound_projected_gradient(A, mask, g, k)
+    r = R.solve_relaxation(A, mask, g, k, opts=R.Options(eps_abs=1e-9, eps_rel=1e-9))
+    assert abs(r["objective"] - v) <= REL * v
+    rng = np.random.default_rng(5)
+    A2 = rng.standard_normal((6, 8)); m2 = rng.random((6, 8)) < 0.6; m2[0, :] = True; m2[:, 0] = True
+    for kk in (1, 2):
+        v, _ = kat.root_bound_projected_gradient(A2, m2, 80.0, kk)
+        r = R.solve_relaxation(A2, m2, 80.0, kk, opts=R.Options(eps_abs=1e-9, eps_rel=1e-9))
+        assert abs(r["objective"] - v) <= REL * v
+
+
+def test_golden_cases_reproduce_and_are_kkt_certified(golden):
+    """The committed golden vectors are regenerated by the oracle and carry an optimality certificate:
+    primal feasible, dual feasible, zero gap -- independent of the algorithm that produced them."""
+    for case in golden[:8]:
+        A, mask, cuts = golden_instance(case)
+        r = R.solve_relaxation(A, mask, case["gamma"], case["k"], case["cut_type"], cuts,
+                               opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=100000))
+        assert r["status"] == R.STATUS_OPTIMAL
+        assert abs(r["objective"] - case["objective"]) <= REL * abs(case["objective"]), case["name"]
+        cert = R.certificate(r, A, mask, case["gamma"], case["k"])
+        for key, v in cert.items():
+            if key.startswith("primal_") and key != "primal_sym":
+                assert v >= -5e-6, (case["name"], key, v)
+        assert cert["dual_cone"] <= 1e-9 and cert["stationarity"] <= 1e-5
+        assert abs(cert["gap"]) <= 1e-4 * max(1.0, abs(case["objective"]))
+        assert cert["colnorm_minus_1"] <= 1e-6          # the dropped ||U_j|| <= 1 rows hold (OMC.jl:1831-1835)
+    for case in golden:
+        c = case["certificate"]
+        assert abs(c["gap"]) <= 1e-5 * max(1.0, abs(case["objective"])) and c["stationarity"] <= 1e-6
+
+
+def test_children_bounds_dominate_parent_and_warm_start_agrees():
+    k, A, mask, g = config_instance("C1", 0)
+    o = R.Options(eps_abs=1e-8, eps_rel=1e-8)
+    root = R.solve_relaxation(A, mask, g, k, opts=o)
+    x, lam = E.breakpoint_vector(root["Y"], root["U"])
+    assert lam[0] < -1e-6 and not E.master_feasible(root["Y"], root["U"])
+    for _, dirs in C.child_directions("linear", k):
+        cold = R.solve_relaxation(A, mask, g, k, "linear", [(x, root["U"], dirs)], opts=o)
+        warm = R.solve_relaxation(A, mask, g, k, "linear", [(x, root["U"], dirs)], opts=o, state=root["state"])
+        assert cold["objective"] >= root["objective"] - 1e-6
+        assert abs(cold["objective"] - warm["objective"]) <= REL * cold["objective"]
+
+
+def test_bound_invariant_to_sign_flip_with_directions_swapped():
+    """x -> -x with left <-> right describes the same child."""
+    k, A, mask, g = config_instance("C1", 1)
+    o = R.Options(eps_abs=1e-8, eps_rel=1e-8)
+    root = R.solve_relaxation(A, mask, g, k, opts=o)
+    x, _ = E.breakpoint_vector(root["Y"], root["U"])
+    rng = np.random.default_rng(0)
+    Uh = 0.3 * rng.standard_normal(root["U"].shape)
+    a = R.solve_relaxation(A, mask, g, k, "linear", [(x, Uh, ["left"])], opts=o)
+    b = R.solve_relaxation(A, mask, g, k, "linear", [(-x, Uh, ["right"])], opts=o)
+    assert abs(a["objective"] - b["objective"]) <= REL * a["objective"]
+
+
+def test_separation_oracle_dense_matches_arpack():
+    rng = np.random.default_rng(6)
+    n, k = 30, 2
+    U = rng.standard_normal((n, k)) / 6; B = rng.standard_normal((n, n)); Y = B @ B.T / n
+    for nev in (1, 2):
+        ld, vd = E.smallest_eigpairs(Y, U, nev, "dense")
+        la, va = E.smallest_eigpairs(Y, U, nev, "arpack")
+        assert np.allclose(ld, la, atol=1e-6)
+        for q in range(nev):
+            assert abs(abs(vd[:, q] @ va[:, q]) - 1) < 1e-4
+            assert vd[np.argmax(np.abs(vd[:, q])), q] > 0          # sign rule
+    x2, lam = E.breakpoint_vector(Y, U, "smallest_2_eigvec")
+    w = np.abs(lam[:2]) / np.linalg.norm(lam[:2])
+    assert lam[1] < -1e-10 and np.allclose(x2, w[0] * vd[:, 0] + w[1] * vd[:, 1])   # OMC.jl:2471-2473
