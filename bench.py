@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- nodes relaxed / second of the B200 bounding engine on BASELINE.json config 2.
+
+Workload ("config.workload"): k = 1, 50 x 50 noisy Gaussian low-rank data, 1250 observed entries, gamma = 80,
+linear cuts, smallest_1_eigvec breakpoints (README quick-start shape).  A *step* is one pass of the hot path --
+the fused per-node relaxation kernel (replaces matrix_completion_SDP_relaxation, OMC.jl:1431-1943) -- over one
+frontier batch of open branch-and-bound nodes, every node relaxed from a cold start to eps = 1e-8.
+The frontier is built once, untimed, by best-first disjunctive expansion from the root with the incumbent
+withheld (the config-2 instances certify optimality within 3 nodes, so a real run never holds a wide frontier).
+
+  value     nodes/s with the batch resident in HBM (CUDA events on the library's launch stream)
+  e2e       same through omc_relax_batch with pinned HOST buffers (descriptor H2D + result D2H inside the timing)
+  roofline  FP64: algorithmic flops of the PSD projections / kernel time against the measured DMMA peak
+  cpu_baseline / --impl reference: the CPU oracle (NumPy restatement of the same program; Mosek/Julia are not
+            installable here) on a bounded sample of the same kind of frontier.
+
+N > 1 (torchrun): the frontier of N*B nodes is sharded block-cyclically, one process per GPU, no data-path
+collective; the tiny [incumbent, min lower bound] all-reduce-min after each step goes over NCCL.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C2: k=1, 50x50 noisy, 1250 observed, gamma=80, linear cuts, smallest_1_eigvec; frontier batch of open B&B nodes"
+EPS = 1e-8
+MAX_ITER = int(os.environ.get("OMC_BENCH_MAX_ITER", "5000"))
+
+
+def f_proj(N):
+    return 16.0 / 3.0 * N ** 3          # tridiagonalise + back-transform + reconstruct
+
+
+def node_iter_flops(n, m, k, L):
+    return f_proj(n + m) + f_proj(n + k) + f_proj(n) + 2.0 * L * (n * n + n * k)
+
+
+def c2_instance(seed=0):
+    from oracle.datagen import generate_matrix_completion_data  # data generator only (synthetic inputs)
+    return generate_matrix_completion_data(1, 50, 50, 1250, seed)
+
+
+# -------------------------------------------------------------------------------------------------
+# clocks sampler
+# -------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons}
+
+
+# -------------------------------------------------------------------------------------------------
+# frontier construction (untimed setup)
+# -------------------------------------------------------------------------------------------------
+def build_frontier_gpu(problem, target, omc):
+    """Best-first expansion with the incumbent withheld: pop the 148 open nodes with the smallest bound, relax them
+    in one launch, branch on the separation oracle's eigenvector (master-feasible nodes are leaves)."""
+    from omc_b200.host import BBNode, JuliaPriorityQueue, create_matrix_cut_child_nodes
+    opts = omc.default_opts(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER)
+    nodes = {1: BBNode(node_id=1, parent_id=0, LB=-np.inf, depth=0)}
+    pq = JuliaPriorityQueue([(1, -np.inf)])
+    counter = 1
+    while len(nodes) < target and len(pq):
+        room = max(1, (target - len(nodes)))           # every split adds (children - 1) open nodes
+        batch = [nodes.pop(pq.dequeue_pair()[0]) for _ in range(min(148, len(pq), room))]
+        res = problem.relax_batch([nd.disjunctive_cuts for nd in batch], opts)
+        ok = [i for i, r in enumerate(res) if r["status_code"] == 0]
+        if not ok:
+            continue
+        lam, vec, bp, feas = omc.smallest_eigvecs_batch(np.stack([res[i]["Y"] for i in ok]), np.stack([res[i]["U"] for i in ok]), 1)
+        for q, i in enumerate(ok):
+            if feas[q] or batch[i].depth >= 60:
+                continue
+            kids = create_matrix_cut_child_nodes(problem, batch[i], bp[q], res[i]["U"], counter, res[i]["objective"])
+            counter += len(kids)
+            for kd in kids:
+                nodes[kd.node_id] = kd
+                pq.enqueue(kd.node_id, kd.LB)
+    out = sorted(nodes.values(), key=lambda nd: (nd.LB, nd.node_id))
+    return out[:target]
+
+
+def build_frontier_cpu(A, mask, gamma, k, target):
+    """Same expansion with the CPU oracle (reference arm / cpu_baseline sample); returns oracle cut lists."""
+    from oracle import relaxation as R
+    from oracle.eigsep import breakpoint_vector, master_feasible
+    from oracle.cuts import child_directions
+    o = R.Options(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER)
+    open_nodes = [(-np.inf, 1, [])]
+    counter = 1
+    while len(open_nodes) < target:
+        open_nodes.sort(key=lambda t: (t[0], t[1]))
+        lb, nid, cuts = open_nodes.pop(0)
+        r = R.solve_relaxation(A, mask, gamma, k, "linear", cuts, opts=o)
+        if r["status"] != 0 or master_feasible(r["Y"], r["U"]):
+            if not open_nodes:
+                break
+            continue
+        x, _ = breakpoint_vector(r["Y"], r["U"])
+        for ind, dirs in child_directions("linear", k):
+            open_nodes.append((r["objective"], counter + ind, cuts + [(x, r["U"].copy(), dirs)]))
+        counter += 2 ** k
+    open_nodes.sort(key=lambda t: (t[0], t[1]))
+    return [c for _, _, c in open_nodes[:target]]
+
+
+def _oracle_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    A, mask, gamma, k, cuts = args
+    from oracle import relaxation as R
+    r = R.solve_relaxation(A, mask, gamma, k, "linear", cuts, opts=R.Options(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER))
+    return r["iters"], r["status"]
+
+
+# -------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the CPU restatement of the path (oracle port) on all host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    A, mask = c2_instance(0)
+    sample = max(2, min(2 * cores, 32))
+    t0 = time.time()
+    cuts = build_frontier_cpu(A, mask, 80.0, 1, sample)
+    setup = time.time() - t0
+    jobs = [(A, mask, 80.0, 1, c) for c in cuts]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(processes=min(cores, len(jobs))) as pool:
+        for _ in range(args.warmup if args.warmup < 1 else 1):
+            pool.map(_oracle_worker, jobs[: min(cores, len(jobs))])
+        t0 = time.perf_counter()
+        iters = 0
+        for _ in range(args.steps):
+            res = pool.map(_oracle_worker, jobs)
+            iters += sum(r[0] for r in res)
+        dt = time.perf_counter() - t0
+    value = len(jobs) * args.steps / dt
+    line = {"impl": "reference", "metric": "nodes relaxed/sec", "value": value, "unit": "nodes/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "nodes_per_step": len(jobs), "eps": EPS, "max_iter": MAX_ITER,
+                       "note": "CPU restatement of the relaxation (NumPy/LAPACK ADMM), not Mosek: Julia and Mosek are absent"},
+            "cpu_baseline": {"value": value, "unit": "nodes/s", "cores": min(cores, len(jobs)), "kind": "port",
+                             "sample": f"{len(jobs)} frontier nodes x {args.steps} steps, {iters} ADMM iterations, frontier setup {setup:.1f}s untimed"},
+            "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import omc_b200
+    omc = omc_b200
+    omc.init(local)
+    lib = omc._lib.load()
+    peaks = omc.measure_fp64_peak()
+    A, mask = c2_instance(0)
+    n, m, k = 50, 50, 1
+    problem = omc.Problem(k, A, mask, 80.0, "linear")
+    B = args.nodes
+    t0 = time.time()
+    frontier_nodes = build_frontier_gpu(problem, B * world, omc)
+    mine = omc.shard_block_cyclic(frontier_nodes, rank, world)
+    setup_s = time.time() - t0
+    node_cuts = [nd.disjunctive_cuts for nd in mine]
+    Bl = len(node_cuts)
+    opts = omc.default_opts(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER)
+    fr = omc.Frontier(problem, node_cuts)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
+    red = torch.zeros(2, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        flush.fill_(1.0)                       # L2 flush between iterations
+        torch.cuda.synchronize()
+        ms = fr.relax(opts)                    # CUDA events on the library stream bracket the fused kernel
+        if world > 1:                          # the path's only exchange: all-reduce-min of [incumbent, min LB]
+            red[0] = 1e300; red[1] = 1e300
+            dist.all_reduce(red, op=dist.ReduceOp.MIN)
+        return ms
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    kernel_ms = [step() for _ in range(args.steps)]
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    out = fr.fetch(matrices=False)
+    iters = np.array([o["iters"] for o in out]); status = np.bincount([o["status_code"] for o in out], minlength=5)
+    Ls = np.array([len(c) for c in node_cuts])
+    flops_step = float(sum(it * node_iter_flops(n, m, k, L) for it, L in zip(iters, Ls)))
+    dev_ms = float(np.sum(kernel_ms)) / args.steps
+
+    # ---- e2e: host buffers through omc_relax_batch (pinned), H2D of descriptors + D2H of results inside the timing
+    ptr, ids, dirs = problem._flatten(node_cuts)
+    pin = lambda t: t.pin_memory()
+    h_ptr, h_ids, h_dirs = pin(torch.from_numpy(ptr.copy())), pin(torch.from_numpy(ids.copy())), pin(torch.from_numpy(dirs.copy()))
+    h_status = pin(torch.zeros(Bl, dtype=torch.int32)); h_iters = pin(torch.zeros(Bl, dtype=torch.int32))
+    h_obj = pin(torch.zeros(Bl, dtype=torch.float64)); h_lb = pin(torch.zeros(Bl, dtype=torch.float64)); h_res = pin(torch.zeros(2 * Bl, dtype=torch.float64))
+    h_X = pin(torch.zeros(Bl * n * m, dtype=torch.float64)); h_Y = pin(torch.zeros(Bl * n * n, dtype=torch.float64)); h_U = pin(torch.zeros(Bl * n * k, dtype=torch.float64))
+    P = lambda t, ty: C.cast(t.data_ptr(), C.POINTER(ty))
+    h2d = ptr.nbytes + ids.nbytes + dirs.nbytes
+    d2h = sum(t.numel() * t.element_size() for t in (h_status, h_iters, h_obj, h_lb, h_res, h_X, h_Y, h_U))
+
+    def e2e_step():
+        flush.fill_(1.0)
+        torch.cuda.synchronize()
+        rc = lib.omc_relax_batch(problem.handle, Bl, P(h_ptr, C.c_int32), P(h_ids, C.c_int32), P(h_dirs, C.c_uint8), None, None,
+                                 C.byref(opts), P(h_status, C.c_int32), P(h_obj, C.c_double), P(h_lb, C.c_double),
+                                 P(h_iters, C.c_int32), P(h_res, C.c_double), P(h_X, C.c_double), P(h_Y, C.c_double),
+                                 P(h_U, C.c_double), None, None)
+        omc._lib.check(rc)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_wall = (time.perf_counter() - t0) / e2e_steps
+
+    # ---- max over ranks
+    tmax = torch.tensor([dev_ms, wall / args.steps * 1e3, e2e_wall * 1e3], dtype=torch.float64, device="cuda")
+    tsum = torch.tensor([float(Bl), flops_step, float(iters.sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max, e2e_ms_max = [float(v) for v in tmax.tolist()]
+    total_nodes, total_flops, total_iters = [float(v) for v in tsum.tolist()]
+
+    if rank == 0:
+        # cpu_baseline: the oracle on one core, bounded sample of the same frontier (N = 1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            from oracle import relaxation as R
+            t0 = time.perf_counter(); done = 0; cit = 0
+            for nd in mine[:: max(1, len(mine) // 8)]:
+                cuts = [(c.x, c.Uhat, c.directions) for c in nd.disjunctive_cuts]
+                r = R.solve_relaxation(A, mask, 80.0, k, "linear", cuts, opts=R.Options(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER))
+                done += 1; cit += r["iters"]
+                if time.perf_counter() - t0 > 20.0:
+                    break
+            dt = time.perf_counter() - t0
+            cpu = {"value": done / dt, "unit": "nodes/s", "cores": 1, "kind": "port",
+                   "sample": f"{done} nodes of the same frontier (every {max(1, len(mine) // 8)}th), {cit} ADMM iterations, {dt:.1f} s; NumPy/LAPACK restatement, not Mosek"}
+        peak_tf = peaks["dmma_tflops"]
+        achieved_tf = (flops_step / (dev_ms * 1e-3)) * 1e-12          # this rank's kernel
+        line = {
+            "metric": "nodes relaxed/sec", "value": total_nodes / (dev_ms_max * 1e-3), "unit": "nodes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "nodes_per_gpu": Bl, "nodes_total": int(total_nodes), "eps": EPS, "max_iter": MAX_ITER,
+                       "start": "cold", "l2": "flushed between steps (256 MiB fill)", "parallelism": f"frontier sharded block-cyclically over {world} GPU(s)",
+                       "iters_per_node_mean": total_iters / total_nodes, "status_counts[opt,iterlim,infeas,time,cutoff]": status.tolist(),
+                       "frontier_setup_s": setup_s, "wall_ms_per_step": wall_ms_max},
+            "e2e": {"value": total_nodes / (e2e_ms_max * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                         "note": "FP64: algorithmic flops = iterations x 16/3 (N1^3+N2^3+N3^3) (+ cut rows) of the fused relaxation kernel; peak = DMMA m8n8k4 FP64 "
+                                 f"measured in this run (DFMA {peaks['dfma_tflops']:.1f} TF); MEASURED_PEAKS.json carries no FP64 figure"},
+            "clocks": sampler.summary(),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    fr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nodes", type=int, default=1184, help="frontier nodes per GPU (8 x 148 SMs)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

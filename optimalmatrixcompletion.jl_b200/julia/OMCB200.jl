@@ -1,0 +1,173 @@
+# OMCB200.jl -- Julia glue that routes OptimalMatrixCompletion.jl's hot path through libomc_b200.so.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: neither Julia nor Mosek exists in the build image (SURVEY.md G4/G5).
+# The same calls are exercised from Python (optimalmatrixcompletion.jl_b200/engine.py + host.py), which
+# mirrors this file function for function.  See INTEGRATION.md for how a maintainer wires it in.
+#
+# The reference keeps its public API and its host loop (node queue, branching, cut bookkeeping, incumbent,
+# printlist / instance outputs).  Only the BODIES of the functions below change: each builds the flat ABI
+# arguments, `ccall`s the engine and returns the same Dict keys the host loop reads
+# (/root/reference/src/OptimalMatrixCompletion.jl, "OMC.jl" below).
+module OMCB200
+
+using LinearAlgebra
+import MathOptInterface
+const MOI = MathOptInterface
+
+const LIB = get(ENV, "OMC_B200_LIB", joinpath(@__DIR__, "..", "libomc_b200.so"))
+
+const STATUS_TO_MOI = Dict(
+    0 => MOI.OPTIMAL,        # OMC_STATUS_OPTIMAL
+    1 => MOI.SLOW_PROGRESS,  # OMC_STATUS_ITERATION_LIMIT (has values -> feasible = true, OMC.jl:1871-1877)
+    2 => MOI.INFEASIBLE,     # OMC_STATUS_INFEASIBLE
+    3 => MOI.TIME_LIMIT,     # OMC_STATUS_TIME_LIMIT
+    4 => MOI.OPTIMAL,        # OMC_STATUS_CUTOFF: objective = certified bound > incumbent, pruned at OMC.jl:797
+)
+const CUT_TYPE = Dict("linear" => 0, "linear2" => 1, "linear3" => 2)
+const LABELS = Dict(
+    "linear" => ["left", "right"],                                 # OMC.jl:2482
+    "linear2" => ["left", "middle", "right"],                      # OMC.jl:2486
+    "linear3" => ["left", "inner_left", "inner_right", "right"],   # OMC.jl:2490
+)
+
+struct OmcError <: Exception
+    code::Int32
+    msg::String
+end
+function check(rc::Int32)
+    rc == 0 && return
+    throw(OmcError(rc, unsafe_string(ccall((:omc_last_error, LIB), Cstring, ()))))
+end
+
+# mirrors omc_relax_opts (include/omc_b200.h)
+mutable struct RelaxOpts
+    eps_abs::Float64; eps_rel::Float64
+    max_iter::Int32; check_every::Int32; adapt_every::Int32; fix_linear3_right::Int32
+    rho0::Float64; sigma::Float64; alpha::Float64; cutoff::Float64; time_limit_s::Float64; jacobi_tol::Float64
+    reortho_every::Int32; reserved::Int32
+end
+function default_opts()
+    o = RelaxOpts(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    ccall((:omc_relax_default_opts, LIB), Cvoid, (Ref{RelaxOpts},), o)
+    return o
+end
+
+init(device::Integer = 0) = check(ccall((:omc_init, LIB), Int32, (Int32,), device))
+
+"""(A, indices, γ, k) resident in HBM + cut pool.  One per `matrix_completion_branchandbound` call."""
+mutable struct Problem
+    handle::Ptr{Cvoid}
+    n::Int; m::Int; k::Int
+    cut_type::String
+    cut_ids::IdDict{Any, Int32}     # (breakpoint_vec, Û) tuple identity -> pool id (children share the tuple, OMC.jl:2522)
+    function Problem(k::Int, A::Matrix{Float64}, indices::BitMatrix, γ::Float64, cut_type::String; state_pool::Int = 0)
+        (n, m) = size(A)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        # BitMatrix.chunks is exactly the ABI's mask layout (column-major bit index, LSB first)
+        check(ccall((:omc_problem_create, LIB), Int32,
+                    (Int32, Int32, Int32, Ptr{Float64}, Ptr{UInt64}, Float64, Int32, Int32, Ref{Ptr{Cvoid}}),
+                    n, m, k, A, indices.chunks, γ, CUT_TYPE[cut_type], state_pool, h))
+        p = new(h[], n, m, k, cut_type, IdDict{Any, Int32}())
+        finalizer(x -> ccall((:omc_problem_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), p)
+        return p
+    end
+end
+
+function cut_id!(p::Problem, breakpoint_vec::Vector{Float64}, Û::Matrix{Float64})
+    key = breakpoint_vec                      # one Vector object per cut, shared by all children (OMC.jl:2522)
+    haskey(p.cut_ids, key) && return p.cut_ids[key]
+    v̂ = Û' * breakpoint_vec                   # the only use of Û (OMC.jl:1577, 2053)
+    id = Ref{Int32}(0)
+    check(ccall((:omc_cutpool_add, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Int32}),
+                p.handle, breakpoint_vec, v̂, id))
+    p.cut_ids[key] = id[]
+    return id[]
+end
+
+function flatten(p::Problem, nodes_cuts)
+    B = length(nodes_cuts)
+    ptr = zeros(Int32, B + 1); ids = Int32[]; dirs = UInt8[]
+    for (b, cuts) in enumerate(nodes_cuts)
+        ptr[b + 1] = ptr[b] + length(cuts)
+        for (x, Û, directions) in cuts
+            push!(ids, cut_id!(p, x, Û))
+            append!(dirs, UInt8[findfirst(isequal(d), LABELS[p.cut_type]) - 1 for d in directions])
+        end
+    end
+    isempty(ids) && (push!(ids, 0); push!(dirs, 0))
+    return ptr, ids, dirs
+end
+
+"""
+Batched body of `matrix_completion_SDP_relaxation` (OMC.jl:1431-1943).  `nodes::Vector{BBNode}`; returns one Dict
+per node with the reference's keys ("model", "solve_time", "termination_status", "feasible", "objective",
+"Y", "U", "X", "Θ" -- OMC.jl:1860-1919).  "Θ" is returned as `nothing`: on the disjunctive path the host only
+reads it through the objective, which the engine already recomputed from the primal point (OMC.jl:1890-1895).
+"""
+function relax_batch(p::Problem, nodes; opts::RelaxOpts = default_opts())
+    B = length(nodes)
+    ptr, ids, dirs = flatten(p, [nd.disjunctive_cuts.cuts for nd in nodes])
+    status = zeros(Int32, B); iters = zeros(Int32, B)
+    objective = zeros(B); lower = zeros(B); res = zeros(2B)
+    X = zeros(p.n, p.m, B); Y = zeros(p.n, p.n, B); U = zeros(p.n, p.k, B)
+    ms = Ref{Float32}(0)
+    t = @elapsed check(ccall((:omc_relax_batch, LIB), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{UInt8}, Ptr{Int32}, Ptr{Int32}, Ref{RelaxOpts},
+         Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ref{Float32}),
+        p.handle, B, ptr, ids, dirs, C_NULL, C_NULL, opts, status, objective, lower, iters, res, X, Y, U, C_NULL, ms))
+    return [Dict{String, Any}(
+        "model" => nothing,
+        "solve_time" => t / B,
+        "termination_status" => STATUS_TO_MOI[Int(status[b])],
+        "feasible" => status[b] != 2,
+        "objective" => objective[b],
+        "Y" => Y[:, :, b], "U" => U[:, :, b], "X" => X[:, :, b], "Θ" => nothing,
+        "lower_bound" => lower[b], "iterations" => iters[b],
+    ) for b in 1:B]
+end
+
+"""Drop-in for `matrix_completion_SDP_relaxation(node, n, k, A, indices, γ, true; disjunctive_cuts_type, ...)`."""
+matrix_completion_SDP_relaxation(p::Problem, node; kwargs...) = relax_batch(p, [node]; kwargs...)[1]
+
+"""Batched `eigs(Symmetric(U*U' - Y), nev, which=:SR)` + the test of OMC.jl:1272-1277."""
+function smallest_eigvecs_batch(Ys::Vector{Matrix{Float64}}, Us::Vector{Matrix{Float64}}, nev::Int)
+    B = length(Ys); (n, k) = size(Us[1])
+    Y = cat(Ys...; dims = 3); U = cat(Us...; dims = 3)
+    lam = zeros(nev, B); vec = zeros(n, nev, B); bp = zeros(n, B); feas = zeros(Int32, B)
+    check(ccall((:omc_smallest_eigvecs_batch, LIB), Int32,
+                (Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                n, k, B, Y, U, nev, lam, vec, bp, feas))
+    return lam, vec, bp, feas .== 1
+end
+matrix_completion_master_feasible(Y, U, X, Θ, use_disjunctive_cuts::Bool) =
+    smallest_eigvecs_batch([Y], [U], 1)[4][1]                                  # OMC.jl:1261-1277
+breakpoint_vector(Y, U, nev::Int) = smallest_eigvecs_batch([Y], [U], nev)[3][:, 1]   # OMC.jl:2466-2477
+
+"""Drop-in body of `alternating_minimization` (OMC.jl:1979-2279); same result Dict (OMC.jl:2249-2278)."""
+function alternating_minimization(p::Problem; U_initial::Matrix{Float64}, disjunctive_cuts = [], ϵ::Float64 = 1e-5,
+                                  max_iters::Int = 100, time_limit::Int = 3600)
+    ids = Int32[cut_id!(p, x, Û) for (x, Û, _) in disjunctive_cuts]
+    dirs = UInt8[findfirst(isequal(d), LABELS[p.cut_type]) - 1 for (_, _, ds) in disjunctive_cuts for d in ds]
+    isempty(ids) && (push!(ids, 0); push!(dirs, 0))
+    U = zeros(p.n, p.k); V = zeros(p.k, p.m); objectives = zeros(max_iters)
+    conv = Ref{Int32}(0); nit = Ref{Int32}(0); st = Ref{Float64}(0)
+    check(ccall((:omc_altmin, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{UInt8}, Float64, Int32, Float64, Ptr{Float64}, Ptr{Float64},
+                 Ref{Int32}, Ref{Int32}, Ptr{Float64}, Ref{Float64}),
+                p.handle, U_initial, length(disjunctive_cuts), ids, dirs, ϵ, max_iters, Float64(time_limit), U, V, conv, nit,
+                objectives, st))
+    return Dict("converged" => conv[] == 1, "U" => U, "V" => V, "solve_time" => st[], "n_iters" => Int(nit[]),
+                "max_iters" => max_iters, "objectives" => objectives[1:nit[]])
+end
+
+"""Fused `evaluate_objective` (OMC.jl:2330-2359) + `compute_MSE` (OMC.jl:2373-2409): (objective, in, out, all)."""
+function objective_mse(p::Problem, X::Matrix{Float64})
+    out = zeros(4)
+    check(ccall((:omc_objective_mse, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), p.handle, X, out))
+    return out
+end
+evaluate_objective(p::Problem, X, A, indices, U, γ) = objective_mse(p, X)[1]
+compute_MSE(p::Problem, X, A, indices; kind = "out") = objective_mse(p, X)[kind == "in" ? 2 : kind == "out" ? 3 : 4]
+
+end # module

@@ -1,0 +1,51 @@
+"""CPU test of the N > 1 host path: world_size = 2 over gloo (the GPU box uses NCCL with the same calls)."""
+import os
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import omc_b200  # noqa: F401
+    from omc_b200.parallel import shard_block_cyclic, allreduce_bounds
+    nodes = list(range(101, 101 + 37))
+    mine = shard_block_cyclic(nodes, rank, world)
+    # every rank "relaxes" its shard: pretend bound = node id / 10, incumbent found by the rank owning node 120
+    lbs = [nid / 10.0 for nid in mine]
+    ub = 11.5 if 120 in mine else 99.0
+    gub, glb = allreduce_bounds(ub, min(lbs))
+    q.put((rank, mine, gub, glb))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_frontier_sharding_and_bound_allreduce_world2():
+    world, port = 2, 29500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shards = [o[1] for o in out]
+    assert sorted(shards[0] + shards[1]) == list(range(101, 138)) and not set(shards[0]) & set(shards[1])
+    assert abs(len(shards[0]) - len(shards[1])) <= 1
+    for _, _, gub, glb in out:                      # both ranks agree on the global incumbent and lower bound
+        assert gub == 11.5 and glb == 10.1
+    sys.path.insert(0, ROOT)
+    import omc_b200  # noqa: F401
+    from omc_b200.parallel import unshard_block_cyclic, rebalance_counts
+    assert unshard_block_cyclic(shards) == list(range(101, 138))
+    c = rebalance_counts([1000, 3000], [10, 10])
+    assert c.sum() == 20 and c[0] > c[1]
