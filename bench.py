@@ -18,6 +18,9 @@ N > 1 (torchrun): the frontier of N*B nodes is sharded block-cyclically, one pro
 collective; the tiny [incumbent, min lower bound] all-reduce-min after each step goes over NCCL.
 """
 import argparse
+import os as _os, sys as _sys
+if "reference" in _sys.argv:   # the oracle runs one node per process: keep BLAS single-threaded inside each
+    _os.environ.setdefault("OMP_NUM_THREADS", "1"); _os.environ.setdefault("OPENBLAS_NUM_THREADS", "1"); _os.environ.setdefault("MKL_NUM_THREADS", "1")  # OMC_REF_THREADS
 import ctypes as C
 import json
 import os
@@ -110,28 +113,22 @@ def build_frontier_gpu(problem, target, omc):
     return out[:target]
 
 
-def build_frontier_cpu(A, mask, gamma, k, target):
-    """Same expansion with the CPU oracle (reference arm / cpu_baseline sample); returns oracle cut lists."""
+def load_frontier_fixture(limit=None):
+    """Cut descriptors of the first frontier nodes (tests/golden/c2_frontier.json, dumped by
+    scripts/dump_frontier_fixture.py): a list of oracle-style cut lists [(x, vhat, dirs), ...] per node."""
+    with open(os.path.join(ROOT, "tests", "golden", "c2_frontier.json")) as f:
+        fx = json.load(f)
+    nodes = fx["nodes"][:limit] if limit else fx["nodes"]
+    return [[(np.array(c["x"]), np.array(c["vhat"]), list(c["dirs"])) for c in nd["cuts"]] for nd in nodes]
+
+
+def _oracle_warm(_):
+    os.environ["OMP_NUM_THREADS"] = "1"
     from oracle import relaxation as R
-    from oracle.eigsep import breakpoint_vector, master_feasible
-    from oracle.cuts import child_directions
-    o = R.Options(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER)
-    open_nodes = [(-np.inf, 1, [])]
-    counter = 1
-    while len(open_nodes) < target:
-        open_nodes.sort(key=lambda t: (t[0], t[1]))
-        lb, nid, cuts = open_nodes.pop(0)
-        r = R.solve_relaxation(A, mask, gamma, k, "linear", cuts, opts=o)
-        if r["status"] != 0 or master_feasible(r["Y"], r["U"]):
-            if not open_nodes:
-                break
-            continue
-        x, _ = breakpoint_vector(r["Y"], r["U"])
-        for ind, dirs in child_directions("linear", k):
-            open_nodes.append((r["objective"], counter + ind, cuts + [(x, r["U"].copy(), dirs)]))
-        counter += 2 ** k
-    open_nodes.sort(key=lambda t: (t[0], t[1]))
-    return [c for _, _, c in open_nodes[:target]]
+    rng = np.random.default_rng(0)
+    Aw = rng.standard_normal((6, 6))
+    R.solve_relaxation(Aw, np.ones((6, 6), bool), 80.0, 1, opts=R.Options(max_iter=50))
+    return 0
 
 
 def _oracle_worker(args):
@@ -151,15 +148,14 @@ def run_reference(args):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     A, mask = c2_instance(0)
-    sample = max(2, min(2 * cores, 32))
+    sample = max(2, min(cores, 64))
     t0 = time.time()
-    cuts = build_frontier_cpu(A, mask, 80.0, 1, sample)
+    cuts = load_frontier_fixture(sample)
     setup = time.time() - t0
     jobs = [(A, mask, 80.0, 1, c) for c in cuts]
     ctx = mp.get_context("fork")
     with ctx.Pool(processes=min(cores, len(jobs))) as pool:
-        for _ in range(args.warmup if args.warmup < 1 else 1):
-            pool.map(_oracle_worker, jobs[: min(cores, len(jobs))])
+        pool.map(_oracle_warm, range(min(cores, len(jobs))))       # warm-up: import + LAPACK init in every worker
         t0 = time.perf_counter()
         iters = 0
         for _ in range(args.steps):
@@ -173,7 +169,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "nodes_per_step": len(jobs), "eps": EPS, "max_iter": MAX_ITER,
                        "note": "CPU restatement of the relaxation (NumPy/LAPACK ADMM), not Mosek: Julia and Mosek are absent"},
             "cpu_baseline": {"value": value, "unit": "nodes/s", "cores": min(cores, len(jobs)), "kind": "port",
-                             "sample": f"{len(jobs)} frontier nodes x {args.steps} steps, {iters} ADMM iterations, frontier setup {setup:.1f}s untimed"},
+                             "sample": f"first {len(jobs)} nodes of the config-2 frontier fixture x {args.steps} steps, {iters} ADMM iterations, one node per core"},
             "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -281,7 +277,8 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             from oracle import relaxation as R
             t0 = time.perf_counter(); done = 0; cit = 0
-            for nd in mine[:: max(1, len(mine) // 8)]:
+            sample_nodes = mine[:: max(1, len(mine) // 8)]
+            for nd in sample_nodes:
                 cuts = [(c.x, c.Uhat, c.directions) for c in nd.disjunctive_cuts]
                 r = R.solve_relaxation(A, mask, 80.0, k, "linear", cuts, opts=R.Options(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER))
                 done += 1; cit += r["iters"]

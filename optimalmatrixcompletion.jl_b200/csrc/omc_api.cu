@@ -44,6 +44,7 @@ int fail(int code, const char* fmt, ...) {
 #define NEED_INIT()                                                                     \
   do {                                                                                  \
     if (g_device < 0) return fail(OMC_ERR_STATE, "omc_init() has not been called");     \
+    cudaSetDevice(g_device); /* the host framework may have switched the thread's GPU */ \
   } while (0)
 
 template <typename T>
@@ -338,6 +339,11 @@ int32_t omc_init(int32_t device) {
   if (prop.major != 10)
     return fail(OMC_ERR_UNSUPPORTED, "device %d is sm_%d%d; libomc_b200 is built for sm_100a only", device, prop.major,
                 prop.minor);
+  if (g_stream != nullptr && g_device != device) {  // the stream belongs to the previously selected GPU
+    cudaStreamSynchronize(g_stream);
+    cudaStreamDestroy(g_stream);
+    g_stream = nullptr;
+  }
   if (g_stream == nullptr) CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   g_device = device;
   g_sm_count = prop.multiProcessorCount;

@@ -26,10 +26,12 @@ MOI_STATUS = {0: "OPTIMAL", 1: "SLOW_PROGRESS", 2: "INFEASIBLE", 3: "TIME_LIMIT"
 _initialised = None
 
 
-def init(device: int = 0):
-    """omc_init: one process drives one GPU."""
+def init(device: Optional[int] = None):
+    """omc_init: one process drives one GPU.  device=None keeps the GPU already selected (0 on first use)."""
     global _initialised
     lib = _lib.load()
+    if device is None:
+        device = _initialised if _initialised is not None else 0
     if _initialised != device:
         check(lib.omc_init(device))
         _initialised = device
@@ -77,7 +79,7 @@ class Problem:
     """(k, A, indices, gamma) resident in HBM, its cut pool and warm-start state pool."""
 
     def __init__(self, k: int, A: np.ndarray, indices: np.ndarray, gamma: float, disjunctive_cuts_type: str = "linear",
-                 state_pool_capacity: int = 0, device: int = 0):
+                 state_pool_capacity: int = 0, device: Optional[int] = None):
         if disjunctive_cuts_type not in CUT_TYPES:
             raise ValueError('Disjunctive cuts type must be either "linear" or "linear2" or "linear3"; '
                              f"{disjunctive_cuts_type} supplied instead.")         # OMC.jl:1456-1462
@@ -261,7 +263,7 @@ def compute_MSE(problem: Problem, X: np.ndarray, kind: str = "out") -> float:
 
 def smallest_eigvecs_batch(Y: np.ndarray, U: np.ndarray, nev: int = 1):
     """Batched OMC.jl:2466-2477 + 1272-1277.  Y (B,n,n), U (B,n,k) -> lam (B,nev), vec (B,n,nev), breakpoint (B,n), feasible (B,)"""
-    lib = init(_initialised if _initialised is not None else 0)
+    lib = init()
     Y = np.asarray(Y, dtype=np.float64); U = np.asarray(U, dtype=np.float64)
     if Y.ndim == 2:
         Y = Y[None]; U = U[None]
@@ -304,7 +306,7 @@ def alternating_minimization(problem: Problem, U_initial: np.ndarray, disjunctiv
 
 def psd_project_batch(V: np.ndarray):
     """Eigensolver self-test entry: V (B,N,N) symmetric -> (P, lam, sweeps, kernel_ms)."""
-    lib = init(_initialised if _initialised is not None else 0)
+    lib = init()
     V = np.ascontiguousarray(V, dtype=np.float64)
     B, N, _ = V.shape
     P = np.zeros_like(V); lam = np.zeros((B, N)); sw = np.zeros(B, np.int32); ms = C.c_float()
@@ -314,7 +316,7 @@ def psd_project_batch(V: np.ndarray):
 
 
 def measure_fp64_peak():
-    lib = init(_initialised if _initialised is not None else 0)
+    lib = init()
     out = np.zeros(2)
     check(lib.omc_measure_fp64_peak(_ptr(out, C.c_double)))
     return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1])}

@@ -259,7 +259,7 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
                                      time_limit: int = 3600, update_step: int = 1000, verbosity: int = 0,
                                      # engine knobs (defaults leave the reference's behaviour unchanged)
                                      frontier_batch: int = 1, relax_opts=None, use_cutoff: bool = False,
-                                     warm_start: bool = False, device: int = 0, stop_at_open_nodes: int = 0, seed: int = 0):
+                                     warm_start: bool = False, device: Optional[int] = None, stop_at_open_nodes: int = 0, seed: int = 0):
     """Mirror of OMC.jl:140-1146 (disjunctive path).  Returns (solution, printlist, instance) with the
     reference's keys.  frontier_batch = 1 reproduces the reference's sequence of pops; larger batches pop B
     nodes, relax them in one launch and consume the results in pop order.
