@@ -537,14 +537,15 @@ int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_p
     if (save_ids && save_ids[b] >= p->state_cap) return fail(OMC_ERR_ARG, "save id out of range");
   }
   const omc::Geo g1 = omc::make_geo(p->n + p->m);
-  if (g1.NP > 104)
-    return fail(OMC_ERR_UNSUPPORTED, "n+m = %d: this build keeps the (n+m) PSD block in one SM's shared memory (n+m <= 104)",
-                p->n + p->m);
+  const omc::Geo g2 = omc::make_geo(p->n + p->k);
+  if (g1.NP > 208 || g2.NP > OMC_SMEM_NP_MAX)
+    return fail(OMC_ERR_UNSUPPORTED, "n+m = %d, n+k = %d: this build supports n+m <= 208 (L2-resident working buffers above 104) and n+k <= 104",
+                p->n + p->m, p->n + p->k);
   omc_frontier* f = new omc_frontier();
   f->p = p; f->B = B; f->E = E; f->Lmax = Lmax;
   f->rmax = 1 + p->Lcap * (p->k + 1);
   // the Gram staging C[L][L] and (when it fits) the Woodbury inverse use buf0
-  f->variant = (g1.NP <= 32) ? 0 : (g1.NP <= 64 ? 1 : 2);
+  f->variant = (g1.NP <= 32) ? 0 : (g1.NP <= 64 ? 1 : (g1.NP <= 104 ? 2 : 3));
   const int ctas_per_sm = (f->variant == 0) ? 4 : (f->variant == 1 ? 2 : 1);
   f->grid = g_sm_count * ctas_per_sm;
   if (f->grid > B) f->grid = B;
@@ -625,10 +626,14 @@ int32_t omc_frontier_relax(omc_frontier* f, const omc_relax_opts* opts, float* k
     auto kern = omc::omc_relax_kernel<256, 16, 2>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
     kern<<<f->grid, 256, f->smem, g_stream>>>(a);
-  } else {
+  } else if (f->variant == 2) {
     auto kern = omc::omc_relax_kernel<512, 26, 1>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
     kern<<<f->grid, 512, f->smem, g_stream>>>(a);
+  } else {  // (n+m) block in L2-resident buffers: 256 threads so that a 52-deep DMMA panel fits in registers
+    auto kern = omc::omc_relax_kernel<256, 52, 1>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
+    kern<<<f->grid, 256, f->smem, g_stream>>>(a);
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(f->ev1, g_stream));

@@ -102,8 +102,10 @@ __device__ __forceinline__ double block_max(double v, double* scratch) {
 
 // ------------------------------------------------------------------------------------------------
 // Geometry of one symmetric block held in shared memory: N real rows, NP = N rounded up to 8 (DMMA
-// tile), leading dimension ld = NP + 4 (ld % 8 == 4 makes both DMMA fragment patterns, 4 rows x 4
-// consecutive doubles, hit 16 distinct 8-byte banks).
+// tile), leading dimension ld = NP + 1.  An ODD leading dimension makes a warp's 64-bit accesses
+// conflict-free both along a row (consecutive doubles) and down a column (stride ld: 16 lanes hit 16
+// distinct 8-byte banks), which the Jacobi column rotations need; the price is a 2-way conflict on part
+// of the DMMA fragment loads (4 rows x 4 doubles), ~10 % of the kernel.
 // ------------------------------------------------------------------------------------------------
 struct Geo {
   int N, NP, ld;
@@ -112,7 +114,7 @@ __host__ __device__ inline Geo make_geo(int N) {
   Geo g;
   g.N = N;
   g.NP = (N + 7) & ~7;
-  g.ld = g.NP + 4;
+  g.ld = g.NP + 1;
   return g;
 }
 
@@ -205,9 +207,22 @@ __device__ __forceinline__ void gemm_cols_inplace(double* M, const double* Q, in
 // in shared memory, accumulating the rotations into Q (Q <- Q * J).  Round-robin ordering: step t
 // pairs (NP-1, t) and ((t+i) mod (NP-1), (t-i) mod (NP-1)), i = 1 .. NP/2-1, so each sweep visits all
 // NP(NP-1)/2 pairs in NP-1 steps of NP/2 disjoint rotations.
+//
 // After every sweep the remaining off-diagonal mass is measured directly (an N^2 pass, ~1% of a sweep);
 // the solver stops when off(S) <= tol * ||S||_F or after max_sweeps.
-// cs / sn / rot: shared arrays of NP/2 entries.  Returns the number of sweeps (same in all threads).
+//
+// projection_mode: the caller only needs the projection onto the PSD cone, i.e. the split into the
+// positive and the negative invariant subspace and the eigenpairs of the SMALLER side.  Indices whose
+// diagonal entry dominates its row by a factor 2 (|s_ii| > 2 sum_j |s_ij|) are "safe": by Gershgorin the
+// principal submatrix on the safe indices of one sign is definite with that sign, whatever basis spans it.
+// Rotations between two safe indices of the majority sign are therefore skipped (inside degenerate
+// clusters of the dual they would be O(1) rotations at every ADMM iteration, for nothing); every other pair
+// is rotated to tolerance, so each non-skipped index ends up as an exact eigenpair decoupled from the rest.
+// *skip_sign returns 0 (nothing skipped), +1 (safe positive indices skipped: use the negative side) or -1;
+// skip[i] != 0 marks the skipped indices.  With projection_mode = 0 this is a full eigensolver.
+//
+// cs / sn: NP/2 doubles; rot: 3*NP/2 ints (>= 1 + NP/2 used); skip: NP ints; scratch: 32 doubles.
+// Returns the sweep count.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void jacobi_pair(int i, int t, int NP, int& p, int& q) {
   const int M = NP - 1;
@@ -223,99 +238,125 @@ __device__ __forceinline__ void jacobi_pair(int i, int t, int NP, int& p, int& q
 }
 
 __device__ inline int jacobi_sym(double* S, double* Q, int NP, int ld, double tol, int max_sweeps, double* cs,
-                                 double* sn, int* rot, double* scratch) {
-  // rot[] holds, per pair i of the current step: rot[i] = rotate flag, rot[H + i] = p_i, rot[2H + i] = q_i
+                                 double* sn, int* rot, double* scratch, int projection_mode = 0, int* skip = nullptr,
+                                 int* skip_sign = nullptr, double* stats = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int H = NP >> 1;
-  int* pidx = rot + H;
-  int* qidx = rot + 2 * H;
   // 2-D thread map without integer division in the hot loops: tx = pair j (fastest), ty = row group
   const int TX = (H <= 16) ? 16 : ((H <= 32) ? 32 : 64);
   const int tx = tid & (TX - 1), ty = tid / TX, TY = nt / TX;
-  double acc = 0.0, acco = 0.0;
+  const bool pm = projection_mode && skip != nullptr;
+  double acc = 0.0;
   for (int e = tid; e < NP * NP; e += nt) {
     const int r = e / NP, c = e - r * NP;
     const double v = S[(size_t)r * ld + c];
     acc += v * v;
-    if (r != c) acco += v * v;
   }
   const double fro2 = block_sum(acc, scratch);
-  const double offin2 = block_sum(acco, scratch);
+  if (pm && tid < NP) skip[tid] = 0;
+  if (skip_sign && tid == 0) *skip_sign = 0;
+  __syncthreads();
   if (fro2 == 0.0) return 0;
   const double stop2 = tol * tol * fro2;
-  if (offin2 <= stop2) return 0;  // already diagonal to the requested accuracy
   const double thr = 1e-20 * sqrt(fro2);
   int sweeps = 0;
-  for (; sweeps < max_sweeps;) {
+  double nrot = 0.0, nskip = 0.0;
+  for (;;) {
+    // ---- classification (projection mode) and the off-diagonal mass that still matters
+    if (pm) {
+      int c = 0;
+      if (tid < NP) {
+        const double* row = S + (size_t)tid * ld;
+        double rs = 0.0;
+        for (int j = 0; j < NP; ++j) rs += fabs(row[j]);
+        const double d = row[tid];
+        rs -= fabs(d);
+        c = (d > 2.0 * rs) ? 1 : ((d < -2.0 * rs) ? -1 : 0);
+      }
+      const int cpos = __syncthreads_count(c > 0);
+      const int cneg = __syncthreads_count(c < 0);
+      const int sg = (cpos == 0 && cneg == 0) ? 0 : ((cneg >= cpos) ? -1 : 1);
+      if (tid < NP) skip[tid] = (sg != 0 && c == sg) ? 1 : 0;
+      if (skip_sign && tid == 0) *skip_sign = sg;
+      if (tid == 0) nskip += (sg < 0) ? cneg : ((sg > 0) ? cpos : 0);
+      __syncthreads();
+    }
+    double off2 = 0.0;
+    for (int r = ty; r < NP; r += TY) {
+      const double* row = S + (size_t)r * ld;
+      const int sr = pm ? skip[r] : 0;
+      for (int c = tx; c < NP; c += TX)
+        if (c != r && !(sr && skip[c])) off2 += row[c] * row[c];
+    }
+    off2 = block_sum(off2, scratch);
+    if (off2 <= stop2 || sweeps >= max_sweeps) break;
+    // ---- one sweep
     for (int t = 0; t < NP - 1; ++t) {
+      if (tid == 0) rot[0] = 0;  // rot[0] = number of rotated pairs of this step, rot[1 + a] = (p << 16) | q
+      __syncthreads();
       if (tid < H) {
         int p, q;
         jacobi_pair(tid, t, NP, p, q);
         const double apq = S[(size_t)p * ld + q];
-        double c = 1.0, s = 0.0;
-        int r = 0;
-        if (fabs(apq) > thr) {
-          const double app = S[(size_t)p * ld + p], aqq = S[(size_t)q * ld + q];
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double tt = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = rsqrt(1.0 + tt * tt);
-          s = tt * c;
-          r = 1;
+        const bool skipped = pm && skip[p] && skip[q];
+        if (!skipped && fabs(apq) > thr) {
+          // symmetric Schur rotation with |theta| <= pi/4: cos 2theta = |d| / r, sin 2theta = +-o / r
+          const double d = S[(size_t)q * ld + q] - S[(size_t)p * ld + p], o = 2.0 * apq;
+          const double ir = rsqrt(d * d + o * o);
+          const double c2 = 0.5 + 0.5 * fabs(d) * ir;       // cos^2 theta
+          const double ic = rsqrt(c2);
+          const double c = c2 * ic;
+          const double s_ = copysign(0.5 * o * ir * ic, d * o);  // sin theta, sign of tau * ... = sign(d) sign(o)
+          const int a = atomicAdd(&rot[0], 1);
+          rot[1 + a] = (p << 16) | q;
+          cs[a] = c;
+          sn[a] = s_;
+          nrot += 1.0;
         }
-        cs[tid] = c;
-        sn[tid] = s;
-        rot[tid] = r;
-        pidx[tid] = p;
-        qidx[tid] = q;
       }
       __syncthreads();
-      // S <- J' S J : every 2x2 block (i, j) is owned by one thread and written in its own orientation
-      // only (row-wise accesses, lanes walk consecutive columns -> no bank conflicts, no mirrored stores)
-      if (tx < H) {
-        const int rj = rot[tx], pj = pidx[tx], qj = qidx[tx];
-        const double cj = cs[tx], sj = sn[tx];
-        for (int i = ty; i < H; i += TY) {
-          const int ri = rot[i];
-          if (!(ri | rj)) continue;
-          const int pi = pidx[i], qi = qidx[i];
-          const double ci = cs[i], si = sn[i];
-          double* rp_ = S + (size_t)pi * ld;
-          double* rq_ = S + (size_t)qi * ld;
-          const double b00 = rp_[pj], b01 = rp_[qj], b10 = rq_[pj], b11 = rq_[qj];
-          const double t00 = ci * b00 - si * b10, t01 = ci * b01 - si * b11;
-          const double t10 = si * b00 + ci * b10, t11 = si * b01 + ci * b11;
-          double n00 = cj * t00 - sj * t01, n01 = sj * t00 + cj * t01;
-          double n10 = cj * t10 - sj * t11, n11 = sj * t10 + cj * t11;
-          if (i == tx) {
-            n01 = 0.0;
-            n10 = 0.0;
-          }
-          rp_[pj] = n00;
-          rp_[qj] = n01;
-          rq_[pj] = n10;
-          rq_[qj] = n11;
+      const int nr = rot[0];
+      if (nr > 0) {
+        // pass 1: S <- J' S  (rows p, q of every rotated pair; lanes walk along the row)
+        for (int e = tid; e < nr * NP; e += nt) {
+          const int a = e / NP, c = e - a * NP;
+          const int pq = rot[1 + a], p = pq >> 16, q = pq & 0xffff;
+          const double ca = cs[a], sa = sn[a];
+          double* rp_ = S + (size_t)p * ld + c;
+          double* rq_ = S + (size_t)q * ld + c;
+          const double x = *rp_, y = *rq_;
+          *rp_ = ca * x - sa * y;
+          *rq_ = sa * x + ca * y;
         }
-        // Q <- Q J
-        if (rj) {
-          for (int r = ty; r < NP; r += TY) {
-            double* row = Q + (size_t)r * ld;
-            const double xp = row[pj], xq = row[qj];
-            row[pj] = cj * xp - sj * xq;
-            row[qj] = sj * xp + cj * xq;
+        __syncthreads();
+        // pass 2: S <- S J and Q <- Q J (columns p, q; lanes walk down the column, conflict-free for odd ld)
+        for (int e = tid; e < 2 * nr * NP; e += nt) {
+          const int h = e / (nr * NP), e2 = e - h * nr * NP;
+          const int a = e2 / NP, r = e2 - a * NP;
+          const int pq = rot[1 + a], p = pq >> 16, q = pq & 0xffff;
+          const double ca = cs[a], sa = sn[a];
+          double* base = (h == 0 ? S : Q) + (size_t)r * ld;
+          const double x = base[p], y = base[q];
+          double xn = ca * x - sa * y, yn = sa * x + ca * y;
+          if (h == 0) {  // the rotated entry is annihilated exactly
+            if (r == p) yn = 0.0;
+            if (r == q) xn = 0.0;
           }
+          base[p] = xn;
+          base[q] = yn;
         }
       }
       __syncthreads();
     }
     ++sweeps;
-    double off2 = 0.0;
-    for (int r = ty; r < NP; r += TY) {
-      const double* row = S + (size_t)r * ld;
-      for (int c = tx; c < NP; c += TX)
-        if (c != r) off2 += row[c] * row[c];
+  }
+  if (stats) {  // diagnostics: rotations applied, skipped-set sizes (summed over classification passes)
+    nrot = block_sum(nrot, scratch);
+    if (tid == 0) {
+      stats[0] += nrot;
+      stats[1] += nskip;
+      stats[2] += 1.0;
     }
-    off2 = block_sum(off2, scratch);
-    if (off2 <= stop2) break;
   }
   return sweeps;
 }

@@ -47,8 +47,21 @@ __host__ __device__ inline StateLayout make_state_layout(int n, int m, int k, in
 
 // per-CTA scratch (doubles): w~ (same shape as w), eigenvector bases of the 3 blocks (shared-memory
 // images, NP x ld), Gram matrix of the dense rows and the Woodbury inverse, and the working state.
+// Largest PSD block that is diagonalised in shared memory (two NP x ld FP64 buffers must fit in 227 KB):
+// blocks with NP > OMC_SMEM_NP_MAX run through the same device functions on an L2-resident global buffer.
+#define OMC_SMEM_NP_MAX 104
+__host__ __device__ inline Geo smem_geo(int N1, int N2, int N3) {
+  Geo best = make_geo(1);
+  const int Ns[3] = {N1, N2, N3};
+  for (int b = 0; b < 3; ++b) {
+    const Geo g = make_geo(Ns[b]);
+    if (g.NP <= OMC_SMEM_NP_MAX && g.NP > best.NP) best = g;
+  }
+  return best;
+}
+
 struct ScratchLayout {
-  size_t wt, Q1, Q2, Q3, G, Minv, state, total;
+  size_t wt, Q1, Q2, Q3, G, Minv, state, big0, total;
 };
 __host__ __device__ inline ScratchLayout make_scratch_layout(const StateLayout& S, int rmax) {
   ScratchLayout C;
@@ -63,6 +76,9 @@ __host__ __device__ inline ScratchLayout make_scratch_layout(const StateLayout& 
   C.Minv = o; o += (size_t)rmax * rmax;
   o = (o + 1) & ~(size_t)1;
   C.state = o; o += S.total;
+  o = (o + 1) & ~(size_t)1;
+  C.big0 = o;
+  if (g1.NP > OMC_SMEM_NP_MAX) o += (size_t)g1.NP * g1.ld;   // working matrix of a block too large for shared memory
   C.total = (o + 1) & ~(size_t)1;
   return C;
 }
@@ -242,7 +258,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
   const int n = P.n, m = P.m, k = P.k;
   const StateLayout& SL = P.SL;
   const Geo g1 = make_geo(SL.N1), g2 = make_geo(SL.N2), g3 = make_geo(SL.N3);
-  const size_t bufsz = (size_t)g1.NP * g1.ld;
+  const Geo gfit = smem_geo(SL.N1, SL.N2, SL.N3);
+  const size_t bufsz = (size_t)gfit.NP * gfit.ld;
 
   // ---- shared memory carve-up
   double* buf0 = reinterpret_cast<double*>(smem_raw);
@@ -263,7 +280,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
   uint64_t* mbar = reinterpret_cast<uint64_t*>(cxp + P.Lcap);           // [1]
   int* jrot = reinterpret_cast<int*>(mbar + 1);                         // [3*NP1/2]
   int* idx = jrot + 3 * (g1.NP / 2);                                    // [NP1]
-  int* ish = idx + g1.NP;                                               // [8] misc ints
+  int* jskip = idx + g1.NP;                                             // [NP1] projection-mode skip flags
+  int* ish = jskip + g1.NP;                                             // [8] misc ints
 
   double* scr = P.scratch + (size_t)blockIdx.x * P.SC.total;
   double* st = scr + P.SC.state;
@@ -300,6 +318,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
     const int node = ish[0];
     if (node >= P.B) break;
     if (tid == 0) ish[3] = 0;
+    if (P.prof)
+      for (int q = tid; q < 16; q += NT) P.prof[(size_t)node * 16 + q] = 0.0;
 
     const int e0 = P.node_cut_ptr[node], L = P.node_cut_ptr[node + 1] - e0;
     const int r = 1 + L * (k + 1);
@@ -545,12 +565,15 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         const int N = g.N, NP = g.NP, ld = g.ld;
         const uint32_t qbytes = (uint32_t)((size_t)NP * ld * sizeof(double));
         const bool warmQ = have_basis[b] && !reortho;
+        const bool fits = (size_t)NP * ld <= bufsz;             // else: L2-resident working buffers
+        double* B0 = fits ? buf0 : (scr + P.SC.big0);
+        double* B1 = fits ? buf1 : Qg[b];
         // start fetching the previous eigenvector basis while V is assembled
 #if OMC_USE_TMA
-        if (warmQ && tid == 0) {
+        if (fits && warmQ && tid == 0) {
           fence_proxy_async();
           mbar_expect_tx(mbar, qbytes);
-          bulk_g2s(buf1, Qg[b], qbytes, mbar);
+          bulk_g2s(B1, Qg[b], qbytes, mbar);
         }
 #endif
         // V = alpha z + (1-alpha) s + mu/rho, lower triangle computed, both triangles stored
@@ -565,48 +588,56 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
             const size_t q = (size_t)rr * N + cc;
             v = al * z_entry(c, b, rr, cc) + (1.0 - al) * sB[q] + mB[q] * irho;
           }
-          buf0[(size_t)rr * ld + cc] = v;
-          buf0[(size_t)cc * ld + rr] = v;
+          B0[(size_t)rr * ld + cc] = v;
+          B0[(size_t)cc * ld + rr] = v;
         }
         OMC_TICK(1)
         if (warmQ) {
+          if (fits) {
 #if OMC_USE_TMA
-          mbar_wait(mbar, mbar_phase);
-          mbar_phase ^= 1;
+            mbar_wait(mbar, mbar_phase);
+            mbar_phase ^= 1;
 #else
-          for (int e = tid; e < NP * ld; e += NT) buf1[e] = Qg[b][e];
+            for (int e = tid; e < NP * ld; e += NT) B1[e] = Qg[b][e];
 #endif
+          }
           __syncthreads();
-          gemm_rows_inplace<KMAX>(buf0, buf1, NP, ld);  // W = V Q
-          gemm_cols_inplace<KMAX>(buf0, buf1, NP, ld);  // S = Q' W
+          gemm_rows_inplace<KMAX>(B0, B1, NP, ld);  // W = V Q
+          gemm_cols_inplace<KMAX>(B0, B1, NP, ld);  // S = Q' W
         } else {
           for (int e = tid; e < NP * NP; e += NT) {
             const int rr = e / NP, cc = e - rr * NP;
-            buf1[(size_t)rr * ld + cc] = (rr == cc) ? 1.0 : 0.0;
+            B1[(size_t)rr * ld + cc] = (rr == cc) ? 1.0 : 0.0;
           }
           __syncthreads();
         }
         OMC_TICK(2)
-        nsweeps += jacobi_sym(buf0, buf1, NP, ld, jtol, 40, jcs, jsn, jrot, red);
+        nsweeps += jacobi_sym(B0, B1, NP, ld, jtol, 40, jcs, jsn, jrot, red, 1, jskip, &ish[4],
+                              P.prof ? (P.prof + (size_t)node * 16 + 8 + 3 * (b == 0 ? 0 : 1)) : nullptr);
         have_basis[b] = true;
         OMC_TICK(3)
         // eigenvalues, the smaller spectral side, compacted index list (warp 0)
-        for (int i = tid; i < NP; i += NT) lam[i] = buf0[(size_t)i * ld + i];
+        for (int i = tid; i < NP; i += NT) lam[i] = B0[(size_t)i * ld + i];
         __syncthreads();
         if (warp == 0) {
-          int npos = 0, nneg = 0;
-          for (int base = 0; base < NP; base += 32) {
-            const int i = base + lane;
-            const double l_ = (i < NP) ? lam[i] : 0.0;
-            npos += __popc(__ballot_sync(0xffffffffu, l_ > 0.0));
-            nneg += __popc(__ballot_sync(0xffffffffu, l_ < 0.0));
+          // side to reconstruct: the one the eigensolver fully diagonalised (the other side's safe indices were
+          // skipped), or the smaller one when nothing was skipped
+          int side = -ish[4];
+          if (side == 0) {
+            int npos = 0, nneg = 0;
+            for (int base = 0; base < NP; base += 32) {
+              const int i = base + lane;
+              const double l_ = (i < NP) ? lam[i] : 0.0;
+              npos += __popc(__ballot_sync(0xffffffffu, l_ > 0.0));
+              nneg += __popc(__ballot_sync(0xffffffffu, l_ < 0.0));
+            }
+            side = (npos <= nneg) ? 1 : -1;
           }
-          const int side = (npos <= nneg) ? 1 : -1;
           int cnt = 0;
           for (int base = 0; base < NP; base += 32) {
             const int i = base + lane;
             const double l_ = (i < NP) ? lam[i] : 0.0;
-            const bool pred = (side > 0) ? (l_ > 0.0) : (l_ < 0.0);
+            const bool pred = (i < NP) && !jskip[i < NP ? i : 0] && ((side > 0) ? (l_ > 0.0) : (l_ < 0.0));
             const unsigned bal = __ballot_sync(0xffffffffu, pred);
             if (pred) {
               const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
@@ -631,12 +662,13 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
 #endif
         __syncthreads();
 #if OMC_USE_TMA
-        if (tid == 0) {
-          bulk_s2g(Qg[b], buf1, qbytes);
+        if (fits && tid == 0) {
+          bulk_s2g(Qg[b], B1, qbytes);
           bulk_commit();
         }
 #else
-        for (int e = tid; e < NP * ld; e += NT) Qg[b][e] = buf1[e];
+        if (fits)
+          for (int e = tid; e < NP * ld; e += NT) Qg[b][e] = B1[e];
 #endif
         // Z = sum_{i in side} |lam_i| q_i q_i' on lower tiles; s+ = Z (positive side) or V + Z (negative side)
         {
@@ -653,8 +685,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
             while (rt * (rt + 1) / 2 > tl) --rt;
             const int ct = tl - rt * (rt + 1) / 2;
             double c0 = 0.0, c1 = 0.0;
-            const double* arow = buf1 + (size_t)(rt * 8 + g_) * ld;
-            const double* brow = buf1 + (size_t)(ct * 8 + g_) * ld;
+            const double* arow = B1 + (size_t)(rt * 8 + g_) * ld;
+            const double* brow = B1 + (size_t)(ct * 8 + g_) * ld;
             for (int kk = 0; kk < KS; ++kk) {
               const int col = idx[kk * 4 + t_];
               const double a_ = arow[col] * wgt[kk * 4 + t_];
@@ -677,7 +709,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           }
         }
 #if OMC_USE_TMA
-        if (tid == 0) bulk_wait_all();
+        if (fits && tid == 0) bulk_wait_all();
 #endif
         __syncthreads();
         OMC_TICK(4)
@@ -775,8 +807,6 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           rpc[q] = block_max(rpc[q], red);
           rp = fmax(rp, rpc[q]);
         }
-        if (P.prof && tid == 0)
-          for (int q = 0; q < 7; ++q) P.prof[(size_t)node * 16 + 8 + q] = rpc[q];
         rd = block_max(rd, red);
         np_ = block_max(np_, red);
         nd_ = block_max(nd_, red);
@@ -877,8 +907,9 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
 // shared memory bytes the kernel carves up (must mirror the carve-up above)
 inline size_t relax_smem_bytes(int n, int m, int k, int Lcap, int rmax) {
   Geo g1 = make_geo(n + m);
+  Geo gf = smem_geo(n + m, n + k, n);
   size_t d = 0;
-  d += 2 * (size_t)g1.NP * g1.ld;        // buf0, buf1
+  d += 2 * (size_t)gf.NP * gf.ld;        // buf0, buf1
   d += 2 * (size_t)g1.NP;                // lam, wgt
   d += 2 * (size_t)(g1.NP / 2);          // jcs, jsn
   d += 32;                               // red
@@ -887,7 +918,7 @@ inline size_t relax_smem_bytes(int n, int m, int k, int Lcap, int rmax) {
   d += (size_t)Lcap;                     // cxp (pointers, 8 bytes)
   d += 1;                                // mbar
   size_t bytes = d * 8;
-  bytes += sizeof(int) * (3 * ((size_t)g1.NP / 2) + g1.NP + 8);
+  bytes += sizeof(int) * (3 * ((size_t)g1.NP / 2) + 2 * (size_t)g1.NP + 8);
   return (bytes + 127) & ~(size_t)127;
 }
 

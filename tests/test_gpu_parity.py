@@ -189,3 +189,31 @@ def test_argument_validation_mirrors_reference_errors(omc):
         omc.Problem(1, A.T, mask.T, 80.0, "linear4")          # OMC.jl:218-224
     with pytest.raises(ValueError, match="Dimension mismatch"):
         omc.Problem(1, A.T, mask, 80.0)                       # OMC.jl:240-246
+
+
+def test_config4_shape_runs_through_the_l2_resident_block_path(omc):
+    """BASELINE config 4 shape (k=3, 100x100, linear3): the (n+m) = 200 PSD block does not fit one SM's shared
+    memory and is diagonalised in an L2-resident buffer by the same device code.  Fixed-iteration trajectory vs the
+    oracle, then a full solve whose returned point must be feasible and whose certified bound must not exceed it."""
+    from oracle import relaxation as R
+    from oracle.datagen import config_instance
+    k, A, mask, g = config_instance("C4", 0)
+    p = omc.Problem(k, A, mask, g, "linear3")
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(100); x /= np.linalg.norm(x); Uh = 0.2 * rng.standard_normal((100, 3))
+    cid = p.add_cut(x, Uh)
+    dirs = ["inner_left", "right", "left"]
+    for cuts_g, cuts_o in (([], []), ([omc.Cut(cid, x, Uh, dirs)], [(x, Uh, dirs)])):
+        r = p.relax_batch([cuts_g], omc.default_opts(eps_abs=1e-30, eps_rel=1e-30, max_iter=20, adapt_every=0, jacobi_tol=1e-13))[0]
+        ro = R.solve_relaxation(A, mask, g, k, "linear3", cuts_o, opts=R.Options(eps_abs=1e-30, eps_rel=1e-30, max_iter=20, adaptive_rho=False))
+        assert np.abs(r["X"] - ro["X"]).max() < 1e-8 and np.abs(r["Y"] - ro["Y"]).max() < 1e-8 and np.abs(r["U"] - ro["U"]).max() < 1e-8
+    full = p.relax_batch([[]], omc.default_opts(max_iter=4000))[0]
+    assert full["termination_status"] == "OPTIMAL"
+    X, Y, U = full["X"], full["Y"], full["U"]
+    assert np.linalg.eigvalsh(np.eye(100) - Y).min() >= -1e-6 and np.trace(Y) <= k + 1e-6 and np.linalg.eigvalsh(Y).min() >= -1e-6
+    assert full["lower_bound"] <= full["objective"] * (1 + 1e-6)
+    am = omc.alternating_minimization(p, np.linalg.svd(np.where(mask, A, 0.0))[0][:, :k])
+    assert full["objective"] <= p.objective_mse(am["U"] @ am["V"])[0] * (1 + 1e-9)      # bound <= a feasible rank-k value
+    lam, vec, bp, feas = omc.smallest_eigvecs_batch(Y, U, 2)                            # config 4 uses smallest_2_eigvec
+    assert lam[0, 0] <= lam[0, 1] and abs(np.linalg.norm(vec[0, :, 0]) - 1) < 1e-10
+    p.close()
