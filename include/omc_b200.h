@@ -66,7 +66,8 @@ typedef struct omc_relax_opts {
   double time_limit_s;     /* per call; <= 0 disables                                      */
   double jacobi_tol;       /* cap of the eigensolver's relative off-diagonal tolerance (it tightens with the ADMM residual) */
   int32_t reortho_every;   /* restart the eigenvector basis from I every this many iterations (0 = never) */
-  int32_t reserved;
+  int32_t exact_projection; /* 0 (default): warm-started low-rank tracking of the minority spectral side, every termination
+                               decision confirmed by an exact projection; 1: full eigendecomposition at every iteration */
 } omc_relax_opts;
 
 /* ---- library / device ------------------------------------------------------------------------ */
@@ -111,10 +112,11 @@ int32_t omc_frontier_relax(omc_frontier* f, const omc_relax_opts* opts, float* k
  * res[2*b] / res[2*b+1] = primal / dual residual.                                                       */
 int32_t omc_frontier_fetch(omc_frontier* f, int32_t* status, double* objective, double* lower_bound,
                            int32_t* iters, double* res, double* X, double* Y, double* U, double* Theta);
-/* per-node kernel profile: prof[16*b + q], q = 0..5 SM cycles spent in (w-update + dense rows, assembling V,
- * DMMA pre-rotation, Jacobi sweeps, reconstruction + dual update, residual checks), 6 = Jacobi sweeps,
- * 7 = iterations, 8..14 = primal residual per constraint family at the last check
- * (psd1, psd2, psd3, trace, box, cut v rows, cut aggregated rows) */
+/* per-node kernel profile: prof[32*b + q], q = 0..5 SM cycles spent in (w-update + dense rows, assembling V,
+ * DMMA pre-rotation or low-rank tracking step, Jacobi sweeps of the full solver, reconstruction + dual update,
+ * residual checks), 6 = Jacobi sweeps, 7 = iterations, 8..13 = full-solver rotation statistics,
+ * 14 / 15 = projections done by the low-rank tracker / by the full solver,
+ * 16..23 = cycles in the sub-phases of the tracking step (V Z, residual, CholQR2, V R~, Gram, Jacobi, select + combine) */
 int32_t omc_frontier_fetch_profile(omc_frontier* f, double* prof);
 int32_t omc_frontier_destroy(omc_frontier* f);
 /* convenience = create + relax + fetch + destroy (host buffers in, host buffers out) */

@@ -22,7 +22,7 @@ class RelaxOpts(C.Structure):
         ("fix_linear3_right", C.c_int32),
         ("rho0", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
         ("cutoff", C.c_double), ("time_limit_s", C.c_double), ("jacobi_tol", C.c_double),
-        ("reortho_every", C.c_int32), ("reserved", C.c_int32),
+        ("reortho_every", C.c_int32), ("exact_projection", C.c_int32),
     ]
 
 

@@ -550,7 +550,8 @@ int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_p
   f->grid = g_sm_count * ctas_per_sm;
   if (f->grid > B) f->grid = B;
   f->SC = omc::make_scratch_layout(p->SL, f->rmax);
-  f->smem = omc::relax_smem_bytes(p->n, p->m, p->k, p->Lcap, f->rmax);
+  f->smem = (f->variant == 0) ? omc::relax_smem_bytes<8>(p->n, p->m, p->k, p->Lcap, f->rmax)
+                              : omc::relax_smem_bytes<16>(p->n, p->m, p->k, p->Lcap, f->rmax);
   cudaError_t e;
 #define FC(call)                                                                \
   do {                                                                          \
@@ -569,7 +570,7 @@ int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_p
   FC(f->Y.alloc((size_t)B * p->n * p->n));
   FC(f->U.alloc((size_t)B * p->n * p->k));
   FC(f->scratch.alloc((size_t)f->grid * f->SC.total));
-  FC(f->prof.alloc((size_t)B * 16));
+  FC(f->prof.alloc((size_t)B * OMC_PROF_STRIDE));
   FC(cudaMemcpyAsync(f->cut_ptr.p, node_cut_ptr, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, g_stream));
   if (E > 0) {
     FC(cudaMemcpyAsync(f->cut_ids.p, node_cut_ids, E * sizeof(int), cudaMemcpyHostToDevice, g_stream));
@@ -619,19 +620,19 @@ int32_t omc_frontier_relax(omc_frontier* f, const omc_relax_opts* opts, float* k
   CU(cudaMemsetAsync(f->queue.p, 0, sizeof(int), g_stream));
   CU(cudaEventRecord(f->ev0, g_stream));
   if (f->variant == 0) {
-    auto kern = omc::omc_relax_kernel<128, 8, 4>;
+    auto kern = omc::omc_relax_kernel<128, 8, 4, 8>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
     kern<<<f->grid, 128, f->smem, g_stream>>>(a);
   } else if (f->variant == 1) {
-    auto kern = omc::omc_relax_kernel<256, 16, 2>;
+    auto kern = omc::omc_relax_kernel<256, 16, 2, 16>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
     kern<<<f->grid, 256, f->smem, g_stream>>>(a);
   } else if (f->variant == 2) {
-    auto kern = omc::omc_relax_kernel<512, 26, 1>;
+    auto kern = omc::omc_relax_kernel<512, 26, 1, 16>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
     kern<<<f->grid, 512, f->smem, g_stream>>>(a);
   } else {  // (n+m) block in L2-resident buffers: 256 threads so that a 52-deep DMMA panel fits in registers
-    auto kern = omc::omc_relax_kernel<256, 52, 1>;
+    auto kern = omc::omc_relax_kernel<256, 52, 1, 16>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem));
     kern<<<f->grid, 256, f->smem, g_stream>>>(a);
   }
@@ -664,7 +665,7 @@ int32_t omc_frontier_fetch(omc_frontier* f, int32_t* status, double* objective, 
 int32_t omc_frontier_fetch_profile(omc_frontier* f, double* prof) {
   NEED_INIT();
   if (!f || !prof) return fail(OMC_ERR_ARG, "null argument");
-  CU(cudaMemcpyAsync(prof, f->prof.p, (size_t)f->B * 16 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CU(cudaMemcpyAsync(prof, f->prof.p, (size_t)f->B * OMC_PROF_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CU(cudaStreamSynchronize(g_stream));
   return OMC_OK;
 }

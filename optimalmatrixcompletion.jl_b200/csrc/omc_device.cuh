@@ -46,6 +46,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                    smem_u32(smem_dst)),
@@ -99,6 +100,29 @@ __device__ __forceinline__ double block_max(double v, double* scratch) {
   r = warp_max(r);
   return r;
 }
+
+// In-place Gauss-Jordan inversion of the SPD r x r matrix M (leading dimension r), no pivoting.
+__device__ inline void spd_invert(double* M, int r) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int p = 0; p < r; ++p) {
+    __syncthreads();
+    const double inv = 1.0 / M[(size_t)p * r + p];
+    __syncthreads();
+    for (int j = tid; j < r; j += nt)
+      if (j != p) M[(size_t)p * r + j] *= inv;
+    __syncthreads();
+    for (int e = tid; e < r * r; e += nt) {
+      const int i = e / r, j = e - i * r;
+      if (i != p && j != p) M[e] -= M[(size_t)i * r + p] * M[(size_t)p * r + j];
+    }
+    __syncthreads();
+    for (int i = tid; i < r; i += nt)
+      if (i != p) M[(size_t)i * r + p] *= -inv;
+    if (tid == 0) M[(size_t)p * r + p] = inv;
+  }
+  __syncthreads();
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // Geometry of one symmetric block held in shared memory: N real rows, NP = N rounded up to 8 (DMMA

@@ -8,6 +8,7 @@
 // spectral side); the ADMM state of the node lives in an L2-resident global record.
 #pragma once
 #include "omc_device.cuh"
+#include "omc_lowrank.cuh"
 #include "../../include/omc_b200.h"
 
 namespace omc {
@@ -50,6 +51,8 @@ __host__ __device__ inline StateLayout make_state_layout(int n, int m, int k, in
 // Largest PSD block that is diagonalised in shared memory (two NP x ld FP64 buffers must fit in 227 KB):
 // blocks with NP > OMC_SMEM_NP_MAX run through the same device functions on an L2-resident global buffer.
 #define OMC_SMEM_NP_MAX 104
+#define OMC_PROF_STRIDE 32  // doubles of per-node profile counters (omc_frontier_fetch_profile)
+#define OMC_XS_CAP 3072  // doubles of shared memory reserved for a node's cut vectors (L * n <= 3072 are cached)
 __host__ __device__ inline Geo smem_geo(int N1, int N2, int N3) {
   Geo best = make_geo(1);
   const int Ns[3] = {N1, N2, N3};
@@ -61,7 +64,7 @@ __host__ __device__ inline Geo smem_geo(int N1, int N2, int N3) {
 }
 
 struct ScratchLayout {
-  size_t wt, Q1, Q2, Q3, G, Minv, state, big0, total;
+  size_t wt, Q1, Q2, Q3, Z1, Z2, Z3, G, Minv, state, big0, total;
 };
 __host__ __device__ inline ScratchLayout make_scratch_layout(const StateLayout& S, int rmax) {
   ScratchLayout C;
@@ -72,8 +75,12 @@ __host__ __device__ inline ScratchLayout make_scratch_layout(const StateLayout& 
   C.Q1 = o; o += (size_t)g1.NP * g1.ld;
   C.Q2 = o; o += (size_t)g2.NP * g2.ld;
   C.Q3 = o; o += (size_t)g3.NP * g3.ld;
-  C.G = o; o += (size_t)rmax * rmax;
-  C.Minv = o; o += (size_t)rmax * rmax;
+  C.Z1 = o; o += (size_t)g1.NP * 16;   // tracked minority-side bases (low-rank projection), NP x 16 row-major
+  C.Z2 = o; o += (size_t)g2.NP * 16;
+  C.Z3 = o; o += (size_t)g3.NP * 16;
+  o = (o + 1) & ~(size_t)1;
+  C.G = o; o += ((size_t)rmax * rmax + 1) & ~(size_t)1;      // 16-byte aligned: re-read by TMA bulk copies
+  C.Minv = o; o += ((size_t)rmax * rmax + 1) & ~(size_t)1;
   o = (o + 1) & ~(size_t)1;
   C.state = o; o += S.total;
   o = (o + 1) & ~(size_t)1;
@@ -180,25 +187,27 @@ __device__ __forceinline__ double w_entry(const NodeCtx& c, int b, int r, int co
   return ((r == col) ? c.a : 0.0) - c.Y[(size_t)r * n + col];
 }
 
-// ---- dense rows R (trace row, cut rows) applied to (Yt, Ut): rhs = R [Yt; Ut] ------------------
-__device__ __noinline__ void dense_rows_apply(const NodeCtx& c, const double* Yp, const double* Up, double* out,
+// ---- dense rows R (trace row, cut rows) applied to (Y, U): out = R [Y; U] -------------------------------------
+// Ys: FULL symmetric n x n with leading dimension ldy in shared memory; Up: n x k column-major (shared or global).
+__device__ __noinline__ void dense_rows_apply(const NodeCtx& c, const double* Ys, int ldy, const double* Up, double* out,
                                               double* scratch) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int n = c.n, k = c.k, L = c.L;
   double tr = 0.0;
-  for (int i = tid; i < n; i += nt) tr += Yp[(size_t)i * n + i];
+  for (int i = tid; i < n; i += nt) tr += Ys[(size_t)i * ldy + i];
   tr = block_sum(tr, scratch);
   if (tid == 0) out[0] = tr;
-  // one warp per cut: xv[l,j] = x_l' Ut[:,j], q_l = x_l' Yt x_l (lower triangle, doubled off-diagonal)
+  // one warp per cut: xv[l,j] = x_l' U[:,j], q_l = x_l' Y x_l (lanes own rows of Y)
   for (int l = warp; l < L; l += nw) {
     const double* x = c.cx[l];
     double q = 0.0;
-    for (int e = lane; e < n * n; e += 32) {
-      const int i = e / n, j = e - i * n;
-      if (j <= i) {
-        const double y = Yp[(size_t)i * n + j];
-        q += ((i == j) ? 1.0 : 2.0) * x[i] * x[j] * y;
-      }
+    for (int i = lane; i < n; i += 32) {
+      const double* yr = Ys + (size_t)i * ldy;
+      double t0 = 0.0, t1 = 0.0;
+      int j = 0;
+      for (; j + 1 < n; j += 2) { t0 += yr[j] * x[j]; t1 += yr[j + 1] * x[j + 1]; }
+      if (j < n) t0 += yr[j] * x[j];
+      q += x[i] * (t0 + t1);
     }
     q = warp_sum(q);
     double agg = 0.0;
@@ -214,28 +223,6 @@ __device__ __noinline__ void dense_rows_apply(const NodeCtx& c, const double* Yp
   __syncthreads();
 }
 
-// In-place Gauss-Jordan inversion of the SPD r x r matrix M (leading dimension r), no pivoting.
-__device__ inline void spd_invert(double* M, int r) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int p = 0; p < r; ++p) {
-    __syncthreads();
-    const double inv = 1.0 / M[(size_t)p * r + p];
-    __syncthreads();
-    for (int j = tid; j < r; j += nt)
-      if (j != p) M[(size_t)p * r + j] *= inv;
-    __syncthreads();
-    for (int e = tid; e < r * r; e += nt) {
-      const int i = e / r, j = e - i * r;
-      if (i != p && j != p) M[e] -= M[(size_t)i * r + p] * M[(size_t)p * r + j];
-    }
-    __syncthreads();
-    for (int i = tid; i < r; i += nt)
-      if (i != p) M[(size_t)i * r + p] *= -inv;
-    if (tid == 0) M[(size_t)p * r + p] = inv;
-  }
-  __syncthreads();
-}
-
 // Minv = ((sigma + 3 rho)/rho I + G)^-1, inverted in shared memory when it fits, else in place in global
 __device__ inline void build_minv(const NodeCtx& c, double* smem_work, size_t smem_cap) {
   const int tid = threadIdx.x, nt = blockDim.x, r = c.r;
@@ -246,10 +233,22 @@ __device__ inline void build_minv(const NodeCtx& c, double* smem_work, size_t sm
   spd_invert(W, r);
   if (W != c.Minv)
     for (int e = tid; e < r * r; e += nt) c.Minv[e] = W[e];
+#if OMC_USE_TMA
+  fence_proxy_async_global();  // G and Minv are re-read through TMA bulk copies every iteration
+#endif
   __syncthreads();
 }
 
-template <int NT, int KMAX, int MINB>
+// doubles of the second shared-memory region: the eigenvector matrix of the full solver, or the three panels and the
+// small matrices of the low-rank projection
+template <int PM>
+__host__ __device__ inline size_t region1_doubles(const Geo& gfit) {
+  const size_t full = (size_t)gfit.NP * gfit.ld;
+  const size_t lr = 3 * (size_t)gfit.NP * OMC_LR_LDZ + (sizeof(LrSmall<PM>) + 7) / 8 + 2;
+  return ((full > lr ? full : lr) + 1) & ~(size_t)1;
+}
+
+template <int NT, int KMAX, int MINB, int PM>
 __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
@@ -264,7 +263,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
   // ---- shared memory carve-up
   double* buf0 = reinterpret_cast<double*>(smem_raw);
   double* buf1 = buf0 + bufsz;
-  double* lam = buf1 + bufsz;              // [NP1]
+  const size_t bufsz1 = region1_doubles<PM>(gfit);
+  double* lam = buf1 + bufsz1;             // [NP1]
   double* wgt = lam + g1.NP;               // [NP1]
   double* jcs = wgt + g1.NP;               // [NP1/2]
   double* jsn = jcs + g1.NP / 2;           // [NP1/2]
@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
   double* cub = clb + P.Lcap * k;
   double* cal = cub + P.Lcap * k;
   double* cbe = cal + P.Lcap * k;          // [Lcap]
-  const double** cxp = reinterpret_cast<const double**>(cbe + P.Lcap);  // [Lcap]
+  double* tgs = cbe + P.Lcap;              // [Lcap]  rho (beta - sg) + mg of the aggregated rows, refreshed every iteration
+  double* xs = tgs + P.Lcap;               // [OMC_XS_CAP] shared-memory copies of the node's cut vectors (when they fit)
+  const double** cxp = reinterpret_cast<const double**>(xs + OMC_XS_CAP);  // [Lcap]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(cxp + P.Lcap);           // [1]
   int* jrot = reinterpret_cast<int*>(mbar + 1);                         // [3*NP1/2]
   int* idx = jrot + 3 * (g1.NP / 2);                                    // [NP1]
@@ -304,6 +306,12 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
   c.G = scr + P.SC.G; c.Minv = scr + P.SC.Minv;
   c.cx = cxp; c.lb = clb; c.ub = cub; c.al = cal; c.be = cbe; c.rhs = rhs; c.cw = cw; c.gc = gc;
   double* Qg[3] = {scr + P.SC.Q1, scr + P.SC.Q2, scr + P.SC.Q3};
+  double* Zg[3] = {scr + P.SC.Z1, scr + P.SC.Z2, scr + P.SC.Z3};
+  // low-rank projection workspace inside region 1 (panels first, then the small matrices)
+  double* lrZ = buf1;
+  double* lrR = lrZ + (size_t)gfit.NP * OMC_LR_LDZ;
+  double* lrW = lrR + (size_t)gfit.NP * OMC_LR_LDZ;
+  LrSmall<PM>& lrS = *reinterpret_cast<LrSmall<PM>*>(lrW + (size_t)gfit.NP * OMC_LR_LDZ);
   double* sb[3] = {c.s1, c.s2, c.s3};
   double* mb[3] = {c.m1, c.m2, c.m3};
   const Geo gb[3] = {g1, g2, g3};
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
     if (node >= P.B) break;
     if (tid == 0) ish[3] = 0;
     if (P.prof)
-      for (int q = tid; q < 16; q += NT) P.prof[(size_t)node * 16 + q] = 0.0;
+      for (int q = tid; q < OMC_PROF_STRIDE; q += NT) P.prof[(size_t)node * OMC_PROF_STRIDE + q] = 0.0;
 
     const int e0 = P.node_cut_ptr[node], L = P.node_cut_ptr[node + 1] - e0;
     const int r = 1 + L * (k + 1);
@@ -329,7 +337,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
     // ---- cut rows (scaled): lb, ub, alpha per column, beta summed over columns
     for (int l = tid; l < L; l += NT) {
       const int cid = P.node_cut_ids[e0 + l];
-      cxp[l] = P.pool_x + (size_t)cid * n;
+      cxp[l] = ((size_t)L * n <= OMC_XS_CAP) ? (const double*)(xs + (size_t)l * n) : (P.pool_x + (size_t)cid * n);
       double bsum = 0.0;
       for (int j = 0; j < k; ++j) {
         double lb, ub, al, be;
@@ -342,6 +350,13 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
     }
     __syncthreads();
 
+    if ((size_t)L * n <= OMC_XS_CAP) {
+      for (int e = tid; e < L * n; e += NT) {
+        const int l = e / n, i = e - l * n;
+        xs[e] = P.pool_x[(size_t)P.node_cut_ids[e0 + l] * n + i];
+      }
+      __syncthreads();
+    }
     // ---- initial state: cold (zeros, s = b) or the parent's record
     int Lw = 0;  // number of cut rows carried by the warm-start record
     if (warm >= 0) {
@@ -427,6 +442,13 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
     }
 
     bool have_basis[3] = {false, false, false};
+    int lr_mode[3] = {0, 0, 0};      // 1: the block's minority side is tracked by the low-rank projection
+    int lr_p[3] = {0, 0, 0};         // columns of the tracked basis
+    int lr_side[3] = {1, 1, 1};      // +1: positive side of V tracked, -1: negative side
+    bool exact_iter = false;         // this iteration runs exact (full) projections on every block
+    bool force_check = false;        // check residuals right after this iteration
+    long long n_lr = 0, n_full = 0;
+    long long lpc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles in the sub-phases of the low-rank step
     // Eigensolver tolerance follows the ADMM residual: off(S) <= jtol ||S||_F with jtol two orders below the
     // current relative residual, inside [1e-13, jacobi_tol].
     double jtol = P.o.jacobi_tol;
@@ -447,77 +469,177 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
       const double rho = c.rho, sig = c.sigma, al = c.alpha;
       const double dYU = sig + 3.0 * rho, dT = sig + rho;
       const double t4 = c.scal[1] + rho * (c.ktr - c.scal[0]);
+      // shared-memory views that live through phases 1-2 only: Y~ (full symmetric, n x ldy) and U~ in region 0, the
+      // Woodbury inverse and the Gram matrix of the dense rows in region 1 (TMA bulk copies, overlapped with phase 1)
+      const int ldy = n | 1;
+      double* Ys = buf0;
+      double* Us = buf0 + (size_t)n * ldy;
+      const size_t r2p = ((size_t)r * r + 1) & ~(size_t)1;
+      const bool ms_smem = 2 * r2p <= bufsz1;
+      const double* Ms = ms_smem ? buf1 : c.Minv;
+      const double* Gs = ms_smem ? buf1 + r2p : c.G;
+#if OMC_USE_TMA
+      if (ms_smem && tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(mbar, (uint32_t)(2 * r2p * sizeof(double)));
+        bulk_g2s(buf1, c.Minv, (uint32_t)(r2p * sizeof(double)), mbar);
+        bulk_g2s(buf1 + r2p, c.G, (uint32_t)(r2p * sizeof(double)), mbar);
+      }
+#else
+      if (ms_smem)
+        for (int e = tid; e < (int)r2p; e += NT) { buf1[e] = c.Minv[e]; buf1[r2p + e] = c.G[e]; }
+#endif
+      for (int l = tid; l < L; l += NT) tgs[l] = c.mg[l] + rho * (cbe[l] - c.sg[l]);
+      __syncthreads();
       // ------------------------------------------------ phase 1: w~ = D^-1 (sigma w - q + A'(rho (b - s) + mu))
-      for (int e = tid; e < n * m; e += NT) {  // X, e = i + n j
-        const int i = e % n, j = e / n;
-        const size_t q1 = (size_t)(n + j) * SL.N1 + i;
-        const double t1 = c.m1[q1] - rho * c.s1[q1];
-        const double mk = c.Mk[e];
-        c.Xt[e] = (sig * c.X[e] + mk * c.A[e] - 2.0 * t1) / (mk + sig + 2.0 * rho);
-      }
-      for (int e = tid; e < n * n; e += NT) {  // Y lower, e = i*n + j
-        const int i = e / n, j = e - i * n;
-        if (j > i) continue;
-        const size_t q1 = (size_t)i * SL.N1 + j, q2 = (size_t)i * SL.N2 + j;
-        const double t1 = c.m1[q1] - rho * c.s1[q1];
-        const double t2 = c.m2[q2] - rho * c.s2[q2];
-        const double t3 = c.m3[e] + rho * (((i == j) ? c.a : 0.0) - c.s3[e]);
-        double gY = -t1 - t2 + t3 + ((i == j) ? t4 : 0.0);
-        for (int l = 0; l < L; ++l) {
-          const double tg = c.mg[l] + rho * (cbe[l] - c.sg[l]);
-          gY += tg * cxp[l][i] * cxp[l][j];
+      // (loads of a batch are issued before any of its stores: the state record lives in L2)
+      {
+        constexpr int UB = 4;
+        const int nm = n * m;
+        for (int e0 = tid; e0 < nm; e0 += NT * UB) {  // X, e = i + n j : w~ and the relaxed w in one pass
+          double vm[UB], vs[UB], vk[UB], vx[UB], va[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int e = e0 + u * NT;
+            if (e < nm) {
+              const int j = e / n, i = e - j * n;
+              const size_t q1 = (size_t)(n + j) * SL.N1 + i;
+              vm[u] = __ldcg(c.m1 + q1); vs[u] = __ldcg(c.s1 + q1); vk[u] = __ldg(c.Mk + e); vx[u] = __ldcg(c.X + e); va[u] = __ldg(c.A + e);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int e = e0 + u * NT;
+            if (e < nm) {
+              const double t1 = vm[u] - rho * vs[u];
+              const double xt = (sig * vx[u] + vk[u] * va[u] - 2.0 * t1) / (vk[u] + sig + 2.0 * rho);
+              c.Xt[e] = xt;
+              c.X[e] = al * xt + (1.0 - al) * vx[u];
+            }
+          }
         }
-        c.Yt[e] = (sig * c.Y[e] + gY) / dYU;
-      }
-      for (int e = tid; e < m * m; e += NT) {  // Theta lower
-        const int i = e / m, j = e - i * m;
-        if (j > i) continue;
-        const size_t q1 = (size_t)(n + i) * SL.N1 + (n + j);
-        const double t1 = c.m1[q1] - rho * c.s1[q1];
-        c.Tt[e] = (sig * c.T[e] - ((i == j) ? c.cT : 0.0) - t1) / dT;
-      }
-      for (int e = tid; e < n * k; e += NT) {  // U, e = i + n j
-        const int i = e % n, j = e / n;
-        const size_t q2 = (size_t)(n + j) * SL.N2 + i;
-        const double t2 = c.m2[q2] - rho * c.s2[q2];
-        const double t5 = c.m5[e] - rho * c.s5[e];
-        double gU = -2.0 * t2 - t5;
-        for (int l = 0; l < L; ++l) {
-          const double tv = c.mv[l * k + j] - rho * c.sv[l * k + j];
-          const double tg = c.mg[l] + rho * (cbe[l] - c.sg[l]);
-          gU -= cxp[l][i] * (tv + tg * cal[l * k + j]);
+        const int nlt = m * (m + 1) / 2;
+        for (int e0 = tid; e0 < nlt; e0 += NT * UB) {  // Theta, lower triangle by linear index
+          double vm[UB], vs[UB], vt[UB];
+          int ix[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int e = e0 + u * NT;
+            if (e < nlt) {
+              int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+              while ((i + 1) * (i + 2) / 2 <= e) ++i;
+              while (i * (i + 1) / 2 > e) --i;
+              const int j = e - i * (i + 1) / 2;
+              const size_t q1 = (size_t)(n + i) * SL.N1 + (n + j);
+              ix[u] = i * m + j;
+              vm[u] = __ldcg(c.m1 + q1); vs[u] = __ldcg(c.s1 + q1); vt[u] = __ldcg(c.T + ix[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int e = e0 + u * NT;
+            if (e < nlt) {
+              const int i = ix[u] / m, j = ix[u] - i * m;
+              const double t1 = vm[u] - rho * vs[u];
+              const double tt = (sig * vt[u] - ((i == j) ? c.cT : 0.0) - t1) / dT;
+              c.Tt[ix[u]] = tt;
+              c.T[ix[u]] = al * tt + (1.0 - al) * vt[u];
+            }
+          }
         }
-        c.Ut[e] = (sig * c.U[e] + gU) / dYU;
+        const int nly = n * (n + 1) / 2;
+        for (int e0 = tid; e0 < nly; e0 += NT * UB) {  // Y lower -> Ys (both triangles), before the dense-row correction
+          double v1m[UB], v1s[UB], v2m[UB], v2s[UB], v3m[UB], v3s[UB], vy[UB];
+          int ii[UB], jj[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int e = e0 + u * NT;
+            if (e < nly) {
+              int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+              while ((i + 1) * (i + 2) / 2 <= e) ++i;
+              while (i * (i + 1) / 2 > e) --i;
+              const int j = e - i * (i + 1) / 2;
+              ii[u] = i; jj[u] = j;
+              const size_t q1 = (size_t)i * SL.N1 + j, q2 = (size_t)i * SL.N2 + j, q3 = (size_t)i * n + j;
+              v1m[u] = __ldcg(c.m1 + q1); v1s[u] = __ldcg(c.s1 + q1);
+              v2m[u] = __ldcg(c.m2 + q2); v2s[u] = __ldcg(c.s2 + q2);
+              v3m[u] = __ldcg(c.m3 + q3); v3s[u] = __ldcg(c.s3 + q3);
+              vy[u] = __ldcg(c.Y + q3);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int e = e0 + u * NT;
+            if (e < nly) {
+              const int i = ii[u], j = jj[u];
+              const double t1 = v1m[u] - rho * v1s[u];
+              const double t2 = v2m[u] - rho * v2s[u];
+              const double t3 = v3m[u] + rho * (((i == j) ? c.a : 0.0) - v3s[u]);
+              double gY = -t1 - t2 + t3 + ((i == j) ? t4 : 0.0);
+              for (int l = 0; l < L; ++l) gY += tgs[l] * cxp[l][i] * cxp[l][j];
+              const double yt = (sig * vy[u] + gY) / dYU;
+              Ys[(size_t)i * ldy + j] = yt;
+              Ys[(size_t)j * ldy + i] = yt;
+            }
+          }
+        }
+        for (int e = tid; e < n * k; e += NT) {  // U, e = i + n j -> Us
+          const int i = e % n, j = e / n;
+          const size_t q2 = (size_t)(n + j) * SL.N2 + i;
+          const double t2 = c.m2[q2] - rho * c.s2[q2];
+          const double t5 = c.m5[e] - rho * c.s5[e];
+          double gU = -2.0 * t2 - t5;
+          for (int l = 0; l < L; ++l) {
+            const double tv = c.mv[l * k + j] - rho * c.sv[l * k + j];
+            gU -= cxp[l][i] * (tv + tgs[l] * cal[l * k + j]);
+          }
+          Us[e] = (sig * c.U[e] + gU) / dYU;
+        }
       }
       __syncthreads();
       // ------------------------------------------------ phase 2: Woodbury correction for the dense rows
-      dense_rows_apply(c, c.Yt, c.Ut, rhs, red);
-      for (int i = tid; i < r; i += NT) {
+      dense_rows_apply(c, Ys, ldy, Us, rhs, red);
+#if OMC_USE_TMA
+      if (ms_smem) {
+        mbar_wait(mbar, mbar_phase);
+        mbar_phase ^= 1;
+      }
+#endif
+      for (int i = warp; i < r; i += NW) {  // cw = Minv rhs : one warp per row
         double v = 0.0;
-        for (int j = 0; j < r; ++j) v += c.Minv[(size_t)i * r + j] * rhs[j];
-        cw[i] = v;
+        for (int j = lane; j < r; j += 32) v += Ms[(size_t)i * r + j] * rhs[j];
+        v = warp_sum(v);
+        if (lane == 0) cw[i] = v;
       }
       __syncthreads();
-      for (int i = tid; i < r; i += NT) {  // gc = G cw  ->  R w~(corrected) = rhs - gc
+      for (int i = warp; i < r; i += NW) {  // gc = G cw  ->  R w~(corrected) = rhs - gc
         double v = 0.0;
-        for (int j = 0; j < r; ++j) v += c.G[(size_t)i * r + j] * cw[j];
-        gc[i] = v;
+        for (int j = lane; j < r; j += 32) v += Gs[(size_t)i * r + j] * cw[j];
+        v = warp_sum(v);
+        if (lane == 0) gc[i] = v;
       }
       // w~ -= R' cw ; then w <- alpha w~ + (1-alpha) w
-      for (int e = tid; e < n * n; e += NT) {
-        const int i = e / n, j = e - i * n;
-        if (j > i) continue;
-        double corr = (i == j) ? cw[0] : 0.0;
-        for (int l = 0; l < L; ++l) corr += cw[1 + L * k + l] * cxp[l][i] * cxp[l][j];
-        const double yt = c.Yt[e] - corr;
-        c.Yt[e] = yt;
-        c.Y[e] = al * yt + (1.0 - al) * c.Y[e];
+      {
+        const int nly = n * (n + 1) / 2;
+        for (int e = tid; e < nly; e += NT) {
+          int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+          while ((i + 1) * (i + 2) / 2 <= e) ++i;
+          while (i * (i + 1) / 2 > e) --i;
+          const int j = e - i * (i + 1) / 2;
+          const size_t q3 = (size_t)i * n + j;
+          const double yold = __ldcg(c.Y + q3);
+          double corr = (i == j) ? cw[0] : 0.0;
+          for (int l = 0; l < L; ++l) corr += cw[1 + L * k + l] * cxp[l][i] * cxp[l][j];
+          const double yt = Ys[(size_t)i * ldy + j] - corr;
+          c.Yt[q3] = yt;
+          c.Y[q3] = al * yt + (1.0 - al) * yold;
+        }
       }
       for (int e = tid; e < n * k; e += NT) {
         const int i = e % n, j = e / n;
         double corr = 0.0;
         for (int l = 0; l < L; ++l) corr -= cxp[l][i] * (cw[1 + l * k + j] + cw[1 + L * k + l] * cal[l * k + j]);
-        const double ut = c.Ut[e] - corr;
+        const double ut = Us[e] - corr;
         c.Ut[e] = ut;
         c.U[e] = al * ut + (1.0 - al) * c.U[e];
         // box rows
@@ -526,11 +648,6 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         const double s5n = fmin(fmax(v5, lo5), c.sa);
         c.s5[e] = s5n;
         c.m5[e] = rho * (v5 - s5n);
-      }
-      for (int e = tid; e < n * m; e += NT) c.X[e] = al * c.Xt[e] + (1.0 - al) * c.X[e];
-      for (int e = tid; e < m * m; e += NT) {
-        const int i = e / m, j = e - i * m;
-        if (j <= i) c.T[e] = al * c.Tt[e] + (1.0 - al) * c.T[e];
       }
       __syncthreads();
       // scalar rows: trace, cut v rows, cut aggregated rows  (z = b - R w~)
@@ -564,8 +681,9 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         const Geo g = gb[b];
         const int N = g.N, NP = g.NP, ld = g.ld;
         const uint32_t qbytes = (uint32_t)((size_t)NP * ld * sizeof(double));
-        const bool warmQ = have_basis[b] && !reortho;
         const bool fits = (size_t)NP * ld <= bufsz;             // else: L2-resident working buffers
+        const bool use_lr = fits && lr_mode[b] && !exact_iter && !P.o.exact_projection;
+        const bool warmQ = have_basis[b] && !reortho && !exact_iter && !use_lr;
         double* B0 = fits ? buf0 : (scr + P.SC.big0);
         double* B1 = fits ? buf1 : Qg[b];
         // start fetching the previous eigenvector basis while V is assembled
@@ -576,106 +694,209 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           bulk_g2s(B1, Qg[b], qbytes, mbar);
         }
 #endif
+        if (use_lr) {  // tracked basis -> panel (columns >= p are zero in the stored copy)
+          const double2* src = reinterpret_cast<const double2*>(Zg[b]);
+          for (int e = tid; e < NP * 8; e += NT) {
+            const int i = e >> 3, c2 = e & 7;
+            *reinterpret_cast<double2*>(lrZ + (size_t)i * OMC_LR_LDZ + 2 * c2) = __ldcg(src + e);
+          }
+        }
         // V = alpha z + (1-alpha) s + mu/rho, lower triangle computed, both triangles stored
         const double* sB = sb[b];
         const double* mB = mb[b];
         const double irho = 1.0 / rho;
-        for (int e = tid; e < NP * NP; e += NT) {
-          const int rr = e / NP, cc = e - rr * NP;
-          if (cc > rr) continue;
-          double v = 0.0;
-          if (rr < N) {
-            const size_t q = (size_t)rr * N + cc;
-            v = al * z_entry(c, b, rr, cc) + (1.0 - al) * sB[q] + mB[q] * irho;
+        double vsq = 0.0;
+        {
+          constexpr int UB = 4;
+          const int nl = N * (N + 1) / 2;
+          for (int e0 = tid; e0 < nl; e0 += NT * UB) {
+            double vz[UB], vs[UB], vm[UB];
+            int r_[UB], c_[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+              const int e = e0 + u * NT;
+              if (e < nl) {
+                int rr = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                while ((rr + 1) * (rr + 2) / 2 <= e) ++rr;
+                while (rr * (rr + 1) / 2 > e) --rr;
+                const int cc = e - rr * (rr + 1) / 2;
+                r_[u] = rr; c_[u] = cc;
+                const size_t q = (size_t)rr * N + cc;
+                vz[u] = z_entry(c, b, rr, cc);
+                vs[u] = __ldcg(sB + q);
+                vm[u] = __ldcg(mB + q);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+              const int e = e0 + u * NT;
+              if (e < nl) {
+                const double v = al * vz[u] + (1.0 - al) * vs[u] + vm[u] * irho;
+                B0[(size_t)r_[u] * ld + c_[u]] = v;
+                B0[(size_t)c_[u] * ld + r_[u]] = v;
+                vsq += ((r_[u] == c_[u]) ? 1.0 : 2.0) * v * v;
+              }
+            }
           }
-          B0[(size_t)rr * ld + cc] = v;
-          B0[(size_t)cc * ld + rr] = v;
+          const int npad = NP - N;   // zero padding rows / columns of the tile grid
+          for (int e = tid; e < npad * NP; e += NT) {
+            const int rr = N + e / NP, cc = e % NP;
+            B0[(size_t)rr * ld + cc] = 0.0;
+            B0[(size_t)cc * ld + rr] = 0.0;
+          }
         }
         OMC_TICK(1)
-        if (warmQ) {
-          if (fits) {
-#if OMC_USE_TMA
-            mbar_wait(mbar, mbar_phase);
-            mbar_phase ^= 1;
-#else
-            for (int e = tid; e < NP * ld; e += NT) B1[e] = Qg[b][e];
-#endif
-          }
+        bool lr_done = false;
+        double* lrOut = lrW;
+        if (use_lr) {
+          const double vscale = sqrt(block_sum(vsq, red));
           __syncthreads();
-          gemm_rows_inplace<KMAX>(B0, B1, NP, ld);  // W = V Q
-          gemm_cols_inplace<KMAX>(B0, B1, NP, ld);  // S = Q' W
-        } else {
-          for (int e = tid; e < NP * NP; e += NT) {
-            const int rr = e / NP, cc = e - rr * NP;
-            B1[(size_t)rr * ld + cc] = (rr == cc) ? 1.0 : 0.0;
+          const int need_full = lowrank_step<PM>(B0, ld, N, NP, (double)lr_side[b], lrZ, lrR, lrW, lr_p[b], lrS, vscale, P.prof ? lpc : nullptr, &lrOut);
+          ++n_lr;
+          OMC_TICK(2)
+          if (!need_full) {
+            lr_done = true;
+            const int pn = lrS.info[0], r_ = lrS.info[1];
+            lr_p[b] = pn;
+            // store the new basis (16 columns; columns >= pn zero) and set up the reconstruction
+            for (int e = tid; e < NP * 16; e += NT) {
+              const int i = e >> 4, j = e & 15;
+              Zg[b][e] = (j < pn) ? lrOut[(size_t)i * OMC_LR_LDZ + j] : 0.0;
+            }
+            if (tid < 16) {
+              idx[tid] = (tid < r_) ? tid : 0;
+              wgt[tid] = (tid < r_) ? lrS.th[tid] : 0.0;
+            }
+            if (tid == 0) {
+              ish[1] = (r_ + 3) & ~3;
+              ish[2] = lr_side[b];
+            }
+            __syncthreads();
+          } else {
+            lr_mode[b] = 0;          // minority side outgrew the panel: full solve on the intact V, cold basis
+            have_basis[b] = false;
+            __syncthreads();
           }
-          __syncthreads();
         }
-        OMC_TICK(2)
-        nsweeps += jacobi_sym(B0, B1, NP, ld, jtol, 40, jcs, jsn, jrot, red, 1, jskip, &ish[4],
-                              P.prof ? (P.prof + (size_t)node * 16 + 8 + 3 * (b == 0 ? 0 : 1)) : nullptr);
-        have_basis[b] = true;
-        OMC_TICK(3)
-        // eigenvalues, the smaller spectral side, compacted index list (warp 0)
-        for (int i = tid; i < NP; i += NT) lam[i] = B0[(size_t)i * ld + i];
-        __syncthreads();
-        if (warp == 0) {
-          // side to reconstruct: the one the eigensolver fully diagonalised (the other side's safe indices were
-          // skipped), or the smaller one when nothing was skipped
-          int side = -ish[4];
-          if (side == 0) {
-            int npos = 0, nneg = 0;
+        if (!lr_done) {
+          ++n_full;
+          const bool warm_now = warmQ && !use_lr;
+          if (warm_now) {
+            if (fits) {
+#if OMC_USE_TMA
+              mbar_wait(mbar, mbar_phase);
+              mbar_phase ^= 1;
+#else
+              for (int e = tid; e < NP * ld; e += NT) B1[e] = Qg[b][e];
+#endif
+            }
+            __syncthreads();
+            gemm_rows_inplace<KMAX>(B0, B1, NP, ld);  // W = V Q
+            gemm_cols_inplace<KMAX>(B0, B1, NP, ld);  // S = Q' W
+          } else {
+            __syncthreads();
+            for (int e = tid; e < NP * NP; e += NT) {
+              const int rr = e / NP, cc = e - rr * NP;
+              B1[(size_t)rr * ld + cc] = (rr == cc) ? 1.0 : 0.0;
+            }
+            __syncthreads();
+          }
+          OMC_TICK(2)
+          nsweeps += jacobi_sym(B0, B1, NP, ld, exact_iter ? fmin(jtol, 1e-10) : jtol, 40, jcs, jsn, jrot, red, 1, jskip, &ish[4],
+                                P.prof ? (P.prof + (size_t)node * OMC_PROF_STRIDE + 8 + 3 * (b == 0 ? 0 : 1)) : nullptr);
+          have_basis[b] = true;
+          OMC_TICK(3)
+          // eigenvalues, the smaller spectral side, compacted index list (warp 0)
+          for (int i = tid; i < NP; i += NT) lam[i] = B0[(size_t)i * ld + i];
+          __syncthreads();
+          if (warp == 0) {
+            // side to reconstruct: the one the eigensolver fully diagonalised (the other side's safe indices were
+            // skipped), or the smaller one when nothing was skipped
+            int side = -ish[4];
+            if (side == 0) {
+              int npos = 0, nneg = 0;
+              for (int base = 0; base < NP; base += 32) {
+                const int i = base + lane;
+                const double l_ = (i < NP) ? lam[i] : 0.0;
+                npos += __popc(__ballot_sync(0xffffffffu, l_ > 0.0));
+                nneg += __popc(__ballot_sync(0xffffffffu, l_ < 0.0));
+              }
+              side = (npos <= nneg) ? 1 : -1;
+            }
+            int cnt = 0;
             for (int base = 0; base < NP; base += 32) {
               const int i = base + lane;
               const double l_ = (i < NP) ? lam[i] : 0.0;
-              npos += __popc(__ballot_sync(0xffffffffu, l_ > 0.0));
-              nneg += __popc(__ballot_sync(0xffffffffu, l_ < 0.0));
+              const bool pred = (i < NP) && !jskip[i < NP ? i : 0] && ((side > 0) ? (l_ > 0.0) : (l_ < 0.0));
+              const unsigned bal = __ballot_sync(0xffffffffu, pred);
+              if (pred) {
+                const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+                idx[pos] = i;
+                wgt[pos] = fabs(l_);
+              }
+              cnt += __popc(bal);
             }
-            side = (npos <= nneg) ? 1 : -1;
-          }
-          int cnt = 0;
-          for (int base = 0; base < NP; base += 32) {
-            const int i = base + lane;
-            const double l_ = (i < NP) ? lam[i] : 0.0;
-            const bool pred = (i < NP) && !jskip[i < NP ? i : 0] && ((side > 0) ? (l_ > 0.0) : (l_ < 0.0));
-            const unsigned bal = __ballot_sync(0xffffffffu, pred);
-            if (pred) {
-              const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-              idx[pos] = i;
-              wgt[pos] = fabs(l_);
+            const int cpad = (cnt + 3) & ~3;
+            if (lane < cpad - cnt) {
+              idx[cnt + lane] = 0;
+              wgt[cnt + lane] = 0.0;
             }
-            cnt += __popc(bal);
+            if (lane == 0) {
+              ish[1] = cpad;
+              ish[2] = side;
+              ish[5] = cnt;
+            }
           }
-          const int cpad = (cnt + 3) & ~3;
-          if (lane < cpad - cnt) {
-            idx[cnt + lane] = 0;
-            wgt[cnt + lane] = 0.0;
-          }
-          if (lane == 0) {
-            ish[1] = cpad;
-            ish[2] = side;
-          }
-        }
 #if OMC_USE_TMA
-        // write the basis back for the next iteration (async proxy reads shared memory)
-        fence_proxy_async();
+          // write the basis back for the next iteration (async proxy reads shared memory)
+          fence_proxy_async();
 #endif
-        __syncthreads();
+          __syncthreads();
 #if OMC_USE_TMA
-        if (fits && tid == 0) {
-          bulk_s2g(Qg[b], B1, qbytes);
-          bulk_commit();
-        }
+          if (fits && tid == 0) {
+            bulk_s2g(Qg[b], B1, qbytes);
+            bulk_commit();
+          }
 #else
-        if (fits)
-          for (int e = tid; e < NP * ld; e += NT) Qg[b][e] = B1[e];
+          if (fits)
+            for (int e = tid; e < NP * ld; e += NT) Qg[b][e] = B1[e];
 #endif
+          // switch to the low-rank projection when the minority side (plus guard band) fits the panel: the tracked
+          // basis = the minority-side eigenvectors and the OMC_LR_BUF eigenvectors next to them across zero
+          if (fits && !P.o.exact_projection && ish[5] + OMC_LR_BUF <= PM && ish[5] + OMC_LR_BUF <= N) {
+            const int side = ish[2], pz = ish[5] + OMC_LR_BUF;
+            if (tid < 16) jrot[tid] = -1;
+            __syncthreads();
+            if (tid < N) {
+              const double key = side * lam[tid];
+              int rank = 0;
+              for (int j = 0; j < N; ++j) {
+                const double o = side * lam[j];
+                if (o > key || (o == key && j < tid)) ++rank;
+              }
+              if (rank < pz) jrot[rank] = tid;
+            }
+            __syncthreads();
+            for (int e = tid; e < NP * 16; e += NT) {
+              const int i = e >> 4, j = e & 15;
+              const int col = jrot[j];
+              Zg[b][e] = (col >= 0 && i < N) ? B1[(size_t)i * ld + col] : 0.0;
+            }
+            lr_mode[b] = 1;
+            lr_p[b] = pz;
+            lr_side[b] = side;
+          } else {
+            lr_mode[b] = 0;
+          }
+        }
         // Z = sum_{i in side} |lam_i| q_i q_i' on lower tiles; s+ = Z (positive side) or V + Z (negative side)
         {
           const int cpad = ish[1], side = ish[2];
           const int T = NP >> 3, KS = cpad >> 2;
           const int g_ = lane >> 2, t_ = lane & 3;
           const int ntile = T * (T + 1) / 2;
+          const double* QB = lr_done ? lrOut : B1;
+          const int ldq = lr_done ? OMC_LR_LDZ : ld;
           double* sW = sb[b];
           double* mW = mb[b];
           for (int tl = warp; tl < ntile; tl += NW) {
@@ -685,8 +906,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
             while (rt * (rt + 1) / 2 > tl) --rt;
             const int ct = tl - rt * (rt + 1) / 2;
             double c0 = 0.0, c1 = 0.0;
-            const double* arow = B1 + (size_t)(rt * 8 + g_) * ld;
-            const double* brow = B1 + (size_t)(ct * 8 + g_) * ld;
+            const double* arow = QB + (size_t)(rt * 8 + g_) * ldq;
+            const double* brow = QB + (size_t)(ct * 8 + g_) * ldq;
             for (int kk = 0; kk < KS; ++kk) {
               const int col = idx[kk * 4 + t_];
               const double a_ = arow[col] * wgt[kk * 4 + t_];
@@ -699,7 +920,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
               const int cc = ct * 8 + 2 * t_ + h;
               if (rr < N && cc <= rr) {
                 const size_t q = (size_t)rr * N + cc;
-                const double v = al * z_entry(c, b, rr, cc) + (1.0 - al) * sW[q] + mW[q] * irho;
+                const double v = lr_done ? B0[(size_t)rr * ld + cc]
+                                         : (al * z_entry(c, b, rr, cc) + (1.0 - al) * sW[q] + mW[q] * irho);
                 const double z = h ? c1 : c0;
                 const double snew = (side > 0) ? z : (v + z);
                 sW[q] = snew;
@@ -709,15 +931,20 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           }
         }
 #if OMC_USE_TMA
-        if (fits && tid == 0) bulk_wait_all();
+        if (!lr_done && fits && tid == 0) bulk_wait_all();
 #endif
         __syncthreads();
         OMC_TICK(4)
       }
 
       // ------------------------------------------------ phase 4: residuals / termination / rho
-      if (it % P.o.check_every == 0 || it == P.o.max_iter) {
+      if (it % P.o.check_every == 0 || it == P.o.max_iter || force_check) {
         tk = clock64();
+        // a termination decision taken on tracked (low-rank) projections is only provisional: it is re-taken right
+        // after one iteration with exact projections on every block (s in the cone and mu in its polar exactly)
+        const bool provisional = !exact_iter && (lr_mode[0] || lr_mode[1] || lr_mode[2]) && !P.o.exact_projection;
+        exact_iter = false;
+        force_check = false;
         double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0, sxx = 0.0, sfit = 0.0;
         double rpc[7] = {0, 0, 0, 0, 0, 0, 0};  // components: psd1, psd2, psd3, trace, box, v rows, aggregated rows
         // PSD rows
@@ -774,7 +1001,19 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         }
         // dense rows with the relaxed w: R [Y; U] needs a reduction -> reuse dense_rows_apply on (Y, U)
         __syncthreads();
-        dense_rows_apply(c, c.Y, c.U, rhs, red);  // rhs = R w
+        {  // stage the relaxed Y (lower triangle in the record) as a full symmetric matrix in region 0
+          const int ldy = n | 1;
+          for (int e = tid; e < n * n; e += NT) {
+            const int i = e / n, j = e - i * n;
+            if (j <= i) {
+              const double y = __ldcg(c.Y + e);
+              buf0[(size_t)i * ldy + j] = y;
+              buf0[(size_t)j * ldy + i] = y;
+            }
+          }
+          __syncthreads();
+          dense_rows_apply(c, buf0, ldy, c.U, rhs, red);  // rhs = R w
+        }
         double dual_rows = 0.0;
 #ifdef OMC_DEBUG_PRINT
         if (tid == 0 && L > 0 && it <= 3) {
@@ -829,11 +1068,21 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         }
         bool stop = false;
         if (rp <= P.o.eps_abs + P.o.eps_rel * np_ && rd <= P.o.eps_abs + P.o.eps_rel * nd_) {
-          status = OMC_STATUS_OPTIMAL;
-          stop = true;
+          if (provisional && it < P.o.max_iter) {
+            exact_iter = true;
+            force_check = true;
+          } else {
+            status = OMC_STATUS_OPTIMAL;
+            stop = true;
+          }
         } else if (P.o.cutoff < 1e299 && lbound > P.o.cutoff) {
-          status = OMC_STATUS_CUTOFF;
-          stop = true;
+          if (provisional && it < P.o.max_iter) {
+            exact_iter = true;
+            force_check = true;
+          } else {
+            status = OMC_STATUS_CUTOFF;
+            stop = true;
+          }
         } else if (P.o.time_limit_s > 0.0 &&
                    (double)(globaltimer_ns() - t_start) * 1e-9 > P.o.time_limit_s) {
           if (tid == 0) ish[3] = 1;
@@ -862,9 +1111,12 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
     if (it > P.o.max_iter) it = P.o.max_iter;
     OMC_TICK(5)
     if (P.prof && tid == 0) {
-      for (int q = 0; q < 6; ++q) P.prof[(size_t)node * 16 + q] = (double)pc[q];
-      P.prof[(size_t)node * 16 + 6] = (double)nsweeps;
-      P.prof[(size_t)node * 16 + 7] = (double)it;
+      for (int q = 0; q < 6; ++q) P.prof[(size_t)node * OMC_PROF_STRIDE + q] = (double)pc[q];
+      P.prof[(size_t)node * OMC_PROF_STRIDE + 6] = (double)nsweeps;
+      P.prof[(size_t)node * OMC_PROF_STRIDE + 7] = (double)it;
+      P.prof[(size_t)node * OMC_PROF_STRIDE + 14] = (double)n_lr;
+      P.prof[(size_t)node * OMC_PROF_STRIDE + 15] = (double)n_full;
+      for (int q = 0; q < 8; ++q) P.prof[(size_t)node * OMC_PROF_STRIDE + 16 + q] = (double)lpc[q];
     }
 
     // ---------------------------------------------------------------- outputs (original units)
@@ -905,17 +1157,19 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
 }
 
 // shared memory bytes the kernel carves up (must mirror the carve-up above)
+template <int PM>
 inline size_t relax_smem_bytes(int n, int m, int k, int Lcap, int rmax) {
   Geo g1 = make_geo(n + m);
   Geo gf = smem_geo(n + m, n + k, n);
   size_t d = 0;
-  d += 2 * (size_t)gf.NP * gf.ld;        // buf0, buf1
+  d += (size_t)gf.NP * gf.ld + region1_doubles<PM>(gf);   // buf0, region 1
   d += 2 * (size_t)g1.NP;                // lam, wgt
   d += 2 * (size_t)(g1.NP / 2);          // jcs, jsn
   d += 32;                               // red
   d += 3 * (size_t)rmax;                 // rhs, cw, gc
   d += 3 * (size_t)Lcap * k + Lcap;      // clb, cub, cal, cbe
   d += (size_t)Lcap;                     // cxp (pointers, 8 bytes)
+  d += (size_t)Lcap + OMC_XS_CAP;        // tgs, xs
   d += 1;                                // mbar
   size_t bytes = d * 8;
   bytes += sizeof(int) * (3 * ((size_t)g1.NP / 2) + 2 * (size_t)g1.NP + 8);

@@ -221,7 +221,7 @@ class Frontier:
 
     def profile(self) -> np.ndarray:
         """(B, 16): SM cycles per phase (w-update, build V, DMMA pre-rotation, Jacobi, reconstruction, residuals), sweeps, iterations."""
-        prof = np.zeros((self.B, 16))
+        prof = np.zeros((self.B, 32))
         check(self.p.lib.omc_frontier_fetch_profile(self.handle, _ptr(prof, C.c_double)))
         return prof
 

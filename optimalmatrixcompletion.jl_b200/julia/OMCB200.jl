@@ -44,7 +44,7 @@ mutable struct RelaxOpts
     eps_abs::Float64; eps_rel::Float64
     max_iter::Int32; check_every::Int32; adapt_every::Int32; fix_linear3_right::Int32
     rho0::Float64; sigma::Float64; alpha::Float64; cutoff::Float64; time_limit_s::Float64; jacobi_tol::Float64
-    reortho_every::Int32; reserved::Int32
+    reortho_every::Int32; exact_projection::Int32
 end
 function default_opts()
     o = RelaxOpts(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)

@@ -55,7 +55,7 @@ def psd_project(V):
 class Options:
     def __init__(self, eps_abs=1e-7, eps_rel=1e-7, max_iter=20000, rho=0.1, sigma=1e-6,
                  alpha=1.6, check_every=25, adapt_every=100, adaptive_rho=True,
-                 eps_inf=1e-6, fix_linear3_right=False, scale=None, verbose=False):
+                 eps_inf=1e-6, fix_linear3_right=False, scale=None, verbose=False, projection="exact", pm=16):
         self.__dict__.update(locals()); del self.__dict__["self"]
 
 
@@ -181,6 +181,13 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
     status = STATUS_ITERATION_LIMIT
     res_p = res_d = np.inf
     it = 0
+    # projection = "tracked": the warm-started low-rank projection of csrc/omc_lowrank.cuh (oracle/lowrank.py); every
+    # termination decision is then re-taken after one iteration with exact projections, as the kernel does
+    trackers = None
+    if o.projection == "tracked":
+        from .lowrank import TrackedProjector
+        trackers = [TrackedProjector(o.pm) for _ in range(3)]
+    exact_iter = force_check = False
     for it in range(1, o.max_iter + 1):
         # ---- w-update: (P + sigma I + rho A'A) w~ = sigma w - q + A'(rho (b - s) + mu)
         gX, gY, gT, gU = c.At(st.m1 - rho * st.s1, st.m2 + rho * (c.E2 - st.s2), st.m3 + rho * (c.I3 - st.s3),
@@ -208,7 +215,10 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
         st.X = al * Xt + (1 - al) * st.X; st.Y = al * Yt + (1 - al) * st.Y
         st.T = al * Tt + (1 - al) * st.T; st.U = al * Ut + (1 - al) * st.U
         m_old = (st.m1, st.m2, st.m3, st.m4, st.m5, st.mv, st.mg)
-        st.s1 = psd_project(v1); st.s2 = psd_project(v2); st.s3 = psd_project(v3)
+        if trackers is None:
+            st.s1 = psd_project(v1); st.s2 = psd_project(v2); st.s3 = psd_project(v3)
+        else:
+            st.s1, st.s2, st.s3 = (tr.project(v, exact=exact_iter) for tr, v in zip(trackers, (v1, v2, v3)))
         st.s4 = max(v4, 0.0)
         st.s5 = np.clip(v5, c.lo, c.hi)
         st.sv = np.clip(vv, c.lb, c.ub); st.sg = np.maximum(vg, 0.0)
@@ -216,7 +226,9 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
         st.m4 = rho * (v4 - st.s4); st.m5 = rho * (v5 - st.s5)
         st.mv = rho * (vv - st.sv); st.mg = rho * (vg - st.sg)
 
-        if it % o.check_every == 0 or it == o.max_iter:
+        if it % o.check_every == 0 or it == o.max_iter or force_check:
+            provisional = trackers is not None and not exact_iter
+            exact_iter = force_check = False
             w = c.S(st.X, st.Y, st.T, st.U)                                       # b - A w
             sblk = (st.s1, st.s2, st.s3, np.array([st.s4]), st.s5, st.sv, st.sg)
             rp = max(np.abs(np.asarray(wi) - si).max() for wi, si in zip(w, sblk) if si.size)
@@ -231,6 +243,9 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
             if o.verbose:
                 print(f"it {it:6d} rp {rp:.3e} rd {rd:.3e} rho {rho:.3e}")
             if rp <= o.eps_abs + o.eps_rel * n_p and rd <= o.eps_abs + o.eps_rel * n_d:
+                if provisional and it < o.max_iter:
+                    exact_iter = force_check = True
+                    continue
                 status = STATUS_OPTIMAL
                 break
             # ---- primal infeasibility (COSMO sec. 5.2): dmu in the polar cone, A'dmu ~ 0, support - b'dmu < 0
@@ -267,7 +282,8 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
             - float(np.sum(np.where(st.m5 < 0, st.m5 * c.lo, st.m5 * c.hi)))
             - float(np.sum(np.where(st.mv < 0, st.mv * c.lb, st.mv * c.ub))))
     return dict(status=status, feasible=status != STATUS_INFEASIBLE, objective=obj, dual_objective=dual,
-                X=X, Y=Y, Theta=T, U=U, iters=it, res_p=res_p, res_d=res_d, state=st, rho=rho, consts=c)
+                X=X, Y=Y, Theta=T, U=U, iters=it, res_p=res_p, res_d=res_d, state=st, rho=rho, consts=c,
+                projections=None if trackers is None else (sum(t.n_lr for t in trackers), sum(t.n_full for t in trackers)))
 
 
 def certificate(res, A, mask, gamma, k):

@@ -12,4 +12,4 @@ for mi in [200, 1000, 5000]:
     f = omc_b200.Frontier(p, nodes); ms = f.relax(omc_b200.default_opts(max_iter=mi)); out = f.fetch(False); prof = f.profile(); f.close()
     pm = prof.sum(axis=0); tot = pm[:6].sum()
     print(f"max_iter {mi}: {ms:.1f} ms iters {pm[7]:.0f} sweeps/iter {pm[6]/pm[7]:.2f} cyc/iter {tot/pm[7]:.0f}", " ".join(f"{nm}={pm[q]/tot*100:.1f}%" for q, nm in enumerate(["wupd", "buildV", "gemm", "jacobi", "recon", "resid"])),
-          f"| blk1: rot/call {pm[8]/pm[10]:.0f} skip/call {pm[9]/pm[10]:.1f} | blk2+3: rot/call {pm[11]/pm[13]:.0f} skip/call {pm[12]/pm[13]:.1f}", flush=True)
+          f"| blk1: rot/call {pm[8]/pm[10]:.0f} blkcyc/call {pm[9]/pm[10]:.0f} | blk2+3: rot/call {pm[11]/pm[13]:.0f} blkcyc/call {pm[12]/pm[13]:.0f}", flush=True)

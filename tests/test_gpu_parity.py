@@ -102,7 +102,7 @@ def test_relaxation_matches_oracle_iterate_for_iterate(omc):
     cid = p.add_cut(x, Uh)
     for dirs in (["left"], ["right"]):
         for mi in (1, 7, 60):
-            r = p.relax_batch([[omc.Cut(cid, x, Uh, dirs)]], omc.default_opts(eps_abs=1e-30, eps_rel=1e-30, max_iter=mi, adapt_every=0, jacobi_tol=1e-13))[0]
+            r = p.relax_batch([[omc.Cut(cid, x, Uh, dirs)]], omc.default_opts(eps_abs=1e-30, eps_rel=1e-30, max_iter=mi, adapt_every=0, jacobi_tol=1e-13, exact_projection=1))[0]
             ro = R.solve_relaxation(A, mask, g, k, "linear", [(x, Uh, dirs)], opts=R.Options(eps_abs=1e-30, eps_rel=1e-30, max_iter=mi, adaptive_rho=False))
             assert np.abs(r["X"] - ro["X"]).max() < 1e-9 and np.abs(r["Y"] - ro["Y"]).max() < 1e-9 and np.abs(r["U"] - ro["U"]).max() < 1e-9
             assert abs(r["res_p"] - ro["res_p"]) <= 1e-7 * max(1.0, ro["res_p"]) and abs(r["res_d"] - ro["res_d"]) <= 1e-7 * max(1.0, ro["res_d"])
@@ -204,7 +204,7 @@ def test_config4_shape_runs_through_the_l2_resident_block_path(omc):
     cid = p.add_cut(x, Uh)
     dirs = ["inner_left", "right", "left"]
     for cuts_g, cuts_o in (([], []), ([omc.Cut(cid, x, Uh, dirs)], [(x, Uh, dirs)])):
-        r = p.relax_batch([cuts_g], omc.default_opts(eps_abs=1e-30, eps_rel=1e-30, max_iter=20, adapt_every=0, jacobi_tol=1e-13))[0]
+        r = p.relax_batch([cuts_g], omc.default_opts(eps_abs=1e-30, eps_rel=1e-30, max_iter=20, adapt_every=0, jacobi_tol=1e-13, exact_projection=1))[0]
         ro = R.solve_relaxation(A, mask, g, k, "linear3", cuts_o, opts=R.Options(eps_abs=1e-30, eps_rel=1e-30, max_iter=20, adaptive_rho=False))
         assert np.abs(r["X"] - ro["X"]).max() < 1e-8 and np.abs(r["Y"] - ro["Y"]).max() < 1e-8 and np.abs(r["U"] - ro["U"]).max() < 1e-8
     full = p.relax_batch([[]], omc.default_opts(max_iter=4000))[0]
@@ -216,4 +216,34 @@ def test_config4_shape_runs_through_the_l2_resident_block_path(omc):
     assert full["objective"] <= p.objective_mse(am["U"] @ am["V"])[0] * (1 + 1e-9)      # bound <= a feasible rank-k value
     lam, vec, bp, feas = omc.smallest_eigvecs_batch(Y, U, 2)                            # config 4 uses smallest_2_eigvec
     assert lam[0, 0] <= lam[0, 1] and abs(np.linalg.norm(vec[0, :, 0]) - 1) < 1e-10
+    p.close()
+
+
+def test_tracked_projection_matches_exact_projection_on_frontier_nodes(omc):
+    """The default path tracks the minority spectral side of every PSD block with one block-LOBPCG step per
+    iteration (csrc/omc_lowrank.cuh); exact_projection=1 diagonalises every block at every iteration.  On deep
+    config-2 frontier nodes both must stop at the same iteration (+1 for the confirming exact iteration) with the
+    same bound, the tracked run must do almost all projections on the tracker, and both reproduce the bounds stored in
+    tests/golden/c2_frontier.json (which tests/test_frontier_fixture.py pins to the CPU oracle) to the north-star tolerance."""
+    import bench, json, os
+    from oracle.datagen import config_instance
+    k, A, mask, g = config_instance("C2", 0)
+    p = omc.Problem(k, A, mask, g, "linear")
+    cuts = bench.load_frontier_fixture(6)
+    nodes = [_cuts_for(omc, p, cl) for cl in cuts]
+    o_t = omc.default_opts(max_iter=6000)
+    o_e = omc.default_opts(max_iter=6000, exact_projection=1)
+    f = omc.Frontier(p, nodes); f.relax(o_t); rt = f.fetch(True); prof = f.profile(); f.close()
+    re_ = p.relax_batch(nodes, o_e)
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_frontier.json")))["nodes"][:6]
+    for a, b, rec in zip(rt, re_, fx):
+        assert a["status_code"] == b["status_code"]
+        assert abs(a["objective"] - b["objective"]) <= 1e-7 * abs(b["objective"])
+        if rec["gpu"]["status"] == 0 and a["status_code"] == 0:
+            assert abs(a["objective"] - rec["gpu"]["objective"]) <= REL_BOUND * abs(a["objective"])
+        assert abs(a["iters"] - b["iters"]) <= 26                     # one check period
+        assert np.abs(a["X"] - b["X"]).max() <= 1e-5 and np.abs(a["Y"] - b["Y"]).max() <= 1e-5
+        Y, U = a["Y"], a["U"]
+        assert np.linalg.eigvalsh(np.eye(50) - Y).min() >= -1e-6 and np.linalg.eigvalsh(Y - U @ U.T).min() >= -1e-6
+    assert prof[:, 14].sum() >= 0.98 * (prof[:, 14].sum() + prof[:, 15].sum())   # tracker did >= 98 % of the projections
     p.close()

@@ -205,3 +205,43 @@ def test_separation_oracle_dense_matches_arpack():
     x2, lam = E.breakpoint_vector(Y, U, "smallest_2_eigvec")
     w = np.abs(lam[:2]) / np.linalg.norm(lam[:2])
     assert lam[1] < -1e-10 and np.allclose(x2, w[0] * vd[:, 0] + w[1] * vd[:, 1])   # OMC.jl:2471-2473
+
+
+def test_tracked_projection_follows_exact_projection():
+    """oracle/lowrank.py (restatement of csrc/omc_lowrank.cuh): along a contracting sequence of symmetric matrices
+    the tracked projection stays close to the exact one and needs the full eigensolver only to start."""
+    from oracle import lowrank as LR
+    rng = np.random.default_rng(0)
+    N = 40
+    Q, _ = np.linalg.qr(rng.standard_normal((N, N)))
+    lam = np.concatenate([[3, 1, 0.2, 0.01], -np.abs(rng.standard_normal(N - 4))])
+    V = (Q * lam) @ Q.T
+    tp = LR.TrackedProjector(16)
+    for it in range(80):
+        D = rng.standard_normal((N, N)); D = (D + D.T) * 1e-3 * 0.9 ** it
+        V = V + D
+        P = tp.project(V)
+        l, Qe = np.linalg.eigh(V)
+        Pe = (Qe * np.maximum(l, 0)) @ Qe.T
+        assert np.linalg.norm(P - Pe) <= 2.0 * np.linalg.norm(D) + 1e-12 * np.linalg.norm(V)   # error below the step itself
+        assert np.linalg.eigvalsh(P).min() >= -1e-12                                           # always inside the cone
+    assert tp.n_full == 1 and tp.n_lr == 79
+    # negative side tracked when it is the smaller one; exact=True refreshes
+    tq = LR.TrackedProjector(8)
+    W = -V
+    P0 = tq.project(W); assert tq.side == -1
+    P1 = tq.project(W + 1e-6 * D)
+    l, Qe = np.linalg.eigh(W + 1e-6 * D)
+    assert np.linalg.norm(P1 - (Qe * np.maximum(l, 0)) @ Qe.T) <= 1e-8 * np.linalg.norm(W)
+
+
+def test_admm_with_tracked_projection_reaches_the_same_bound():
+    k, A, mask, g = config_instance("C1", 0)
+    a = R.solve_relaxation(A, mask, g, k, opts=R.Options(eps_abs=1e-9, eps_rel=1e-9))
+    b = R.solve_relaxation(A, mask, g, k, opts=R.Options(eps_abs=1e-9, eps_rel=1e-9, projection="tracked", pm=8))
+    assert a["status"] == b["status"] == R.STATUS_OPTIMAL and abs(a["iters"] - b["iters"]) <= 26
+    assert abs(a["objective"] - b["objective"]) <= 1e-8 * abs(a["objective"])
+    lr, full = b["projections"]
+    assert lr > 20 * full
+    cert = R.certificate(b, A, mask, g, k)
+    assert cert["dual_cone"] <= 1e-9 and cert["primal_psd1"] >= -1e-7 and abs(cert["gap"]) <= 1e-6
