@@ -150,7 +150,7 @@ __host__ __device__ inline Geo make_geo(int N) {
 // shares a panel has loaded its fragments (one __syncthreads).  KMAX >= NP/4.
 // ------------------------------------------------------------------------------------------------
 template <int KMAX>
-__device__ __forceinline__ void gemm_rows_inplace(double* M, const double* Q, int NP, int ld) {
+__device__ __noinline__ void gemm_rows_inplace(double* M, const double* Q, int NP, int ld) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int T = NP >> 3, KS = NP >> 2;
   const int g = lane >> 2, t = lane & 3;
@@ -188,7 +188,7 @@ __device__ __forceinline__ void gemm_rows_inplace(double* M, const double* Q, in
 }
 
 template <int KMAX>
-__device__ __forceinline__ void gemm_cols_inplace(double* M, const double* Q, int NP, int ld) {
+__device__ __noinline__ void gemm_cols_inplace(double* M, const double* Q, int NP, int ld) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int T = NP >> 3, KS = NP >> 2;
   const int g = lane >> 2, t = lane & 3;
@@ -261,7 +261,7 @@ __device__ __forceinline__ void jacobi_pair(int i, int t, int NP, int& p, int& q
   }
 }
 
-__device__ inline int jacobi_sym(double* S, double* Q, int NP, int ld, double tol, int max_sweeps, double* cs,
+__device__ __noinline__ int jacobi_sym(double* S, double* Q, int NP, int ld, double tol, int max_sweeps, double* cs,
                                  double* sn, int* rot, double* scratch, int projection_mode = 0, int* skip = nullptr,
                                  int* skip_sign = nullptr, double* stats = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;

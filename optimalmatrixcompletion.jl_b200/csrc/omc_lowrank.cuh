@@ -35,6 +35,8 @@ struct LrSmall {
   double Gc[N2 * PM];    // selected eigenvectors, compact: Gc[k * PM + j]
   double th[N2];         // Ritz values
   double cs[PM], sn[PM];
+  double invd[PM];       // reciprocal diagonal of the Cholesky factor
+  int ptab[(N2 - 1) * PM];  // round-robin pair table of the Jacobi sweeps: (p << 8) | q per (step, pair)
   int sel[PM];
   int valid[PM];         // residual directions that survived the rank guard
   int cidx[N2];          // live directions of [Z R~] (compacted index -> panel column, R~ columns offset by pc)
@@ -51,6 +53,7 @@ __device__ __forceinline__ void panel_gram(const double* __restrict__ A, const d
   for (int a = warp; a < pc; a += nw) {
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     if (4 * b4 < pc) {
+#pragma unroll 4
       for (int i = ic; i < N; i += 8) {
         const double av = A[(size_t)i * OMC_LR_LDZ + a];
         const double2 b01 = *reinterpret_cast<const double2*>(B + (size_t)i * OMC_LR_LDZ + 4 * b4);
@@ -123,68 +126,66 @@ __device__ __forceinline__ void panel_small_mul(double* Dst, const double* Src, 
   }
 }
 
-// Cholesky of the Gram matrix M (pc x pc in shared memory, leading dimension ld) with a rank guard, and the inverse
-// of the factor, by warp 0 in registers: lane i owns row i, pivots and multipliers travel by warp shuffles.  A column
-// whose pivot falls below piv_rel * max diag (or that is already marked dead in valid[] when use_valid_in) is
-// dropped: valid[j] = 0, unit pivot, zero column.  T = L^-1 (lower) is written to shared memory.
-template <int PM>
-__device__ __forceinline__ void warp_chol_inv(const double* M, double* T, int ld, int pc, int* valid, double piv_rel,
-                                              bool use_valid_in, int* illcond) {
-  if ((threadIdx.x >> 5) != 0) return;
-  const int lane = threadIdx.x & 31;
-  const unsigned full = 0xffffffffu;
-  double m[PM];
-#pragma unroll
-  for (int c = 0; c < PM; ++c) m[c] = (lane < pc && c < pc) ? M[lane * ld + c] : ((lane == c) ? 1.0 : 0.0);
+// Cholesky of the Gram matrix M (pc x pc in shared memory, leading dimension ld, lower triangle used and destroyed)
+// with a rank guard, by the first pc*pc threads: one barrier per column, every thread owns one entry (i, c) of the
+// trailing matrix.  A column whose pivot falls below piv_rel * max diag (or that is already marked dead in valid[]
+// when use_valid_in) is dropped: valid[j] = 0, unit pivot, zero column.  On exit Lf holds the factor (lower, incl.
+// diagonal), invd[j] = 1 / L[j][j], *illcond (optional) tells whether the smallest accepted pivot is below 1e-5 max.
+__device__ __forceinline__ void block_chol(double* M, double* Lf, double* invd, int ld, int pc, int* valid, double piv_rel,
+                                           bool use_valid_in, int* illcond) {
+  const int tid = threadIdx.x;
+  const int i = tid / pc, c = tid - i * pc;
+  const bool act = tid < pc * pc;
   double dmax = 0.0;
-#pragma unroll
-  for (int c = 0; c < PM; ++c)
-    if (lane == c && c < pc) dmax = m[c];
-  dmax = warp_max(dmax);
+  for (int j = 0; j < pc; ++j) dmax = fmax(dmax, M[j * ld + j]);
   const double thr = piv_rel * dmax;
-  const int vin = (use_valid_in && lane < pc) ? valid[lane] : 1;
-  double invd = 1.0;  // 1 / L[lane][lane]
   double pmin = dmax;
-  unsigned okmask = 0u;
-#pragma unroll
-  for (int j = 0; j < PM; ++j) {
-    const double piv = __shfl_sync(full, m[j], j);
-    const int vj = __shfl_sync(full, vin, j);
-    const bool ok = (j < pc) && (piv > thr) && (piv > 0.0) && (vj != 0);
-    const double inv = ok ? rsqrt(piv) : 1.0;
-    const double d = ok ? piv * inv : 1.0;
-    if (ok) { okmask |= (1u << j); pmin = fmin(pmin, piv); }
-    double lij = m[j];
-    if (lane > j) lij = ok ? m[j] * inv : 0.0;
-    if (lane == j) { lij = d; invd = inv; }
-    m[j] = lij;
-#pragma unroll
-    for (int c = j + 1; c < PM; ++c) {
-      const double lcj = __shfl_sync(full, m[j], c);
-      if (lane >= c) m[c] -= lij * lcj;   // lanes >= c > j hold multipliers (zero when the column was dropped)
+  __syncthreads();   // everybody has read the original diagonal
+  for (int j = 0; j < pc; ++j) {
+    const double piv = M[j * ld + j];
+    const bool ok = (piv > thr) && (piv > 0.0) && (!use_valid_in || valid[j] != 0);
+    if (ok) pmin = fmin(pmin, piv);
+    if (act && c >= j && i >= c) {
+      const double inv = ok ? rsqrt(piv) : 1.0;
+      const double lij = ok ? M[i * ld + j] * inv : 0.0;
+      if (c == j) {
+        Lf[i * ld + j] = (i == j) ? (ok ? piv * inv : 1.0) : lij;
+        if (i == j) invd[j] = inv;
+      } else {
+        const double lcj = ok ? M[c * ld + j] * inv : 0.0;
+        M[i * ld + c] -= lij * lcj;
+      }
     }
+    __syncthreads();
+    if (tid == 0) valid[j] = ok ? 1 : 0;
   }
-  if (lane < pc) valid[lane] = (okmask >> lane) & 1u;
-  if (lane == 0 && illcond) *illcond = (pmin < 1e-5 * dmax) ? 1 : 0;
-  // T = L^-1: lane c builds column c by forward substitution
-  double t[PM];
+  if (tid == 0 && illcond) *illcond = (pmin < 1e-5 * dmax) ? 1 : 0;
+  __syncthreads();
+}
+
+// dst[i][:] = src[i][:] L^-T (row-wise forward substitution with the Cholesky factor Lf), dropped columns zeroed.
+template <int PM>
+__device__ __forceinline__ void panel_trsm(const double* src, double* dst, int NP, int pc, const double* Lf, int ld,
+                                           const double* invd, const int* valid) {
+  for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+    double rt[PM];
+    const double* rr = src + (size_t)i * OMC_LR_LDZ;
 #pragma unroll
-  for (int i = 0; i < PM; ++i) {
-    double acc = (i == lane) ? 1.0 : 0.0;
+    for (int a = 0; a < PM; ++a) {
+      double acc = 0.0;
+      if (a < pc) {
+        acc = rr[a];
 #pragma unroll
-    for (int k = 0; k < i; ++k) {
-      const double lik = __shfl_sync(full, m[k], i);
-      acc -= lik * t[k];
+        for (int b = 0; b < a; ++b) acc -= rt[b] * Lf[a * ld + b];
+        acc = valid[a] ? acc * invd[a] : 0.0;
+      }
+      rt[a] = acc;
     }
-    const double ii = __shfl_sync(full, invd, i);
-    t[i] = (i >= lane) ? acc * ii : 0.0;
-  }
-  if (lane < pc) {
+    double* d = dst + (size_t)i * OMC_LR_LDZ;
 #pragma unroll
-    for (int i = 0; i < PM; ++i)
-      if (i < pc) T[i * ld + lane] = t[i];
+    for (int a = 0; a < PM; ++a)
+      if (a < pc) d[a] = rt[a];
   }
-  __syncwarp();
 }
 
 // symmetric Schur rotation of the pivot (app, aqq, apq): |theta| <= pi/4
@@ -203,40 +204,58 @@ __device__ __forceinline__ void schur_rot(double app, double aqq, double apq, do
 // Cyclic two-sided Jacobi sweeps on the symmetric n x n matrix M (n even, <= 32, leading dimension ld, both
 // triangles), rotations accumulated into G (G <- G J).  Round-robin ordering, all threads of the CTA: the first n/2
 // threads compute the rotation parameters of a step, then every 2x2 block (pair a, pair b) is updated on both
-// sides at once, in place (a block is read and written by one thread only).
-__device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld, int sweeps, double* cs, double* sn) {
+// sides at once, in place (a block is read and written by one thread only).  A step in which no pivot exceeds
+// skip_tol * sqrt|a_pp a_qq| is skipped (the barrier doubles as the vote), which makes warm sweeps cheap.
+__device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld, int sweeps, double* cs, double* sn,
+                                             int* ptab, int ldt, double skip_tol) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int h = n >> 1;
   const int nblk = h * h, items = nblk + h * n;
+  for (int e = tid; e < (n - 1) * h; e += nt) {
+    const int t = e / h, a = e - t * h;
+    int p, q;
+    jacobi_pair(a, t, n, p, q);
+    ptab[t * ldt + a] = (p << 8) | q;
+  }
+  // static item descriptors (at most two items per thread are kept in registers; more fall back to recomputation)
+  int ia0 = -1, ib0 = 0, ia1 = -1, ib1 = 0;
+  if (tid < items) { if (tid < nblk) { ia0 = tid / h; ib0 = tid - ia0 * h; } else { const int e = tid - nblk; ia0 = e / n; ib0 = e - ia0 * n; } }
+  if (tid + nt < items) { const int it = tid + nt; if (it < nblk) { ia1 = it / h; ib1 = it - ia1 * h; } else { const int e = it - nblk; ia1 = e / n; ib1 = e - ia1 * n; } }
+  __syncthreads();
   for (int sw = 0; sw < sweeps; ++sw) {
     for (int t = 0; t < n - 1; ++t) {
+      const int* pt = ptab + t * ldt;
+      int need = 0;
       if (tid < h) {
-        int p, q;
-        jacobi_pair(tid, t, n, p, q);
-        double c, s_;
-        schur_rot(M[p * ld + p], M[q * ld + q], M[p * ld + q], c, s_);
+        const int pq = pt[tid], p = pq >> 8, q = pq & 0xff;
+        const double app = M[p * ld + p], aqq = M[q * ld + q], apq = M[p * ld + q];
+        double c = 1.0, s_ = 0.0;
+        if (apq * apq > skip_tol * skip_tol * fabs(app * aqq)) {
+          schur_rot(app, aqq, apq, c, s_);
+          need = 1;
+        }
         cs[tid] = c;
         sn[tid] = s_;
       }
-      __syncthreads();
-      for (int it = tid; it < items; it += nt) {
+      if (!__syncthreads_or(need)) continue;
+      for (int it = tid, k = 0; it < items; it += nt, ++k) {
+        int ia, ib;
+        if (k == 0) { ia = ia0; ib = ib0; }
+        else if (k == 1) { ia = ia1; ib = ib1; }
+        else if (it < nblk) { ia = it / h; ib = it - ia * h; }
+        else { const int e = it - nblk; ia = e / n; ib = e - ia * n; }
         if (it < nblk) {
-          const int a = it / h, b = it - a * h;
-          int pa, qa, pb, qb;
-          jacobi_pair(a, t, n, pa, qa);
-          jacobi_pair(b, t, n, pb, qb);
-          const double ca = cs[a], sa = sn[a], cb = cs[b], sb = sn[b];
+          const int pqa = pt[ia], pa = pqa >> 8, qa = pqa & 0xff;
+          const int pqb = pt[ib], pb = pqb >> 8, qb = pqb & 0xff;
+          const double ca = cs[ia], sa = sn[ia], cb = cs[ib], sb = sn[ib];
           const double x = M[pa * ld + pb], y = M[pa * ld + qb], z = M[qa * ld + pb], w = M[qa * ld + qb];
           const double x1 = ca * x - sa * z, z1 = sa * x + ca * z, y1 = ca * y - sa * w, w1 = sa * y + ca * w;
           double x2 = cb * x1 - sb * y1, y2 = sb * x1 + cb * y1, z2 = cb * z1 - sb * w1, w2 = sb * z1 + cb * w1;
-          if (a == b) { y2 = 0.0; z2 = 0.0; }
+          if (ia == ib && sa != 0.0) { y2 = 0.0; z2 = 0.0; }
           M[pa * ld + pb] = x2; M[pa * ld + qb] = y2; M[qa * ld + pb] = z2; M[qa * ld + qb] = w2;
         } else {
-          const int e = it - nblk;
-          const int a = e / n, r = e - a * n;
-          int p, q;
-          jacobi_pair(a, t, n, p, q);
-          const double c = cs[a], s_ = sn[a];
+          const int pq = pt[ia], p = pq >> 8, q = pq & 0xff, r = ib;
+          const double c = cs[ia], s_ = sn[ia];
           const double x = G[r * ld + p], y = G[r * ld + q];
           G[r * ld + p] = c * x - s_ * y;
           G[r * ld + q] = s_ * x + c * y;
@@ -253,7 +272,7 @@ __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld
 // side of V, -1 the negative side (the positive side of -V).  lp (optional, 8 slots): cycles per sub-phase.
 // Returns need_full (uniform over the CTA).
 template <int PM>
-__device__ inline int lowrank_step(const double* V, int ldv, int N, int NP, double side, double* P0, double* P1, double* P2,
+__device__ __noinline__ int lowrank_step(const double* V, int ldv, int N, int NP, double side, double* P0, double* P1, double* P2,
                                    int p, LrSmall<PM>& S, double vscale, long long* lp, double** Zout) {
   constexpr int LD = LrSmall<PM>::LD, LD2 = LrSmall<PM>::LD2;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -262,7 +281,7 @@ __device__ inline int lowrank_step(const double* V, int ldv, int N, int NP, doub
 #define OMC_LRT(slot)                        \
   {                                          \
     const long long now_ = clock64();        \
-    if (lp) lp[slot] += now_ - tk;           \
+    if (lp && tid == 0) lp[slot] += now_ - tk; \
     tk = now_;                               \
   }
   // W = side V Z -> P1 ; H = Z'W
@@ -295,29 +314,8 @@ __device__ inline int lowrank_step(const double* V, int ldv, int N, int NP, doub
     }
     panel_gram(src, src, N, pc, S.C, LD, 1.0);
     __syncthreads();
-    warp_chol_inv<PM>(S.C, S.T, LD, pc, S.valid, pass == 0 ? 1e-10 : 1e-24, pass != 0, pass == 0 ? &S.info[4] : nullptr);
-    __syncthreads();
-    // R~[i][a] = sum_{b <= a} R[i][b] T[a][b]
-    const int ng = pc >> 2, items = NP * ng;
-    for (int it = tid; it < items; it += nt) {
-      const int i = it / ng, jg = it - i * ng;
-      const double* rr = src + (size_t)i * OMC_LR_LDZ;
-      double o4[4] = {0.0, 0.0, 0.0, 0.0};
-      const int amax = 4 * jg + 3;
-      for (int b = 0; b <= amax; ++b) {
-        const double rb = rr[b];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int a = 4 * jg + u;
-          if (b <= a) o4[u] += rb * S.T[a * LD + b];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (!S.valid[4 * jg + u]) o4[u] = 0.0;
-      double* d = dst + (size_t)i * OMC_LR_LDZ + 4 * jg;
-      d[0] = o4[0]; d[1] = o4[1]; d[2] = o4[2]; d[3] = o4[3];
-    }
+    block_chol(S.C, S.T, S.invd, LD, pc, S.valid, pass == 0 ? 1e-10 : 1e-24, pass != 0, pass == 0 ? &S.info[4] : nullptr);
+    panel_trsm<PM>(src, dst, NP, pc, S.T, LD, S.invd, S.valid);
     __syncthreads();
     if (pass == 0) {
       if (!S.info[4]) break;
@@ -366,7 +364,7 @@ __device__ inline int lowrank_step(const double* V, int ldv, int N, int NP, doub
     S.G2[ia * LD2 + ib] = (ia == ib) ? 1.0 : 0.0;
   }
   __syncthreads();
-  small_jacobi(S.H2, S.G2, n2, LD2, OMC_LR_SWEEPS, S.cs, S.sn);
+  small_jacobi(S.H2, S.G2, n2, LD2, OMC_LR_SWEEPS, S.cs, S.sn, S.ptab, PM, 1e-15);
   const double* Hd = S.H2;
   OMC_LRT(5)
   // Ritz values, selection of the top r + BUF (warp 0)

@@ -189,7 +189,7 @@ __device__ __forceinline__ double w_entry(const NodeCtx& c, int b, int r, int co
 
 // ---- dense rows R (trace row, cut rows) applied to (Y, U): out = R [Y; U] -------------------------------------
 // Ys: FULL symmetric n x n with leading dimension ldy in shared memory; Up: n x k column-major (shared or global).
-__device__ __noinline__ void dense_rows_apply(const NodeCtx& c, const double* Ys, int ldy, const double* Up, double* out,
+__device__ __forceinline__ void dense_rows_apply(const NodeCtx& c, const double* Ys, int ldy, const double* Up, double* out,
                                               double* scratch) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int n = c.n, k = c.k, L = c.L;
@@ -248,90 +248,84 @@ __host__ __device__ inline size_t region1_doubles(const Geo& gfit) {
   return ((full > lr ? full : lr) + 1) & ~(size_t)1;
 }
 
-template <int NT, int KMAX, int MINB, int PM>
-__global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = NT / 32;
-  const int n = P.n, m = P.m, k = P.k;
-  const StateLayout& SL = P.SL;
-  const Geo g1 = make_geo(SL.N1), g2 = make_geo(SL.N2), g3 = make_geo(SL.N3);
-  const Geo gfit = smem_geo(SL.N1, SL.N2, SL.N3);
-  const size_t bufsz = (size_t)gfit.NP * gfit.ld;
-
-  // ---- shared memory carve-up
-  double* buf0 = reinterpret_cast<double*>(smem_raw);
-  double* buf1 = buf0 + bufsz;
-  const size_t bufsz1 = region1_doubles<PM>(gfit);
-  double* lam = buf1 + bufsz1;             // [NP1]
-  double* wgt = lam + g1.NP;               // [NP1]
-  double* jcs = wgt + g1.NP;               // [NP1/2]
-  double* jsn = jcs + g1.NP / 2;           // [NP1/2]
-  double* red = jsn + g1.NP / 2;           // [32]
-  double* rhs = red + 32;                  // [rmax]
-  double* cw = rhs + P.rmax;               // [rmax]
-  double* gc = cw + P.rmax;                // [rmax]
-  double* clb = gc + P.rmax;               // [Lcap*k]
-  double* cub = clb + P.Lcap * k;
-  double* cal = cub + P.Lcap * k;
-  double* cbe = cal + P.Lcap * k;          // [Lcap]
-  double* tgs = cbe + P.Lcap;              // [Lcap]  rho (beta - sg) + mg of the aggregated rows, refreshed every iteration
-  double* xs = tgs + P.Lcap;               // [OMC_XS_CAP] shared-memory copies of the node's cut vectors (when they fit)
-  const double** cxp = reinterpret_cast<const double**>(xs + OMC_XS_CAP);  // [Lcap]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(cxp + P.Lcap);           // [1]
-  int* jrot = reinterpret_cast<int*>(mbar + 1);                         // [3*NP1/2]
-  int* idx = jrot + 3 * (g1.NP / 2);                                    // [NP1]
-  int* jskip = idx + g1.NP;                                             // [NP1] projection-mode skip flags
-  int* ish = jskip + g1.NP;                                             // [8] misc ints
-
-  double* scr = P.scratch + (size_t)blockIdx.x * P.SC.total;
-  double* st = scr + P.SC.state;
-
-  uint32_t mbar_phase = 0;
-#if OMC_USE_TMA
-  if (tid == 0) mbar_init(mbar, 1);
-  __syncthreads();
-#endif
-
+// ------------------------------------------------------------------------------------------------------------------
+// The kernel is split into __noinline__ phase functions that share one frame in shared memory: with everything inlined
+// the register allocator kept ~200 values live across the ADMM loop and spilled into local memory inside the hot loops
+// (80 % of the L2 read traffic of the first version was spill reloads).  Every phase function re-reads the few pointers it
+// needs from the frame; values that change (flags, rho, mbarrier phase, counters) are written back by thread 0.
+// ------------------------------------------------------------------------------------------------------------------
+struct KFrame {
+  double *buf0, *buf1, *lam, *wgt, *jcs, *jsn, *red, *rhs, *cw, *gc, *clb, *cub, *cal, *cbe, *tgs, *xs;
+  const double** cxp;
+  uint64_t* mbar;
+  long long* sprof;
+  int *jrot, *idx, *jskip, *ish;
+  double *scr, *st, *lrZ, *lrR, *lrW;
+  void* lrS;
   NodeCtx c;
-  c.n = n; c.m = m; c.k = k; c.N1 = SL.N1; c.N2 = SL.N2; c.N3 = SL.N3;
-  c.a = P.a; c.sa = P.sa; c.cT = P.cT; c.ktr = P.a * k; c.alpha = P.o.alpha; c.sigma = P.o.sigma;
-  c.A = P.A; c.Mk = P.Mk;
-  c.X = st + SL.X; c.Y = st + SL.Y; c.T = st + SL.T; c.U = st + SL.U;
-  c.Xt = scr + P.SC.wt; c.Yt = c.Xt + (size_t)n * m; c.Tt = c.Yt + (size_t)n * n; c.Ut = c.Tt + (size_t)m * m;
-  c.s1 = st + SL.s1; c.m1 = st + SL.m1; c.s2 = st + SL.s2; c.m2 = st + SL.m2; c.s3 = st + SL.s3; c.m3 = st + SL.m3;
-  c.s5 = st + SL.s5; c.m5 = st + SL.m5; c.sv = st + SL.sv; c.mv = st + SL.mv; c.sg = st + SL.sg; c.mg = st + SL.mg;
-  c.scal = st + SL.scal;
-  c.G = scr + P.SC.G; c.Minv = scr + P.SC.Minv;
-  c.cx = cxp; c.lb = clb; c.ub = cub; c.al = cal; c.be = cbe; c.rhs = rhs; c.cw = cw; c.gc = gc;
-  double* Qg[3] = {scr + P.SC.Q1, scr + P.SC.Q2, scr + P.SC.Q3};
-  double* Zg[3] = {scr + P.SC.Z1, scr + P.SC.Z2, scr + P.SC.Z3};
-  // low-rank projection workspace inside region 1 (panels first, then the small matrices)
-  double* lrZ = buf1;
-  double* lrR = lrZ + (size_t)gfit.NP * OMC_LR_LDZ;
-  double* lrW = lrR + (size_t)gfit.NP * OMC_LR_LDZ;
-  LrSmall<PM>& lrS = *reinterpret_cast<LrSmall<PM>*>(lrW + (size_t)gfit.NP * OMC_LR_LDZ);
-  double* sb[3] = {c.s1, c.s2, c.s3};
-  double* mb[3] = {c.m1, c.m2, c.m3};
-  const Geo gb[3] = {g1, g2, g3};
+  unsigned long long t_start;
+  int node;
+  // per-node iteration state
+  unsigned have_basis_bits;   // bit b: a full eigenvector basis of block b is stored
+  unsigned lr_mode_bits;      // bit b: the block's minority side is tracked by the low-rank projection
+  unsigned lr_neg_bits;       // bit b: the NEGATIVE side of V is the tracked one
+  unsigned lr_p_pack;         // byte b: columns of the tracked basis
+  int exact_iter;             // this iteration runs exact (full) projections on every block
+  int force_check;            // check residuals right after this iteration
+  uint32_t mbar_phase;
+  int status, it;
+  double jtol, res_p, res_d, obj_p, obj_d, lbound;
+  long long nsweeps, n_lr, n_full;
+};
 
-  const unsigned long long t_start = globaltimer_ns();
+#define OMC_BIT(w_, b_) (((w_) >> (b_)) & 1u)
+#define OMC_SETBIT(w_, b_, v_) w_ = ((w_) & ~(1u << (b_))) | ((unsigned)((v_) ? 1u : 0u) << (b_))
+#define OMC_SEL3(b_, x0, x1, x2) ((b_) == 0 ? (x0) : ((b_) == 1 ? (x1) : (x2)))
+#define OMC_QG(b_) (scr + OMC_SEL3(b_, P.SC.Q1, P.SC.Q2, P.SC.Q3))
+#define OMC_ZG(b_) (scr + OMC_SEL3(b_, P.SC.Z1, P.SC.Z2, P.SC.Z3))
+#define OMC_SB(b_) (st + OMC_SEL3(b_, SL.s1, SL.s2, SL.s3))
+#define OMC_MB(b_) (st + OMC_SEL3(b_, SL.m1, SL.m2, SL.m3))
+#define OMC_GB(b_) make_geo(OMC_SEL3(b_, SL.N1, SL.N2, SL.N3))
+#define OMC_TICK(slot)                      \
+  {                                         \
+    const long long now_ = clock64();       \
+    if (tid == 0) sprof[slot] += now_ - tk; \
+    tk = now_;                              \
+  }
+#define OMC_WT(slot) { const long long now_ = clock64(); if (tid == 0) sprof[16 + slot] += now_ - tw; tw = now_; }
 
-  for (;;) {
-    // ---------------------------------------------------------------- next node from the queue
-    __syncthreads();
-    if (tid == 0) ish[0] = atomicAdd(P.queue, 1);
-    __syncthreads();
-    const int node = ish[0];
-    if (node >= P.B) break;
-    if (tid == 0) ish[3] = 0;
-    if (P.prof)
-      for (int q = tid; q < OMC_PROF_STRIDE; q += NT) P.prof[(size_t)node * OMC_PROF_STRIDE + q] = 0.0;
+// locals every phase function starts from (unused ones are dead code)
+#define OMC_FRAME_LOCALS                                                                             \
+  const int tid = threadIdx.x;                                                                       \
+  const int lane = tid & 31, warp = tid >> 5;                                                        \
+  constexpr int NW = NT / 32;                                                                        \
+  const int n = P.n, m = P.m, k = P.k;                                                               \
+  const StateLayout& SL = P.SL;                                                                      \
+  const Geo g1 = make_geo(SL.N1);                                                                    \
+  const Geo gfit = smem_geo(SL.N1, SL.N2, SL.N3);                                                    \
+  const size_t bufsz = (size_t)gfit.NP * gfit.ld;                                                    \
+  const size_t bufsz1 = region1_doubles<PM>(gfit);                                                   \
+  double* const buf0 = F.buf0; double* const buf1 = F.buf1;                                          \
+  double* const lam = F.lam; double* const wgt = F.wgt; double* const jcs = F.jcs; double* const jsn = F.jsn; \
+  double* const red = F.red; double* const rhs = F.rhs; double* const cw = F.cw; double* const gc = F.gc;    \
+  double* const clb = F.clb; double* const cub = F.cub; double* const cal = F.cal; double* const cbe = F.cbe; \
+  double* const tgs = F.tgs; double* const xs = F.xs; const double** const cxp = F.cxp;              \
+  uint64_t* const mbar = F.mbar; long long* const sprof = F.sprof;                                   \
+  int* const jrot = F.jrot; int* const idx = F.idx; int* const jskip = F.jskip; int* const ish = F.ish; \
+  double* const scr = F.scr; double* const st = F.st;                                                \
+  double* const lrZ = F.lrZ; double* const lrR = F.lrR; double* const lrW = F.lrW;                   \
+  LrSmall<PM>& lrS = *reinterpret_cast<LrSmall<PM>*>(F.lrS);                                         \
+  const NodeCtx& c = F.c;                                                                            \
+  const int node = F.node, L = F.c.L, r = F.c.r;                                                     \
+  (void)lane; (void)warp; (void)n; (void)m; (void)k; (void)g1; (void)bufsz; (void)bufsz1; (void)node; (void)L; (void)r; \
+  (void)lam; (void)wgt; (void)jcs; (void)jsn; (void)red; (void)rhs; (void)cw; (void)gc; (void)clb; (void)cub; (void)cal; \
+  (void)cbe; (void)tgs; (void)xs; (void)cxp; (void)mbar; (void)sprof; (void)jrot; (void)idx; (void)jskip; (void)ish; \
+  (void)scr; (void)st; (void)lrZ; (void)lrR; (void)lrW; (void)lrS; (void)buf0; (void)buf1; (void)SL; (void)NW;
 
-    const int e0 = P.node_cut_ptr[node], L = P.node_cut_ptr[node + 1] - e0;
-    const int r = 1 + L * (k + 1);
-    c.L = L; c.r = r;
+template <int NT, int KMAX, int PM>
+__device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
+  OMC_FRAME_LOCALS
+    const int e0 = P.node_cut_ptr[node];
     const int warm = P.warm_ids ? P.warm_ids[node] : -1;
 
     // ---- cut rows (scaled): lb, ub, alpha per column, beta summed over columns
@@ -359,20 +353,21 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
     }
     // ---- initial state: cold (zeros, s = b) or the parent's record
     int Lw = 0;  // number of cut rows carried by the warm-start record
+    double rho_init = P.o.rho0;
     if (warm >= 0) {
       const double* src = P.pool_state + (size_t)warm * SL.total;
       for (size_t e = tid; e < SL.total; e += NT) st[e] = src[e];
       __syncthreads();
       Lw = (int)c.scal[3];
       if (Lw > L) Lw = L;
-      c.rho = c.scal[2];
+      rho_init = c.scal[2];
     } else {
       for (size_t e = tid; e < SL.total; e += NT) st[e] = 0.0;
       __syncthreads();
       for (int i = tid; i < k; i += NT) c.s2[(size_t)(n + i) * SL.N2 + (n + i)] = 1.0;
       for (int i = tid; i < n; i += NT) c.s3[(size_t)i * n + i] = P.a;
       if (tid == 0) c.scal[0] = c.ktr;
-      c.rho = P.o.rho0;
+      rho_init = P.o.rho0;
     }
     __syncthreads();
     // rows of the cuts this node adds on top of the warm-start record: s = clipped row value, mu = 0
@@ -438,34 +433,33 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         c.G[e] = v;
       }
       __syncthreads();
+      if (tid == 0) F.c.rho = rho_init;
+      __syncthreads();
       build_minv(c, buf0, bufsz);
     }
 
-    bool have_basis[3] = {false, false, false};
-    int lr_mode[3] = {0, 0, 0};      // 1: the block's minority side is tracked by the low-rank projection
-    int lr_p[3] = {0, 0, 0};         // columns of the tracked basis
-    int lr_side[3] = {1, 1, 1};      // +1: positive side of V tracked, -1: negative side
-    bool exact_iter = false;         // this iteration runs exact (full) projections on every block
-    bool force_check = false;        // check residuals right after this iteration
-    long long n_lr = 0, n_full = 0;
-    long long lpc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cycles in the sub-phases of the low-rank step
+
+  if (tid < 24) sprof[tid] = 0;   // [0..5] phases, [8..15] sub-phases of the low-rank step, [16..23] of the w-update
+  if (tid == 0) {
+    F.have_basis_bits = 0u; F.lr_mode_bits = 0u; F.lr_neg_bits = 0u; F.lr_p_pack = 0u;
+    F.exact_iter = 0; F.force_check = 0;
     // Eigensolver tolerance follows the ADMM residual: off(S) <= jtol ||S||_F with jtol two orders below the
     // current relative residual, inside [1e-13, jacobi_tol].
-    double jtol = P.o.jacobi_tol;
-    long long pc[6] = {0, 0, 0, 0, 0, 0};
-    long long nsweeps = 0;
-    long long tk = clock64();
-#define OMC_TICK(slot)                 \
-  {                                    \
-    const long long now_ = clock64();  \
-    pc[slot] += now_ - tk;             \
-    tk = now_;                         \
+    F.jtol = P.o.jacobi_tol;
+    F.nsweeps = 0; F.n_lr = 0; F.n_full = 0;
+    F.status = OMC_STATUS_ITERATION_LIMIT;
+    F.res_p = 1e300; F.res_d = 1e300; F.obj_p = 0.0; F.obj_d = -1e300; F.lbound = -1e300;
+    F.it = 0;
   }
-    int status = OMC_STATUS_ITERATION_LIMIT;
-    double res_p = 1e300, res_d = 1e300, obj_p = 0.0, obj_d = -1e300, lbound = -1e300;
-    int it = 0;
+  __syncthreads();
+}
 
-    for (it = 1; it <= P.o.max_iter; ++it) {
+template <int NT, int KMAX, int PM>
+__device__ __noinline__ void relax_phase12(const RelaxArgs& P, KFrame& F) {
+  OMC_FRAME_LOCALS
+  uint32_t mbar_phase = F.mbar_phase;
+  long long tk = clock64();
+  {
       const double rho = c.rho, sig = c.sigma, al = c.alpha;
       const double dYU = sig + 3.0 * rho, dT = sig + rho;
       const double t4 = c.scal[1] + rho * (c.ktr - c.scal[0]);
@@ -493,8 +487,10 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
       __syncthreads();
       // ------------------------------------------------ phase 1: w~ = D^-1 (sigma w - q + A'(rho (b - s) + mu))
       // (loads of a batch are issued before any of its stores: the state record lives in L2)
+      long long tw = clock64();
+#define OMC_WT(slot) { const long long now_ = clock64(); if (tid == 0) sprof[16 + slot] += now_ - tw; tw = now_; }
       {
-        constexpr int UB = 4;
+        constexpr int UB = 2;
         const int nm = n * m;
         for (int e0 = tid; e0 < nm; e0 += NT * UB) {  // X, e = i + n j : w~ and the relaxed w in one pass
           double vm[UB], vs[UB], vk[UB], vx[UB], va[UB];
@@ -547,6 +543,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
             }
           }
         }
+        OMC_WT(0)
         const int nly = n * (n + 1) / 2;
         for (int e0 = tid; e0 < nly; e0 += NT * UB) {  // Y lower -> Ys (both triangles), before the dense-row correction
           double v1m[UB], v1s[UB], v2m[UB], v2s[UB], v3m[UB], v3s[UB], vy[UB];
@@ -597,8 +594,10 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         }
       }
       __syncthreads();
+      OMC_WT(1)
       // ------------------------------------------------ phase 2: Woodbury correction for the dense rows
       dense_rows_apply(c, Ys, ldy, Us, rhs, red);
+      OMC_WT(2)
 #if OMC_USE_TMA
       if (ms_smem) {
         mbar_wait(mbar, mbar_phase);
@@ -618,6 +617,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         v = warp_sum(v);
         if (lane == 0) gc[i] = v;
       }
+      OMC_WT(3)
       // w~ -= R' cw ; then w <- alpha w~ + (1-alpha) w
       {
         const int nly = n * (n + 1) / 2;
@@ -650,6 +650,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         c.m5[e] = rho * (v5 - s5n);
       }
       __syncthreads();
+      OMC_WT(4)
       // scalar rows: trace, cut v rows, cut aggregated rows  (z = b - R w~)
       if (tid == 0) {
         const double z4 = c.ktr - (rhs[0] - gc[0]);
@@ -675,39 +676,54 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
       __syncthreads();
 
       OMC_TICK(0)
-      // ------------------------------------------------ phase 3: the three PSD projections
-      const bool reortho = (P.o.reortho_every > 0) && (it % P.o.reortho_every == 0);
-      for (int b = 0; b < 3; ++b) {
-        const Geo g = gb[b];
+      if (tid == 0) F.mbar_phase = mbar_phase;
+      __syncthreads();
+  }
+}
+
+template <int NT, int KMAX, int PM>
+__device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, const int b) {
+  OMC_FRAME_LOCALS
+  uint32_t mbar_phase = F.mbar_phase;
+  unsigned have_basis_bits = F.have_basis_bits, lr_mode_bits = F.lr_mode_bits, lr_neg_bits = F.lr_neg_bits, lr_p_pack = F.lr_p_pack;
+  const bool exact_iter = F.exact_iter != 0;
+  const double jtol = F.jtol;
+  const int it = F.it;
+  long long nsweeps = 0, n_lr = 0, n_full = 0;
+  const double rho = c.rho, al = c.alpha;
+  const bool reortho = (P.o.reortho_every > 0) && (it % P.o.reortho_every == 0);
+  long long tk = clock64();
+      {
+        const Geo g = OMC_GB(b);
         const int N = g.N, NP = g.NP, ld = g.ld;
         const uint32_t qbytes = (uint32_t)((size_t)NP * ld * sizeof(double));
         const bool fits = (size_t)NP * ld <= bufsz;             // else: L2-resident working buffers
-        const bool use_lr = fits && lr_mode[b] && !exact_iter && !P.o.exact_projection;
-        const bool warmQ = have_basis[b] && !reortho && !exact_iter && !use_lr;
+        const bool use_lr = fits && OMC_BIT(lr_mode_bits, b) && !exact_iter && !P.o.exact_projection;
+        const bool warmQ = OMC_BIT(have_basis_bits, b) && !reortho && !exact_iter && !use_lr;
         double* B0 = fits ? buf0 : (scr + P.SC.big0);
-        double* B1 = fits ? buf1 : Qg[b];
+        double* B1 = fits ? buf1 : OMC_QG(b);
         // start fetching the previous eigenvector basis while V is assembled
 #if OMC_USE_TMA
         if (fits && warmQ && tid == 0) {
           fence_proxy_async();
           mbar_expect_tx(mbar, qbytes);
-          bulk_g2s(B1, Qg[b], qbytes, mbar);
+          bulk_g2s(B1, OMC_QG(b), qbytes, mbar);
         }
 #endif
         if (use_lr) {  // tracked basis -> panel (columns >= p are zero in the stored copy)
-          const double2* src = reinterpret_cast<const double2*>(Zg[b]);
+          const double2* src = reinterpret_cast<const double2*>(OMC_ZG(b));
           for (int e = tid; e < NP * 8; e += NT) {
             const int i = e >> 3, c2 = e & 7;
             *reinterpret_cast<double2*>(lrZ + (size_t)i * OMC_LR_LDZ + 2 * c2) = __ldcg(src + e);
           }
         }
         // V = alpha z + (1-alpha) s + mu/rho, lower triangle computed, both triangles stored
-        const double* sB = sb[b];
-        const double* mB = mb[b];
+        const double* sB = OMC_SB(b);
+        const double* mB = OMC_MB(b);
         const double irho = 1.0 / rho;
         double vsq = 0.0;
         {
-          constexpr int UB = 4;
+          constexpr int UB = 2;
           const int nl = N * (N + 1) / 2;
           for (int e0 = tid; e0 < nl; e0 += NT * UB) {
             double vz[UB], vs[UB], vm[UB];
@@ -751,17 +767,17 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         if (use_lr) {
           const double vscale = sqrt(block_sum(vsq, red));
           __syncthreads();
-          const int need_full = lowrank_step<PM>(B0, ld, N, NP, (double)lr_side[b], lrZ, lrR, lrW, lr_p[b], lrS, vscale, P.prof ? lpc : nullptr, &lrOut);
+          const int need_full = lowrank_step<PM>(B0, ld, N, NP, OMC_BIT(lr_neg_bits, b) ? -1.0 : 1.0, lrZ, lrR, lrW, (int)((lr_p_pack >> (8 * b)) & 0xffu), lrS, vscale, P.prof ? sprof + 8 : nullptr, &lrOut);
           ++n_lr;
           OMC_TICK(2)
           if (!need_full) {
             lr_done = true;
             const int pn = lrS.info[0], r_ = lrS.info[1];
-            lr_p[b] = pn;
+            lr_p_pack = (lr_p_pack & ~(0xffu << (8 * b))) | ((unsigned)pn << (8 * b));
             // store the new basis (16 columns; columns >= pn zero) and set up the reconstruction
             for (int e = tid; e < NP * 16; e += NT) {
               const int i = e >> 4, j = e & 15;
-              Zg[b][e] = (j < pn) ? lrOut[(size_t)i * OMC_LR_LDZ + j] : 0.0;
+              OMC_ZG(b)[e] = (j < pn) ? lrOut[(size_t)i * OMC_LR_LDZ + j] : 0.0;
             }
             if (tid < 16) {
               idx[tid] = (tid < r_) ? tid : 0;
@@ -769,12 +785,12 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
             }
             if (tid == 0) {
               ish[1] = (r_ + 3) & ~3;
-              ish[2] = lr_side[b];
+              ish[2] = OMC_BIT(lr_neg_bits, b) ? -1 : 1;
             }
             __syncthreads();
           } else {
-            lr_mode[b] = 0;          // minority side outgrew the panel: full solve on the intact V, cold basis
-            have_basis[b] = false;
+            OMC_SETBIT(lr_mode_bits, b, 0);   // minority side outgrew the panel: full solve on the intact V, cold basis
+            OMC_SETBIT(have_basis_bits, b, 0);
             __syncthreads();
           }
         }
@@ -787,7 +803,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
               mbar_wait(mbar, mbar_phase);
               mbar_phase ^= 1;
 #else
-              for (int e = tid; e < NP * ld; e += NT) B1[e] = Qg[b][e];
+              for (int e = tid; e < NP * ld; e += NT) B1[e] = OMC_QG(b)[e];
 #endif
             }
             __syncthreads();
@@ -804,7 +820,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           OMC_TICK(2)
           nsweeps += jacobi_sym(B0, B1, NP, ld, exact_iter ? fmin(jtol, 1e-10) : jtol, 40, jcs, jsn, jrot, red, 1, jskip, &ish[4],
                                 P.prof ? (P.prof + (size_t)node * OMC_PROF_STRIDE + 8 + 3 * (b == 0 ? 0 : 1)) : nullptr);
-          have_basis[b] = true;
+          OMC_SETBIT(have_basis_bits, b, 1);
           OMC_TICK(3)
           // eigenvalues, the smaller spectral side, compacted index list (warp 0)
           for (int i = tid; i < NP; i += NT) lam[i] = B0[(size_t)i * ld + i];
@@ -854,12 +870,12 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           __syncthreads();
 #if OMC_USE_TMA
           if (fits && tid == 0) {
-            bulk_s2g(Qg[b], B1, qbytes);
+            bulk_s2g(OMC_QG(b), B1, qbytes);
             bulk_commit();
           }
 #else
           if (fits)
-            for (int e = tid; e < NP * ld; e += NT) Qg[b][e] = B1[e];
+            for (int e = tid; e < NP * ld; e += NT) OMC_QG(b)[e] = B1[e];
 #endif
           // switch to the low-rank projection when the minority side (plus guard band) fits the panel: the tracked
           // basis = the minority-side eigenvectors and the OMC_LR_BUF eigenvectors next to them across zero
@@ -880,13 +896,13 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
             for (int e = tid; e < NP * 16; e += NT) {
               const int i = e >> 4, j = e & 15;
               const int col = jrot[j];
-              Zg[b][e] = (col >= 0 && i < N) ? B1[(size_t)i * ld + col] : 0.0;
+              OMC_ZG(b)[e] = (col >= 0 && i < N) ? B1[(size_t)i * ld + col] : 0.0;
             }
-            lr_mode[b] = 1;
-            lr_p[b] = pz;
-            lr_side[b] = side;
+            OMC_SETBIT(lr_mode_bits, b, 1);
+            lr_p_pack = (lr_p_pack & ~(0xffu << (8 * b))) | ((unsigned)pz << (8 * b));
+            OMC_SETBIT(lr_neg_bits, b, side < 0);
           } else {
-            lr_mode[b] = 0;
+            OMC_SETBIT(lr_mode_bits, b, 0);
           }
         }
         // Z = sum_{i in side} |lam_i| q_i q_i' on lower tiles; s+ = Z (positive side) or V + Z (negative side)
@@ -897,8 +913,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
           const int ntile = T * (T + 1) / 2;
           const double* QB = lr_done ? lrOut : B1;
           const int ldq = lr_done ? OMC_LR_LDZ : ld;
-          double* sW = sb[b];
-          double* mW = mb[b];
+          double* sW = OMC_SB(b);
+          double* mW = OMC_MB(b);
           for (int tl = warp; tl < ntile; tl += NW) {
             // tile (rt, ct), rt >= ct, from the linear index
             int rt = (int)((sqrt(8.0 * tl + 1.0) - 1.0) * 0.5);
@@ -936,21 +952,42 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         __syncthreads();
         OMC_TICK(4)
       }
+  if (tid == 0) {
+    F.mbar_phase = mbar_phase;
+    F.have_basis_bits = have_basis_bits; F.lr_mode_bits = lr_mode_bits; F.lr_neg_bits = lr_neg_bits; F.lr_p_pack = lr_p_pack;
+    F.nsweeps += nsweeps; F.n_lr += n_lr; F.n_full += n_full;
+  }
+  __syncthreads();
+}
 
-      // ------------------------------------------------ phase 4: residuals / termination / rho
-      if (it % P.o.check_every == 0 || it == P.o.max_iter || force_check) {
+// returns true when the node is finished
+template <int NT, int KMAX, int PM>
+__device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
+  OMC_FRAME_LOCALS
+  const int it = F.it;
+  const unsigned lr_mode_bits = F.lr_mode_bits;
+  bool exact_iter = F.exact_iter != 0, force_check = false;
+  double jtol = F.jtol;
+  int status = F.status;
+  double res_p, res_d, obj_p, obj_d, lbound;
+  const double rho = c.rho;
+  const unsigned long long t_start = F.t_start;
+  long long tk;
+  __syncthreads();   // every thread has read the frame before thread 0 rewrites it below
+      {
         tk = clock64();
         // a termination decision taken on tracked (low-rank) projections is only provisional: it is re-taken right
         // after one iteration with exact projections on every block (s in the cone and mu in its polar exactly)
-        const bool provisional = !exact_iter && (lr_mode[0] || lr_mode[1] || lr_mode[2]) && !P.o.exact_projection;
+        const bool provisional = !exact_iter && lr_mode_bits != 0u && !P.o.exact_projection;
         exact_iter = false;
         force_check = false;
         double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0, sxx = 0.0, sfit = 0.0;
         double rpc[7] = {0, 0, 0, 0, 0, 0, 0};  // components: psd1, psd2, psd3, trace, box, v rows, aggregated rows
         // PSD rows
+#pragma unroll
         for (int b = 0; b < 3; ++b) {
-          const int N = gb[b].N;
-          const double* sB = sb[b];
+          const int N = OMC_GB(b).N;
+          const double* sB = OMC_SB(b);
           for (int e = tid; e < N * N; e += NT) {
             const int rr = e / N, cc = e - rr * N;
             if (cc > rr) continue;
@@ -1094,7 +1131,14 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
             stop = true;
           }
         }
-        if (stop) break;
+        if (stop) {
+          if (tid == 0) {
+            F.status = status; F.res_p = res_p; F.res_d = res_d; F.obj_p = obj_p; F.obj_d = obj_d; F.lbound = lbound;
+            F.exact_iter = 0; F.force_check = 0;
+          }
+          __syncthreads();
+          return true;
+        }
         {
           const double rel = fmax(rp / fmax(np_, 1.0), rd / fmax(nd_, 1.0));
           jtol = fmin(P.o.jacobi_tol, fmax(1e-13, 1e-2 * rel));
@@ -1102,21 +1146,37 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
         if (P.o.adapt_every > 0 && it % P.o.adapt_every == 0) {
           const double ratio = sqrt((rp / fmax(np_, 1e-12)) / fmax(rd / fmax(nd_, 1e-12), 1e-30));
           if (ratio > 5.0 || ratio < 0.2) {
-            c.rho = fmin(fmax(rho * ratio, 1e-6), 1e6);
+            if (tid == 0) F.c.rho = fmin(fmax(rho * ratio, 1e-6), 1e6);
+            __syncthreads();
             build_minv(c, buf0, bufsz);
           }
         }
       }
-    }
-    if (it > P.o.max_iter) it = P.o.max_iter;
+  if (tid == 0) {
+    F.status = status; F.res_p = res_p; F.res_d = res_d; F.obj_p = obj_p; F.obj_d = obj_d; F.lbound = lbound;
+    F.exact_iter = exact_iter ? 1 : 0; F.force_check = force_check ? 1 : 0; F.jtol = jtol;
+  }
+  __syncthreads();
+  return false;
+}
+
+template <int NT, int KMAX, int PM>
+__device__ __noinline__ void relax_node_output(const RelaxArgs& P, KFrame& F) {
+  OMC_FRAME_LOCALS
+  const int it = F.it > P.o.max_iter ? P.o.max_iter : F.it;
+  const int status = F.status;
+  const double res_p = F.res_p, res_d = F.res_d, obj_p = F.obj_p, lbound = F.lbound;
+  const long long nsweeps = F.nsweeps, n_lr = F.n_lr, n_full = F.n_full;
+  long long tk = clock64();
     OMC_TICK(5)
     if (P.prof && tid == 0) {
-      for (int q = 0; q < 6; ++q) P.prof[(size_t)node * OMC_PROF_STRIDE + q] = (double)pc[q];
+      for (int q = 0; q < 6; ++q) P.prof[(size_t)node * OMC_PROF_STRIDE + q] = (double)sprof[q];
       P.prof[(size_t)node * OMC_PROF_STRIDE + 6] = (double)nsweeps;
       P.prof[(size_t)node * OMC_PROF_STRIDE + 7] = (double)it;
       P.prof[(size_t)node * OMC_PROF_STRIDE + 14] = (double)n_lr;
       P.prof[(size_t)node * OMC_PROF_STRIDE + 15] = (double)n_full;
-      for (int q = 0; q < 8; ++q) P.prof[(size_t)node * OMC_PROF_STRIDE + 16 + q] = (double)lpc[q];
+      for (int q = 0; q < 8; ++q) P.prof[(size_t)node * OMC_PROF_STRIDE + 16 + q] = (double)sprof[8 + q];
+      for (int q = 0; q < 8; ++q) P.prof[(size_t)node * OMC_PROF_STRIDE + 24 + q] = (double)sprof[16 + q];
     }
 
     // ---------------------------------------------------------------- outputs (original units)
@@ -1153,8 +1213,109 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const RelaxArgs P) 
       double* dst = P.pool_state + (size_t)save * SL.total;
       for (size_t e = tid; e < SL.total; e += NT) dst[e] = st[e];
     }
+  __syncthreads();
+}
+
+template <int NT, int KMAX, int MINB, int PM>
+__global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const __grid_constant__ RelaxArgs P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int k = P.k;
+  const StateLayout& SL = P.SL;
+  const Geo g1 = make_geo(SL.N1);
+  const Geo gfit = smem_geo(SL.N1, SL.N2, SL.N3);
+  const size_t bufsz = (size_t)gfit.NP * gfit.ld;
+
+  // ---- shared memory carve-up
+  double* buf0 = reinterpret_cast<double*>(smem_raw);
+  double* buf1 = buf0 + bufsz;
+  const size_t bufsz1 = region1_doubles<PM>(gfit);
+  double* lam = buf1 + bufsz1;             // [NP1]
+  double* wgt = lam + g1.NP;               // [NP1]
+  double* jcs = wgt + g1.NP;               // [NP1/2]
+  double* jsn = jcs + g1.NP / 2;           // [NP1/2]
+  double* red = jsn + g1.NP / 2;           // [32]
+  double* rhs = red + 32;                  // [rmax]
+  double* cw = rhs + P.rmax;               // [rmax]
+  double* gc = cw + P.rmax;                // [rmax]
+  double* clb = gc + P.rmax;               // [Lcap*k]
+  double* cub = clb + P.Lcap * k;
+  double* cal = cub + P.Lcap * k;
+  double* cbe = cal + P.Lcap * k;          // [Lcap]
+  double* tgs = cbe + P.Lcap;              // [Lcap]  rho (beta - sg) + mg of the aggregated rows, refreshed every iteration
+  double* xs = tgs + P.Lcap;               // [OMC_XS_CAP] shared-memory copies of the node's cut vectors (when they fit)
+  const double** cxp = reinterpret_cast<const double**>(xs + OMC_XS_CAP);  // [Lcap]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(cxp + P.Lcap);           // [1]
+  long long* sprof = reinterpret_cast<long long*>(mbar + 1);            // [24] cycle counters (thread 0 accumulates)
+  KFrame& F = *reinterpret_cast<KFrame*>(sprof + 24);                   // the shared frame
+  int* jrot = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(&F) + ((sizeof(KFrame) + 7) & ~(size_t)7));  // [3*NP1/2]
+  int* idx = jrot + 3 * (g1.NP / 2);                                    // [NP1]
+  int* jskip = idx + g1.NP;                                             // [NP1] projection-mode skip flags
+  int* ish = jskip + g1.NP;                                             // [8] misc ints
+
+  if (tid == 0) {
+    double* scr = P.scratch + (size_t)blockIdx.x * P.SC.total;
+    double* st = scr + P.SC.state;
+    const int n = P.n, m = P.m;
+    F.buf0 = buf0; F.buf1 = buf1; F.lam = lam; F.wgt = wgt; F.jcs = jcs; F.jsn = jsn; F.red = red; F.rhs = rhs; F.cw = cw; F.gc = gc;
+    F.clb = clb; F.cub = cub; F.cal = cal; F.cbe = cbe; F.tgs = tgs; F.xs = xs; F.cxp = cxp; F.mbar = mbar; F.sprof = sprof;
+    F.jrot = jrot; F.idx = idx; F.jskip = jskip; F.ish = ish; F.scr = scr; F.st = st;
+    // low-rank projection workspace inside region 1 (panels first, then the small matrices)
+    F.lrZ = buf1;
+    F.lrR = F.lrZ + (size_t)gfit.NP * OMC_LR_LDZ;
+    F.lrW = F.lrR + (size_t)gfit.NP * OMC_LR_LDZ;
+    F.lrS = F.lrW + (size_t)gfit.NP * OMC_LR_LDZ;
+    NodeCtx& c = F.c;
+    c.n = n; c.m = m; c.k = k; c.N1 = SL.N1; c.N2 = SL.N2; c.N3 = SL.N3; c.L = 0; c.r = 1;
+    c.a = P.a; c.sa = P.sa; c.cT = P.cT; c.ktr = P.a * k; c.alpha = P.o.alpha; c.sigma = P.o.sigma; c.rho = P.o.rho0;
+    c.A = P.A; c.Mk = P.Mk;
+    c.X = st + SL.X; c.Y = st + SL.Y; c.T = st + SL.T; c.U = st + SL.U;
+    c.Xt = scr + P.SC.wt; c.Yt = c.Xt + (size_t)n * m; c.Tt = c.Yt + (size_t)n * n; c.Ut = c.Tt + (size_t)m * m;
+    c.s1 = st + SL.s1; c.m1 = st + SL.m1; c.s2 = st + SL.s2; c.m2 = st + SL.m2; c.s3 = st + SL.s3; c.m3 = st + SL.m3;
+    c.s5 = st + SL.s5; c.m5 = st + SL.m5; c.sv = st + SL.sv; c.mv = st + SL.mv; c.sg = st + SL.sg; c.mg = st + SL.mg;
+    c.scal = st + SL.scal;
+    c.G = scr + P.SC.G; c.Minv = scr + P.SC.Minv;
+    c.cx = cxp; c.lb = clb; c.ub = cub; c.al = cal; c.be = cbe; c.rhs = rhs; c.cw = cw; c.gc = gc;
+    F.mbar_phase = 0;
+    F.t_start = globaltimer_ns();
+#if OMC_USE_TMA
+    mbar_init(mbar, 1);
+#endif
+  }
+  __syncthreads();
+
+  for (;;) {
+    // ---------------------------------------------------------------- next node from the queue
+    __syncthreads();
+    if (tid == 0) {
+      const int node = atomicAdd(P.queue, 1);
+      F.node = node;
+      ish[3] = 0;
+      if (node < P.B) {
+        const int L = P.node_cut_ptr[node + 1] - P.node_cut_ptr[node];
+        F.c.L = L;
+        F.c.r = 1 + L * (k + 1);
+      }
+    }
+    __syncthreads();
+    const int node = F.node;
+    if (node >= P.B) break;
+    if (P.prof)
+      for (int q = tid; q < OMC_PROF_STRIDE; q += NT) P.prof[(size_t)node * OMC_PROF_STRIDE + q] = 0.0;
+    relax_node_setup<NT, KMAX, PM>(P, F);
+    for (int it = 1; it <= P.o.max_iter; ++it) {
+      if (tid == 0) F.it = it;
+      __syncthreads();
+      relax_phase12<NT, KMAX, PM>(P, F);
+      for (int b = 0; b < 3; ++b) relax_project_block<NT, KMAX, PM>(P, F, b);
+      if (it % P.o.check_every == 0 || it == P.o.max_iter || F.force_check) {
+        if (relax_phase4<NT, KMAX, PM>(P, F)) break;
+      }
+    }
+    relax_node_output<NT, KMAX, PM>(P, F);
   }
 }
+
 
 // shared memory bytes the kernel carves up (must mirror the carve-up above)
 template <int PM>
@@ -1170,7 +1331,8 @@ inline size_t relax_smem_bytes(int n, int m, int k, int Lcap, int rmax) {
   d += 3 * (size_t)Lcap * k + Lcap;      // clb, cub, cal, cbe
   d += (size_t)Lcap;                     // cxp (pointers, 8 bytes)
   d += (size_t)Lcap + OMC_XS_CAP;        // tgs, xs
-  d += 1;                                // mbar
+  d += 1 + 24;                           // mbar, sprof
+  d += (sizeof(KFrame) + 7) / 8;         // the shared frame
   size_t bytes = d * 8;
   bytes += sizeof(int) * (3 * ((size_t)g1.NP / 2) + 2 * (size_t)g1.NP + 8);
   return (bytes + 127) & ~(size_t)127;

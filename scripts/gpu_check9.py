@@ -16,6 +16,8 @@ def run(nodes_, label, **kw):
           f"| lr proj {pm[14]:.0f} full proj {pm[15]:.0f} sweeps {pm[6]:.0f}", flush=True)
     if pm[14] > 0:
         print("    lr step cycles/proj:", " ".join(f"{nm}={pm[16+q]/pm[14]/1e3:.2f}k" for q, nm in enumerate(lrn)), f"total={pm[16:24].sum()/pm[14]/1e3:.1f}k", flush=True)
+        wn = ["X,T loops", "Y,U loops", "dense rows", "woodbury", "corrections"]
+        print("    w-update cycles/iter:", " ".join(f"{nm}={pm[24+q]/pm[7]/1e3:.1f}k" for q, nm in enumerate(wn)), flush=True)
     return out
 golden = json.load(open(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "check9_ref.json"))) if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "check9_ref.json")) else None
 sub = nodes[:4]
