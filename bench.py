@@ -261,6 +261,7 @@ def run_b200(args):
         e2e_step()
     barrier()
     e2e_wall = (time.perf_counter() - t0) / e2e_steps
+    print(f"[bench rank {rank}] kernel ms per step {[round(v) for v in kernel_ms]}, e2e wall ms per step {e2e_wall * 1e3:.0f}, e2e kernel iters {int(h_iters.sum())} vs {int(iters.sum())}", file=sys.stderr, flush=True)
 
     # ---- max over ranks
     tmax = torch.tensor([dev_ms, wall / args.steps * 1e3, e2e_wall * 1e3], dtype=torch.float64, device="cuda")

@@ -53,9 +53,10 @@ def psd_project(V):
 
 
 class Options:
-    def __init__(self, eps_abs=1e-7, eps_rel=1e-7, max_iter=20000, rho=0.1, sigma=1e-6,
+    def __init__(self, eps_abs=1e-7, eps_rel=1e-7, max_iter=20000, rho=0.3, sigma=1e-6,
                  alpha=1.6, check_every=25, adapt_every=100, adaptive_rho=True,
-                 eps_inf=1e-6, fix_linear3_right=False, scale=None, verbose=False, projection="exact", pm=16):
+                 eps_inf=1e-6, fix_linear3_right=False, scale=None, verbose=False, projection="exact", pm=16,
+                 adapt_thresh=5.0):
         self.__dict__.update(locals()); del self.__dict__["self"]
 
 
@@ -271,7 +272,7 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
             # ---- adaptive rho (residual balancing, OSQP style)
             if o.adaptive_rho and it % o.adapt_every == 0:
                 ratio = np.sqrt((rp / max(n_p, 1e-12)) / max(rd / max(n_d, 1e-12), 1e-30))
-                if ratio > 5.0 or ratio < 0.2:
+                if ratio > o.adapt_thresh or ratio < 1.0 / o.adapt_thresh:
                     rho = float(np.clip(rho * ratio, 1e-6, 1e6))
     st.rho = rho
     X, Y, T, U = st.X, st.Y / c.a, st.T * c.a, st.U / c.sa

@@ -32,7 +32,7 @@ def test_opts_struct_layout_and_defaults():
     assert ctypes.sizeof(o) == 88
     assert o.eps_abs == 1e-8 and o.eps_rel == 1e-8 and o.max_iter == 20000
     assert o.check_every == 25 and o.adapt_every == 100 and o.fix_linear3_right == 0
-    assert o.rho0 == 0.1 and o.sigma == 1e-6 and o.alpha == 1.6 and o.cutoff == float("inf")
+    assert o.rho0 == 0.3 and o.sigma == 1e-6 and o.alpha == 1.6 and o.cutoff == float("inf")
     with pytest.raises(TypeError):
         omc_b200.default_opts(nonsense=1)
 
