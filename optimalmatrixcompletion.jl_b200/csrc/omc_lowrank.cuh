@@ -207,7 +207,7 @@ __device__ __forceinline__ void schur_rot(double app, double aqq, double apq, do
 // sides at once, in place (a block is read and written by one thread only).  A step in which no pivot exceeds
 // skip_tol * sqrt|a_pp a_qq| is skipped (the barrier doubles as the vote), which makes warm sweeps cheap.
 __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld, int sweeps, double* cs, double* sn,
-                                             int* ptab, int ldt, double skip_tol) {
+                                             int* ptab, int ldt, double skip_tol, long long* lp = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int h = n >> 1;
   const int nblk = h * h, items = nblk + h * n;
@@ -226,6 +226,7 @@ __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld
     for (int t = 0; t < n - 1; ++t) {
       const int* pt = ptab + t * ldt;
       int need = 0;
+      const long long tp0 = clock64();
       if (tid < h) {
         const int pq = pt[tid], p = pq >> 8, q = pq & 0xff;
         const double app = M[p * ld + p], aqq = M[q * ld + q], apq = M[p * ld + q];
@@ -237,7 +238,9 @@ __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld
         cs[tid] = c;
         sn[tid] = s_;
       }
-      if (!__syncthreads_or(need)) continue;
+      const int any = __syncthreads_or(need);
+      if (lp && tid == 0) lp[7] += clock64() - tp0;
+      if (!any) continue;
       for (int it = tid, k = 0; it < items; it += nt, ++k) {
         int ia, ib;
         if (k == 0) { ia = ia0; ib = ib0; }
@@ -364,7 +367,7 @@ __device__ __noinline__ int lowrank_step(const double* V, int ldv, int N, int NP
     S.G2[ia * LD2 + ib] = (ia == ib) ? 1.0 : 0.0;
   }
   __syncthreads();
-  small_jacobi(S.H2, S.G2, n2, LD2, OMC_LR_SWEEPS, S.cs, S.sn, S.ptab, PM, 1e-15);
+  small_jacobi(S.H2, S.G2, n2, LD2, OMC_LR_SWEEPS, S.cs, S.sn, S.ptab, PM, 1e-15, lp);
   const double* Hd = S.H2;
   OMC_LRT(5)
   // Ritz values, selection of the top r + BUF (warp 0)

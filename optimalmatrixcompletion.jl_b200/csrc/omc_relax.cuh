@@ -275,7 +275,12 @@ struct KFrame {
   uint32_t mbar_phase;
   int status, it;
   double jtol, res_p, res_d, obj_p, obj_d, lbound;
-  long long nsweeps, n_lr, n_full;
+  long long nsweeps, n_lr, n_full, n_idle;
+  // idle tracker: a block whose minority side is EMPTY (r = 0: the projection is the identity or zero) is not re-tracked
+  // while the accumulated change of V since the last tracking step, sum ||alpha (z - s)||_F, stays below half the
+  // distance of its spectrum from zero (lr_margin, the top Ritz value of the tracked guard pair)
+  double lr_margin[3], lr_drift[3];
+  int lr_r[3];
 };
 
 #define OMC_BIT(w_, b_) (((w_) >> (b_)) & 1u)
@@ -446,7 +451,8 @@ __device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
     // Eigensolver tolerance follows the ADMM residual: off(S) <= jtol ||S||_F with jtol two orders below the
     // current relative residual, inside [1e-13, jacobi_tol].
     F.jtol = P.o.jacobi_tol;
-    F.nsweeps = 0; F.n_lr = 0; F.n_full = 0;
+    F.nsweeps = 0; F.n_lr = 0; F.n_full = 0; F.n_idle = 0;
+    for (int b = 0; b < 3; ++b) { F.lr_margin[b] = 0.0; F.lr_drift[b] = 0.0; F.lr_r[b] = -1; }
     F.status = OMC_STATUS_ITERATION_LIMIT;
     F.res_p = 1e300; F.res_d = 1e300; F.obj_p = 0.0; F.obj_d = -1e300; F.lbound = -1e300;
     F.it = 0;
@@ -721,7 +727,7 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
         const double* sB = OMC_SB(b);
         const double* mB = OMC_MB(b);
         const double irho = 1.0 / rho;
-        double vsq = 0.0;
+        double vsq = 0.0, dsq = 0.0;
         {
           constexpr int UB = 2;
           const int nl = N * (N + 1) / 2;
@@ -750,7 +756,9 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
                 const double v = al * vz[u] + (1.0 - al) * vs[u] + vm[u] * irho;
                 B0[(size_t)r_[u] * ld + c_[u]] = v;
                 B0[(size_t)c_[u] * ld + r_[u]] = v;
-                vsq += ((r_[u] == c_[u]) ? 1.0 : 2.0) * v * v;
+                const double wgt2 = (r_[u] == c_[u]) ? 1.0 : 2.0, dz = vz[u] - vs[u];
+                vsq += wgt2 * v * v;
+                dsq += wgt2 * dz * dz;
               }
             }
           }
@@ -766,11 +774,25 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
         double* lrOut = lrW;
         if (use_lr) {
           const double vscale = sqrt(block_sum(vsq, red));
+          const double dstep = al * sqrt(block_sum(dsq, red));   // ||V - V_prev||_F = alpha ||z - s||_F
           __syncthreads();
-          const int need_full = lowrank_step<PM>(B0, ld, N, NP, OMC_BIT(lr_neg_bits, b) ? -1.0 : 1.0, lrZ, lrR, lrW, (int)((lr_p_pack >> (8 * b)) & 0xffu), lrS, vscale, P.prof ? sprof + 8 : nullptr, &lrOut);
-          ++n_lr;
+          const bool idle = !P.o.exact_projection && F.lr_r[b] == 0 && (F.lr_drift[b] + dstep) < 0.5 * F.lr_margin[b];
+          if (idle) {  // nothing can have crossed zero: s+ = V (or 0), mu+ = 0 (or rho V); the guard pair is kept as it is
+            lr_done = true;
+            __syncthreads();
+            if (tid == 0) {
+              F.lr_drift[b] += dstep;
+              F.n_idle += 1;
+              ish[1] = 0;
+              ish[2] = OMC_BIT(lr_neg_bits, b) ? -1 : 1;
+            }
+            __syncthreads();
+          }
+          const int need_full = idle ? 0 : lowrank_step<PM>(B0, ld, N, NP, OMC_BIT(lr_neg_bits, b) ? -1.0 : 1.0, lrZ, lrR, lrW, (int)((lr_p_pack >> (8 * b)) & 0xffu), lrS, vscale, P.prof ? sprof + 8 : nullptr, &lrOut);
+          if (!idle) ++n_lr;
           OMC_TICK(2)
-          if (!need_full) {
+          if (idle) {
+          } else if (!need_full) {
             lr_done = true;
             const int pn = lrS.info[0], r_ = lrS.info[1];
             lr_p_pack = (lr_p_pack & ~(0xffu << (8 * b))) | ((unsigned)pn << (8 * b));
@@ -784,6 +806,9 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
               wgt[tid] = (tid < r_) ? lrS.th[tid] : 0.0;
             }
             if (tid == 0) {
+              F.lr_r[b] = r_;
+              F.lr_drift[b] = 0.0;
+              F.lr_margin[b] = (r_ == 0 && pn > 0 && -lrS.th[0] > 1e-4 * vscale) ? -lrS.th[0] : 0.0;
               ish[1] = (r_ + 3) & ~3;
               ish[2] = OMC_BIT(lr_neg_bits, b) ? -1 : 1;
             }
@@ -899,6 +924,7 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
               OMC_ZG(b)[e] = (col >= 0 && i < N) ? B1[(size_t)i * ld + col] : 0.0;
             }
             OMC_SETBIT(lr_mode_bits, b, 1);
+            if (tid == 0) { F.lr_r[b] = -1; F.lr_margin[b] = 0.0; F.lr_drift[b] = 0.0; }
             lr_p_pack = (lr_p_pack & ~(0xffu << (8 * b))) | ((unsigned)pz << (8 * b));
             OMC_SETBIT(lr_neg_bits, b, side < 0);
           } else {
@@ -1166,7 +1192,7 @@ __device__ __noinline__ void relax_node_output(const RelaxArgs& P, KFrame& F) {
   const int it = F.it > P.o.max_iter ? P.o.max_iter : F.it;
   const int status = F.status;
   const double res_p = F.res_p, res_d = F.res_d, obj_p = F.obj_p, lbound = F.lbound;
-  const long long nsweeps = F.nsweeps, n_lr = F.n_lr, n_full = F.n_full;
+  const long long nsweeps = F.nsweeps, n_lr = F.n_lr, n_full = F.n_full, n_idle = F.n_idle;
   long long tk = clock64();
     OMC_TICK(5)
     if (P.prof && tid == 0) {
@@ -1175,6 +1201,7 @@ __device__ __noinline__ void relax_node_output(const RelaxArgs& P, KFrame& F) {
       P.prof[(size_t)node * OMC_PROF_STRIDE + 7] = (double)it;
       P.prof[(size_t)node * OMC_PROF_STRIDE + 14] = (double)n_lr;
       P.prof[(size_t)node * OMC_PROF_STRIDE + 15] = (double)n_full;
+      P.prof[(size_t)node * OMC_PROF_STRIDE + 13] = (double)n_idle;
       for (int q = 0; q < 8; ++q) P.prof[(size_t)node * OMC_PROF_STRIDE + 16 + q] = (double)sprof[8 + q];
       for (int q = 0; q < 8; ++q) P.prof[(size_t)node * OMC_PROF_STRIDE + 24 + q] = (double)sprof[16 + q];
     }
