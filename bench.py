@@ -306,6 +306,12 @@ def run_b200(args):
                          "altmin_c5": {"n_iters": am["n_iters"], "converged": am["converged"], "objective": am["objectives"][-1], "solve_time_s": am["solve_time"]}}
             p5.close()
         peak_tf = peaks["dmma_tflops"]
+        traffic = None
+        try:   # DRAM bytes per ADMM iteration from the committed ncu --set full capture of this kernel
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_relax_summary.json")) as f:
+                traffic = float(json.load(f)["dram_bytes_per_admm_iteration"]) * total_iters / max(1, world)
+        except Exception:
+            traffic = None
         achieved_tf = (flops_step / (dev_ms * 1e-3)) * 1e-12          # this rank's kernel
         line = {
             "metric": "nodes relaxed/sec", "value": total_nodes / (dev_ms_max * 1e-3), "unit": "nodes/s", "n_gpus": world,
@@ -317,9 +323,12 @@ def run_b200(args):
                        "frontier_setup_s": setup_s, "wall_ms_per_step": wall_ms_max},
             "e2e": {"value": total_nodes / (e2e_ms_max * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": args.steps,
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
-                         "note": "FP64: algorithmic flops = iterations x 16/3 (N1^3+N2^3+N3^3) (+ cut rows) of the fused relaxation kernel; peak = DMMA m8n8k4 FP64 "
-                                 f"measured in this run (DFMA {peaks['dfma_tflops']:.1f} TF); MEASURED_PEAKS.json carries no FP64 figure"},
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+                         "note": "FP64: algorithmic flops = iterations x 16/3 (N1^3+N2^3+N3^3) (+ cut rows) of the fused relaxation kernel (SURVEY 8d); the tracked "
+                                 "low-rank projection executes ~10x fewer flops than that and the kernel is bound by dependent-latency chains, not by the FP64 pipe "
+                                 "(DESIGN.md 4-5); peak = DMMA m8n8k4 FP64 "
+                                 f"measured in this run (DFMA {peaks['dfma_tflops']:.1f} TF); MEASURED_PEAKS.json carries no FP64 figure; traffic = DRAM bytes per launch "
+                                 "estimated as iterations x the per-iteration DRAM bytes of the committed ncu capture (profiles/r01_ncu_relax_summary.json)"},
             "clocks": sampler.summary(),
         }
         if cpu is not None:

@@ -95,6 +95,7 @@ struct omc_frontier {
   bool has_warm = false, has_save = false, want_T = false;
   size_t smem = 0;
   int variant = 0;
+  int xs_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -385,7 +386,8 @@ int32_t omc_problem_create(int32_t n, int32_t m, int32_t k, const double* A, con
   if (cut_type < 0 || cut_type > 2) return fail(OMC_ERR_ARG, "cut_type must be 0 (linear), 1 (linear2) or 2 (linear3)");
   omc_problem* p = new omc_problem();
   p->n = n; p->m = m; p->k = k; p->cut_type = cut_type; p->gamma = gamma;
-  p->Lcap = 64;
+  // cuts per node (= depth): P^k children per split keep trees with large k shallow; n + m > 104 needs the shared memory
+  p->Lcap = (n + m > 104) ? 32 : 64;
   p->state_cap = state_pool_capacity > 0 ? state_pool_capacity : 0;
   const long long total = (long long)n * m;
   const size_t nchunks = (size_t)((total + 63) / 64);
@@ -550,8 +552,15 @@ int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_p
   f->grid = g_sm_count * ctas_per_sm;
   if (f->grid > B) f->grid = B;
   f->SC = omc::make_scratch_layout(p->SL, f->rmax);
-  f->smem = (f->variant == 0) ? omc::relax_smem_bytes<8>(p->n, p->m, p->k, p->Lcap, f->rmax)
-                              : omc::relax_smem_bytes<16>(p->n, p->m, p->k, p->Lcap, f->rmax);
+  // cut vectors are cached in shared memory except where the panels of the tracked projection need the room (n + m > 104)
+  f->xs_cap = (f->variant == 3) ? 0 : OMC_XS_CAP;
+  f->smem = (f->variant == 0) ? omc::relax_smem_bytes<8>(p->n, p->m, p->k, p->Lcap, f->rmax, f->xs_cap)
+                              : omc::relax_smem_bytes<16>(p->n, p->m, p->k, p->Lcap, f->rmax, f->xs_cap);
+  if (f->smem > 227 * 1024) {
+    const size_t need = f->smem;
+    delete f;
+    return fail(OMC_ERR_UNSUPPORTED, "shared memory need %zu bytes exceeds 227 KB for n = %d, m = %d, k = %d", need, p->n, p->m, p->k);
+  }
   cudaError_t e;
 #define FC(call)                                                                \
   do {                                                                          \
@@ -616,7 +625,7 @@ int32_t omc_frontier_relax(omc_frontier* f, const omc_relax_opts* opts, float* k
   a.status = f->status.p; a.objective = f->objective.p; a.lower_bound = f->lower_bound.p; a.iters = f->iters.p;
   a.prof = f->prof.p;
   a.res = f->res.p; a.outX = f->X.p; a.outY = f->Y.p; a.outU = f->U.p; a.outT = f->T.p;
-  a.o = o; a.Lcap = p->Lcap; a.rmax = f->rmax; a.SL = p->SL; a.SC = f->SC;
+  a.o = o; a.Lcap = p->Lcap; a.rmax = f->rmax; a.xs_cap = f->xs_cap; a.SL = p->SL; a.SC = f->SC;
   CU(cudaMemsetAsync(f->queue.p, 0, sizeof(int), g_stream));
   CU(cudaEventRecord(f->ev0, g_stream));
   if (f->variant == 0) {

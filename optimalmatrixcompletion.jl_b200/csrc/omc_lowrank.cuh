@@ -75,8 +75,10 @@ __device__ __forceinline__ void panel_gram(const double* __restrict__ A, const d
   }
 }
 
-// Wout[i][0..pc) = scale * sum_k V[i][k] * Zin[k][0..pc)   (V symmetric N x N in shared memory, leading dimension ldv)
-__device__ __forceinline__ void panel_vmul(const double* __restrict__ V, int ldv, int N, int NP,
+// Wout[i][0..pc) = scale * sum_k V[i][k] * Zin[k][0..pc)   (V symmetric N x N, both triangles, leading dimension ldv).
+// V in shared memory: thread (row i, 4 columns) walks its row.  V in a global (L2-resident) buffer, vglobal: the same
+// thread walks COLUMN i instead (V[k][i] = V[i][k]) so that the 8 rows of a warp read 64 contiguous bytes per step.
+__device__ __forceinline__ void panel_vmul(const double* __restrict__ V, int ldv, bool vglobal, int N, int NP,
                                            const double* __restrict__ Zin, double* __restrict__ Wout, int pc, double scale) {
   const int ng = pc >> 2;
   const int items = NP * ng;
@@ -84,14 +86,25 @@ __device__ __forceinline__ void panel_vmul(const double* __restrict__ V, int ldv
     const int i = it / ng, jg = it - i * ng;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     if (i < N) {
-      const double* vr = V + (size_t)i * ldv;
       const double* zc = Zin + 4 * jg;
+      if (!vglobal) {
+        const double* vr = V + (size_t)i * ldv;
 #pragma unroll 4
-      for (int k = 0; k < N; ++k) {
-        const double v = vr[k];
-        const double2 z01 = *reinterpret_cast<const double2*>(zc + (size_t)k * OMC_LR_LDZ);
-        const double2 z23 = *reinterpret_cast<const double2*>(zc + (size_t)k * OMC_LR_LDZ + 2);
-        a0 += v * z01.x; a1 += v * z01.y; a2 += v * z23.x; a3 += v * z23.y;
+        for (int k = 0; k < N; ++k) {
+          const double v = vr[k];
+          const double2 z01 = *reinterpret_cast<const double2*>(zc + (size_t)k * OMC_LR_LDZ);
+          const double2 z23 = *reinterpret_cast<const double2*>(zc + (size_t)k * OMC_LR_LDZ + 2);
+          a0 += v * z01.x; a1 += v * z01.y; a2 += v * z23.x; a3 += v * z23.y;
+        }
+      } else {
+        const double* vcol = V + i;
+#pragma unroll 8
+        for (int k = 0; k < N; ++k) {
+          const double v = __ldcg(vcol + (size_t)k * ldv);
+          const double2 z01 = *reinterpret_cast<const double2*>(zc + (size_t)k * OMC_LR_LDZ);
+          const double2 z23 = *reinterpret_cast<const double2*>(zc + (size_t)k * OMC_LR_LDZ + 2);
+          a0 += v * z01.x; a1 += v * z01.y; a2 += v * z23.x; a3 += v * z23.y;
+        }
       }
     }
     double* w = Wout + (size_t)i * OMC_LR_LDZ + 4 * jg;
@@ -203,24 +216,29 @@ __device__ __forceinline__ void schur_rot(double app, double aqq, double apq, do
 
 // Cyclic two-sided Jacobi sweeps on the symmetric n x n matrix M (n even, <= 32, leading dimension ld, both
 // triangles), rotations accumulated into G (G <- G J).  Round-robin ordering, all threads of the CTA: the first n/2
-// threads compute the rotation parameters of a step, then every 2x2 block (pair a, pair b) is updated on both
-// sides at once, in place (a block is read and written by one thread only).  A step in which no pivot exceeds
-// skip_tol * sqrt|a_pp a_qq| is skipped (the barrier doubles as the vote), which makes warm sweeps cheap.
+// threads compute the rotation parameters of a step (a serial chain of ~500 cycles: two dependent FP64 rsqrt), then
+// every 2x2 block (pair a, pair b) of M is updated on both sides at once, in place, and the columns of G are rotated;
+// the M blocks and the G entries are mapped to different warps (no divergence), one item per thread when the CTA is
+// large enough.  A step in which no pivot exceeds skip_tol * sqrt|a_pp a_qq| is skipped (the barrier is the vote).
 __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld, int sweeps, double* cs, double* sn,
                                              int* ptab, int ldt, double skip_tol, long long* lp = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int h = n >> 1;
-  const int nblk = h * h, items = nblk + h * n;
+  const int nblk = h * h, ngi = h * n;
+  const int g0 = (nblk + 31) & ~31;                    // first thread of the G items (warp aligned)
+  const bool one_pass = (g0 + ngi <= nt);
   for (int e = tid; e < (n - 1) * h; e += nt) {
     const int t = e / h, a = e - t * h;
     int p, q;
     jacobi_pair(a, t, n, p, q);
     ptab[t * ldt + a] = (p << 8) | q;
   }
-  // static item descriptors (at most two items per thread are kept in registers; more fall back to recomputation)
-  int ia0 = -1, ib0 = 0, ia1 = -1, ib1 = 0;
-  if (tid < items) { if (tid < nblk) { ia0 = tid / h; ib0 = tid - ia0 * h; } else { const int e = tid - nblk; ia0 = e / n; ib0 = e - ia0 * n; } }
-  if (tid + nt < items) { const int it = tid + nt; if (it < nblk) { ia1 = it / h; ib1 = it - ia1 * h; } else { const int e = it - nblk; ia1 = e / n; ib1 = e - ia1 * n; } }
+  // static item of this thread in the one-pass mapping
+  int ia0 = -1, ib0 = 0;
+  if (one_pass) {
+    if (tid < nblk) { ia0 = tid / h; ib0 = tid - ia0 * h; }
+    else if (tid >= g0 && tid < g0 + ngi) { const int e = tid - g0; ia0 = e / n; ib0 = e - ia0 * n; }
+  }
   __syncthreads();
   for (int sw = 0; sw < sweeps; ++sw) {
     for (int t = 0; t < n - 1; ++t) {
@@ -228,7 +246,8 @@ __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld
       int need = 0;
       const long long tp0 = clock64();
       if (tid < h) {
-        const int pq = pt[tid], p = pq >> 8, q = pq & 0xff;
+        int p, q;
+        jacobi_pair(tid, t, n, p, q);
         const double app = M[p * ld + p], aqq = M[q * ld + q], apq = M[p * ld + q];
         double c = 1.0, s_ = 0.0;
         if (apq * apq > skip_tol * skip_tol * fabs(app * aqq)) {
@@ -241,13 +260,9 @@ __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld
       const int any = __syncthreads_or(need);
       if (lp && tid == 0) lp[7] += clock64() - tp0;
       if (!any) continue;
-      for (int it = tid, k = 0; it < items; it += nt, ++k) {
-        int ia, ib;
-        if (k == 0) { ia = ia0; ib = ib0; }
-        else if (k == 1) { ia = ia1; ib = ib1; }
-        else if (it < nblk) { ia = it / h; ib = it - ia * h; }
-        else { const int e = it - nblk; ia = e / n; ib = e - ia * n; }
-        if (it < nblk) {
+      if (one_pass) {
+        if (tid < nblk) {
+          const int ia = ia0, ib = ib0;
           const int pqa = pt[ia], pa = pqa >> 8, qa = pqa & 0xff;
           const int pqb = pt[ib], pb = pqb >> 8, qb = pqb & 0xff;
           const double ca = cs[ia], sa = sn[ia], cb = cs[ib], sb = sn[ib];
@@ -256,12 +271,34 @@ __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld
           double x2 = cb * x1 - sb * y1, y2 = sb * x1 + cb * y1, z2 = cb * z1 - sb * w1, w2 = sb * z1 + cb * w1;
           if (ia == ib && sa != 0.0) { y2 = 0.0; z2 = 0.0; }
           M[pa * ld + pb] = x2; M[pa * ld + qb] = y2; M[qa * ld + pb] = z2; M[qa * ld + qb] = w2;
-        } else {
-          const int pq = pt[ia], p = pq >> 8, q = pq & 0xff, r = ib;
-          const double c = cs[ia], s_ = sn[ia];
+        } else if (ia0 >= 0) {
+          const int pq = pt[ia0], p = pq >> 8, q = pq & 0xff, r = ib0;
+          const double c = cs[ia0], s_ = sn[ia0];
           const double x = G[r * ld + p], y = G[r * ld + q];
           G[r * ld + p] = c * x - s_ * y;
           G[r * ld + q] = s_ * x + c * y;
+        }
+      } else {
+        for (int it = tid; it < nblk + ngi; it += nt) {
+          if (it < nblk) {
+            const int ia = it / h, ib = it - ia * h;
+            const int pqa = pt[ia], pa = pqa >> 8, qa = pqa & 0xff;
+            const int pqb = pt[ib], pb = pqb >> 8, qb = pqb & 0xff;
+            const double ca = cs[ia], sa = sn[ia], cb = cs[ib], sb = sn[ib];
+            const double x = M[pa * ld + pb], y = M[pa * ld + qb], z = M[qa * ld + pb], w = M[qa * ld + qb];
+            const double x1 = ca * x - sa * z, z1 = sa * x + ca * z, y1 = ca * y - sa * w, w1 = sa * y + ca * w;
+            double x2 = cb * x1 - sb * y1, y2 = sb * x1 + cb * y1, z2 = cb * z1 - sb * w1, w2 = sb * z1 + cb * w1;
+            if (ia == ib && sa != 0.0) { y2 = 0.0; z2 = 0.0; }
+            M[pa * ld + pb] = x2; M[pa * ld + qb] = y2; M[qa * ld + pb] = z2; M[qa * ld + qb] = w2;
+          } else {
+            const int e = it - nblk;
+            const int ia = e / n, r = e - ia * n;
+            const int pq = pt[ia], p = pq >> 8, q = pq & 0xff;
+            const double c = cs[ia], s_ = sn[ia];
+            const double x = G[r * ld + p], y = G[r * ld + q];
+            G[r * ld + p] = c * x - s_ * y;
+            G[r * ld + q] = s_ * x + c * y;
+          }
         }
       }
       __syncthreads();
@@ -275,7 +312,7 @@ __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld
 // side of V, -1 the negative side (the positive side of -V).  lp (optional, 8 slots): cycles per sub-phase.
 // Returns need_full (uniform over the CTA).
 template <int PM>
-__device__ __noinline__ int lowrank_step(const double* V, int ldv, int N, int NP, double side, double* P0, double* P1, double* P2,
+__device__ __noinline__ int lowrank_step(const double* V, int ldv, bool vglobal, int N, int NP, double side, double* P0, double* P1, double* P2,
                                    int p, LrSmall<PM>& S, double vscale, long long* lp, double** Zout) {
   constexpr int LD = LrSmall<PM>::LD, LD2 = LrSmall<PM>::LD2;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -288,7 +325,7 @@ __device__ __noinline__ int lowrank_step(const double* V, int ldv, int N, int NP
     tk = now_;                               \
   }
   // W = side V Z -> P1 ; H = Z'W
-  panel_vmul(V, ldv, N, NP, P0, P1, pc, side);
+  panel_vmul(V, ldv, vglobal, N, NP, P0, P1, pc, side);
   __syncthreads();
   OMC_LRT(0)
   panel_gram(P0, P1, N, pc, S.H, LD, 1.0);
@@ -328,7 +365,7 @@ __device__ __noinline__ int lowrank_step(const double* V, int ldv, int N, int NP
   }
   OMC_LRT(2)
   // WR = side V R~ -> Wq ; X = Z'WR ; C = R~'WR
-  panel_vmul(V, ldv, N, NP, Rq, Wq, pc, side);
+  panel_vmul(V, ldv, vglobal, N, NP, Rq, Wq, pc, side);
   __syncthreads();
   OMC_LRT(3)
   panel_gram(P0, Wq, N, pc, S.X, LD, 1.0);

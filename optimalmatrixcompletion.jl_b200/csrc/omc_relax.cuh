@@ -18,7 +18,7 @@ namespace omc {
 struct StateLayout {
   int n, m, k, Lcap;
   int N1, N2, N3;
-  size_t X, Y, T, U, s1, m1, s2, m2, s3, m3, s5, m5, sv, mv, sg, mg, scal, total;
+  size_t X, Y, T, U, s1, m1, s2, m2, s3, m3, s5, m5, sv, mv, sg, mg, scal, z1, z2, z3, total;
 };
 __host__ __device__ inline StateLayout make_state_layout(int n, int m, int k, int Lcap) {
   StateLayout L;
@@ -41,7 +41,13 @@ __host__ __device__ inline StateLayout make_state_layout(int n, int m, int k, in
   L.mv = o; o += (size_t)Lcap * k;
   L.sg = o; o += (size_t)Lcap;
   L.mg = o; o += (size_t)Lcap;
-  L.scal = o; o += 8;  // s4, m4, rho, ncuts, iters, ...
+  L.scal = o; o += 8;  // s4, m4, rho, ncuts, iters, tracker flags (lr_mode_bits, lr_neg_bits, lr_p_pack)
+  // tracked minority-side bases of the three PSD blocks (NP x 16 row-major, 16-byte aligned): part of the record so that a
+  // child warm-started from its parent's record starts on the tracker instead of three cold eigendecompositions
+  o = (o + 1) & ~(size_t)1;
+  L.z1 = o; o += (size_t)((L.N1 + 7) & ~7) * 16;
+  L.z2 = o; o += (size_t)((L.N2 + 7) & ~7) * 16;
+  L.z3 = o; o += (size_t)((L.N3 + 7) & ~7) * 16;
   L.total = (o + 1) & ~(size_t)1;
   return L;
 }
@@ -75,9 +81,7 @@ __host__ __device__ inline ScratchLayout make_scratch_layout(const StateLayout& 
   C.Q1 = o; o += (size_t)g1.NP * g1.ld;
   C.Q2 = o; o += (size_t)g2.NP * g2.ld;
   C.Q3 = o; o += (size_t)g3.NP * g3.ld;
-  C.Z1 = o; o += (size_t)g1.NP * 16;   // tracked minority-side bases (low-rank projection), NP x 16 row-major
-  C.Z2 = o; o += (size_t)g2.NP * 16;
-  C.Z3 = o; o += (size_t)g3.NP * 16;
+  C.Z1 = C.Z2 = C.Z3 = 0;              // (the tracked bases live in the state record, StateLayout::z1..z3)
   o = (o + 1) & ~(size_t)1;
   C.G = o; o += ((size_t)rmax * rmax + 1) & ~(size_t)1;      // 16-byte aligned: re-read by TMA bulk copies
   C.Minv = o; o += ((size_t)rmax * rmax + 1) & ~(size_t)1;
@@ -118,6 +122,7 @@ struct RelaxArgs {
   double* prof;  // [B][16]: [8..14] = primal residual components at the last check; cycles in phase1+2, build V, gemm, jacobi, reconstruct, residual; sweeps; iterations
   omc_relax_opts o;
   int Lcap, rmax;
+  int xs_cap;   // doubles of shared memory for the node's cut vectors (L * n <= xs_cap are cached; 0 = read them from the pool)
   StateLayout SL;
   ScratchLayout SC;
 };
@@ -242,9 +247,9 @@ __device__ inline void build_minv(const NodeCtx& c, double* smem_work, size_t sm
 // doubles of the second shared-memory region: the eigenvector matrix of the full solver, or the three panels and the
 // small matrices of the low-rank projection
 template <int PM>
-__host__ __device__ inline size_t region1_doubles(const Geo& gfit) {
+__host__ __device__ inline size_t region1_doubles(const Geo& gfit, int NPmax) {
   const size_t full = (size_t)gfit.NP * gfit.ld;
-  const size_t lr = 3 * (size_t)gfit.NP * OMC_LR_LDZ + (sizeof(LrSmall<PM>) + 7) / 8 + 2;
+  const size_t lr = 3 * (size_t)NPmax * OMC_LR_LDZ + (sizeof(LrSmall<PM>) + 7) / 8 + 2;
   return ((full > lr ? full : lr) + 1) & ~(size_t)1;
 }
 
@@ -287,7 +292,7 @@ struct KFrame {
 #define OMC_SETBIT(w_, b_, v_) w_ = ((w_) & ~(1u << (b_))) | ((unsigned)((v_) ? 1u : 0u) << (b_))
 #define OMC_SEL3(b_, x0, x1, x2) ((b_) == 0 ? (x0) : ((b_) == 1 ? (x1) : (x2)))
 #define OMC_QG(b_) (scr + OMC_SEL3(b_, P.SC.Q1, P.SC.Q2, P.SC.Q3))
-#define OMC_ZG(b_) (scr + OMC_SEL3(b_, P.SC.Z1, P.SC.Z2, P.SC.Z3))
+#define OMC_ZG(b_) (st + OMC_SEL3(b_, SL.z1, SL.z2, SL.z3))
 #define OMC_SB(b_) (st + OMC_SEL3(b_, SL.s1, SL.s2, SL.s3))
 #define OMC_MB(b_) (st + OMC_SEL3(b_, SL.m1, SL.m2, SL.m3))
 #define OMC_GB(b_) make_geo(OMC_SEL3(b_, SL.N1, SL.N2, SL.N3))
@@ -309,7 +314,7 @@ struct KFrame {
   const Geo g1 = make_geo(SL.N1);                                                                    \
   const Geo gfit = smem_geo(SL.N1, SL.N2, SL.N3);                                                    \
   const size_t bufsz = (size_t)gfit.NP * gfit.ld;                                                    \
-  const size_t bufsz1 = region1_doubles<PM>(gfit);                                                   \
+  const size_t bufsz1 = region1_doubles<PM>(gfit, g1.NP);                                            \
   double* const buf0 = F.buf0; double* const buf1 = F.buf1;                                          \
   double* const lam = F.lam; double* const wgt = F.wgt; double* const jcs = F.jcs; double* const jsn = F.jsn; \
   double* const red = F.red; double* const rhs = F.rhs; double* const cw = F.cw; double* const gc = F.gc;    \
@@ -336,7 +341,7 @@ __device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
     // ---- cut rows (scaled): lb, ub, alpha per column, beta summed over columns
     for (int l = tid; l < L; l += NT) {
       const int cid = P.node_cut_ids[e0 + l];
-      cxp[l] = ((size_t)L * n <= OMC_XS_CAP) ? (const double*)(xs + (size_t)l * n) : (P.pool_x + (size_t)cid * n);
+      cxp[l] = ((size_t)L * n <= (size_t)P.xs_cap) ? (const double*)(xs + (size_t)l * n) : (P.pool_x + (size_t)cid * n);
       double bsum = 0.0;
       for (int j = 0; j < k; ++j) {
         double lb, ub, al, be;
@@ -349,7 +354,7 @@ __device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
     }
     __syncthreads();
 
-    if ((size_t)L * n <= OMC_XS_CAP) {
+    if ((size_t)L * n <= (size_t)P.xs_cap) {
       for (int e = tid; e < L * n; e += NT) {
         const int l = e / n, i = e - l * n;
         xs[e] = P.pool_x[(size_t)P.node_cut_ids[e0 + l] * n + i];
@@ -447,6 +452,9 @@ __device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
   if (tid < 24) sprof[tid] = 0;   // [0..5] phases, [8..15] sub-phases of the low-rank step, [16..23] of the w-update
   if (tid == 0) {
     F.have_basis_bits = 0u; F.lr_mode_bits = 0u; F.lr_neg_bits = 0u; F.lr_p_pack = 0u;
+    if (warm >= 0 && !P.o.exact_projection) {   // the parent's tracked bases came with its record
+      F.lr_mode_bits = (unsigned)c.scal[5]; F.lr_neg_bits = (unsigned)c.scal[6]; F.lr_p_pack = (unsigned)c.scal[7];
+    }
     F.exact_iter = 0; F.force_check = 0;
     // Eigensolver tolerance follows the ADMM residual: off(S) <= jtol ||S||_F with jtol two orders below the
     // current relative residual, inside [1e-13, jacobi_tol].
@@ -460,41 +468,15 @@ __device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
   __syncthreads();
 }
 
+// phase 1a: X and Theta rows of the w-update (own function: its register-staged loads must not compete with the rest)
 template <int NT, int KMAX, int PM>
-__device__ __noinline__ void relax_phase12(const RelaxArgs& P, KFrame& F) {
-  OMC_FRAME_LOCALS
-  uint32_t mbar_phase = F.mbar_phase;
-  long long tk = clock64();
-  {
-      const double rho = c.rho, sig = c.sigma, al = c.alpha;
-      const double dYU = sig + 3.0 * rho, dT = sig + rho;
-      const double t4 = c.scal[1] + rho * (c.ktr - c.scal[0]);
-      // shared-memory views that live through phases 1-2 only: Y~ (full symmetric, n x ldy) and U~ in region 0, the
-      // Woodbury inverse and the Gram matrix of the dense rows in region 1 (TMA bulk copies, overlapped with phase 1)
-      const int ldy = n | 1;
-      double* Ys = buf0;
-      double* Us = buf0 + (size_t)n * ldy;
-      const size_t r2p = ((size_t)r * r + 1) & ~(size_t)1;
-      const bool ms_smem = 2 * r2p <= bufsz1;
-      const double* Ms = ms_smem ? buf1 : c.Minv;
-      const double* Gs = ms_smem ? buf1 + r2p : c.G;
-#if OMC_USE_TMA
-      if (ms_smem && tid == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(mbar, (uint32_t)(2 * r2p * sizeof(double)));
-        bulk_g2s(buf1, c.Minv, (uint32_t)(r2p * sizeof(double)), mbar);
-        bulk_g2s(buf1 + r2p, c.G, (uint32_t)(r2p * sizeof(double)), mbar);
-      }
-#else
-      if (ms_smem)
-        for (int e = tid; e < (int)r2p; e += NT) { buf1[e] = c.Minv[e]; buf1[r2p + e] = c.G[e]; }
-#endif
-      for (int l = tid; l < L; l += NT) tgs[l] = c.mg[l] + rho * (cbe[l] - c.sg[l]);
-      __syncthreads();
-      // ------------------------------------------------ phase 1: w~ = D^-1 (sigma w - q + A'(rho (b - s) + mu))
-      // (loads of a batch are issued before any of its stores: the state record lives in L2)
-      long long tw = clock64();
-#define OMC_WT(slot) { const long long now_ = clock64(); if (tid == 0) sprof[16 + slot] += now_ - tw; tw = now_; }
+__device__ __noinline__ void relax_p1_xt(const RelaxArgs& P, KFrame& F) {
+  const int tid = threadIdx.x;
+  const int n = P.n, m = P.m;
+  const StateLayout& SL = P.SL;
+  const NodeCtx& c = F.c;
+  const double rho = c.rho, sig = c.sigma, al = c.alpha;
+  const double dT = sig + rho;
       {
         constexpr int UB = 2;
         const int nm = n * m;
@@ -549,7 +531,29 @@ __device__ __noinline__ void relax_phase12(const RelaxArgs& P, KFrame& F) {
             }
           }
         }
-        OMC_WT(0)
+      }
+}
+
+// phase 1b: Y and U rows of the w-update into shared memory (before the dense-row correction)
+template <int NT, int KMAX, int PM>
+__device__ __noinline__ void relax_p1_yu(const RelaxArgs& P, KFrame& F) {
+  const int tid = threadIdx.x;
+  const int n = P.n, k = P.k;
+  const StateLayout& SL = P.SL;
+  const NodeCtx& c = F.c;
+  const int L = F.c.L;
+  double* const buf0 = F.buf0;
+  const double* const tgs = F.tgs;
+  const double* const cal = F.cal;
+  const double* const* const cxp = F.cxp;
+  const double rho = c.rho, sig = c.sigma;
+  const double dYU = sig + 3.0 * rho;
+  const double t4 = c.scal[1] + rho * (c.ktr - c.scal[0]);
+  const int ldy = n | 1;
+  double* Ys = buf0;
+  double* Us = buf0 + (size_t)n * ldy;
+      {
+        constexpr int UB = 2;
         const int nly = n * (n + 1) / 2;
         for (int e0 = tid; e0 < nly; e0 += NT * UB) {  // Y lower -> Ys (both triangles), before the dense-row correction
           double v1m[UB], v1s[UB], v2m[UB], v2s[UB], v3m[UB], v3s[UB], vy[UB];
@@ -599,6 +603,45 @@ __device__ __noinline__ void relax_phase12(const RelaxArgs& P, KFrame& F) {
           Us[e] = (sig * c.U[e] + gU) / dYU;
         }
       }
+}
+
+template <int NT, int KMAX, int PM>
+__device__ __noinline__ void relax_phase12(const RelaxArgs& P, KFrame& F) {
+  OMC_FRAME_LOCALS
+  uint32_t mbar_phase = F.mbar_phase;
+  long long tk = clock64();
+  {
+      const double rho = c.rho, sig = c.sigma, al = c.alpha;
+      (void)sig;
+      // shared-memory views that live through phases 1-2 only: Y~ (full symmetric, n x ldy) and U~ in region 0, the
+      // Woodbury inverse and the Gram matrix of the dense rows in region 1 (TMA bulk copies, overlapped with phase 1)
+      const int ldy = n | 1;
+      double* Ys = buf0;
+      double* Us = buf0 + (size_t)n * ldy;
+      const size_t r2p = ((size_t)r * r + 1) & ~(size_t)1;
+      const bool ms_smem = 2 * r2p <= bufsz1;
+      const double* Ms = ms_smem ? buf1 : c.Minv;
+      const double* Gs = ms_smem ? buf1 + r2p : c.G;
+#if OMC_USE_TMA
+      if (ms_smem && tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(mbar, (uint32_t)(2 * r2p * sizeof(double)));
+        bulk_g2s(buf1, c.Minv, (uint32_t)(r2p * sizeof(double)), mbar);
+        bulk_g2s(buf1 + r2p, c.G, (uint32_t)(r2p * sizeof(double)), mbar);
+      }
+#else
+      if (ms_smem)
+        for (int e = tid; e < (int)r2p; e += NT) { buf1[e] = c.Minv[e]; buf1[r2p + e] = c.G[e]; }
+#endif
+      for (int l = tid; l < L; l += NT) tgs[l] = c.mg[l] + rho * (cbe[l] - c.sg[l]);
+      __syncthreads();
+      // ------------------------------------------------ phase 1: w~ = D^-1 (sigma w - q + A'(rho (b - s) + mu))
+      // (loads of a batch are issued before any of its stores: the state record lives in L2)
+      long long tw = clock64();
+#define OMC_WT(slot) { const long long now_ = clock64(); if (tid == 0) sprof[16 + slot] += now_ - tw; tw = now_; }
+      relax_p1_xt<NT, KMAX, PM>(P, F);
+      OMC_WT(0)
+      relax_p1_yu<NT, KMAX, PM>(P, F);
       __syncthreads();
       OMC_WT(1)
       // ------------------------------------------------ phase 2: Woodbury correction for the dense rows
@@ -704,7 +747,7 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
         const int N = g.N, NP = g.NP, ld = g.ld;
         const uint32_t qbytes = (uint32_t)((size_t)NP * ld * sizeof(double));
         const bool fits = (size_t)NP * ld <= bufsz;             // else: L2-resident working buffers
-        const bool use_lr = fits && OMC_BIT(lr_mode_bits, b) && !exact_iter && !P.o.exact_projection;
+        const bool use_lr = OMC_BIT(lr_mode_bits, b) && !exact_iter && !P.o.exact_projection;
         const bool warmQ = OMC_BIT(have_basis_bits, b) && !reortho && !exact_iter && !use_lr;
         double* B0 = fits ? buf0 : (scr + P.SC.big0);
         double* B1 = fits ? buf1 : OMC_QG(b);
@@ -788,7 +831,7 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
             }
             __syncthreads();
           }
-          const int need_full = idle ? 0 : lowrank_step<PM>(B0, ld, N, NP, OMC_BIT(lr_neg_bits, b) ? -1.0 : 1.0, lrZ, lrR, lrW, (int)((lr_p_pack >> (8 * b)) & 0xffu), lrS, vscale, P.prof ? sprof + 8 : nullptr, &lrOut);
+          const int need_full = idle ? 0 : lowrank_step<PM>(B0, ld, !fits, N, NP, OMC_BIT(lr_neg_bits, b) ? -1.0 : 1.0, lrZ, lrR, lrW, (int)((lr_p_pack >> (8 * b)) & 0xffu), lrS, vscale, P.prof ? sprof + 8 : nullptr, &lrOut);
           if (!idle) ++n_lr;
           OMC_TICK(2)
           if (idle) {
@@ -904,7 +947,7 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
 #endif
           // switch to the low-rank projection when the minority side (plus guard band) fits the panel: the tracked
           // basis = the minority-side eigenvectors and the OMC_LR_BUF eigenvectors next to them across zero
-          if (fits && !P.o.exact_projection && ish[5] + OMC_LR_BUF <= PM && ish[5] + OMC_LR_BUF <= N) {
+          if (!P.o.exact_projection && ish[5] + OMC_LR_BUF <= PM && ish[5] + OMC_LR_BUF <= N) {
             const int side = ish[2], pz = ish[5] + OMC_LR_BUF;
             if (tid < 16) jrot[tid] = -1;
             __syncthreads();
@@ -1217,6 +1260,7 @@ __device__ __noinline__ void relax_node_output(const RelaxArgs& P, KFrame& F) {
       c.scal[2] = c.rho;
       c.scal[3] = (double)L;
       c.scal[4] = (double)it;
+      c.scal[5] = (double)F.lr_mode_bits; c.scal[6] = (double)F.lr_neg_bits; c.scal[7] = (double)F.lr_p_pack;
     }
     if (P.outX)
       for (int e = tid; e < n * m; e += NT) P.outX[(size_t)node * n * m + e] = c.X[e];
@@ -1256,7 +1300,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const __grid_consta
   // ---- shared memory carve-up
   double* buf0 = reinterpret_cast<double*>(smem_raw);
   double* buf1 = buf0 + bufsz;
-  const size_t bufsz1 = region1_doubles<PM>(gfit);
+  const size_t bufsz1 = region1_doubles<PM>(gfit, g1.NP);
   double* lam = buf1 + bufsz1;             // [NP1]
   double* wgt = lam + g1.NP;               // [NP1]
   double* jcs = wgt + g1.NP;               // [NP1/2]
@@ -1270,8 +1314,8 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const __grid_consta
   double* cal = cub + P.Lcap * k;
   double* cbe = cal + P.Lcap * k;          // [Lcap]
   double* tgs = cbe + P.Lcap;              // [Lcap]  rho (beta - sg) + mg of the aggregated rows, refreshed every iteration
-  double* xs = tgs + P.Lcap;               // [OMC_XS_CAP] shared-memory copies of the node's cut vectors (when they fit)
-  const double** cxp = reinterpret_cast<const double**>(xs + OMC_XS_CAP);  // [Lcap]
+  double* xs = tgs + P.Lcap;               // [xs_cap] shared-memory copies of the node's cut vectors (when they fit)
+  const double** cxp = reinterpret_cast<const double**>(xs + P.xs_cap);  // [Lcap]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(cxp + P.Lcap);           // [1]
   long long* sprof = reinterpret_cast<long long*>(mbar + 1);            // [24] cycle counters (thread 0 accumulates)
   KFrame& F = *reinterpret_cast<KFrame*>(sprof + 24);                   // the shared frame
@@ -1289,9 +1333,9 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const __grid_consta
     F.jrot = jrot; F.idx = idx; F.jskip = jskip; F.ish = ish; F.scr = scr; F.st = st;
     // low-rank projection workspace inside region 1 (panels first, then the small matrices)
     F.lrZ = buf1;
-    F.lrR = F.lrZ + (size_t)gfit.NP * OMC_LR_LDZ;
-    F.lrW = F.lrR + (size_t)gfit.NP * OMC_LR_LDZ;
-    F.lrS = F.lrW + (size_t)gfit.NP * OMC_LR_LDZ;
+    F.lrR = F.lrZ + (size_t)g1.NP * OMC_LR_LDZ;
+    F.lrW = F.lrR + (size_t)g1.NP * OMC_LR_LDZ;
+    F.lrS = F.lrW + (size_t)g1.NP * OMC_LR_LDZ;
     NodeCtx& c = F.c;
     c.n = n; c.m = m; c.k = k; c.N1 = SL.N1; c.N2 = SL.N2; c.N3 = SL.N3; c.L = 0; c.r = 1;
     c.a = P.a; c.sa = P.sa; c.cT = P.cT; c.ktr = P.a * k; c.alpha = P.o.alpha; c.sigma = P.o.sigma; c.rho = P.o.rho0;
@@ -1346,18 +1390,18 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const __grid_consta
 
 // shared memory bytes the kernel carves up (must mirror the carve-up above)
 template <int PM>
-inline size_t relax_smem_bytes(int n, int m, int k, int Lcap, int rmax) {
+inline size_t relax_smem_bytes(int n, int m, int k, int Lcap, int rmax, int xs_cap) {
   Geo g1 = make_geo(n + m);
   Geo gf = smem_geo(n + m, n + k, n);
   size_t d = 0;
-  d += (size_t)gf.NP * gf.ld + region1_doubles<PM>(gf);   // buf0, region 1
+  d += (size_t)gf.NP * gf.ld + region1_doubles<PM>(gf, g1.NP);   // buf0, region 1
   d += 2 * (size_t)g1.NP;                // lam, wgt
   d += 2 * (size_t)(g1.NP / 2);          // jcs, jsn
   d += 32;                               // red
   d += 3 * (size_t)rmax;                 // rhs, cw, gc
   d += 3 * (size_t)Lcap * k + Lcap;      // clb, cub, cal, cbe
   d += (size_t)Lcap;                     // cxp (pointers, 8 bytes)
-  d += (size_t)Lcap + OMC_XS_CAP;        // tgs, xs
+  d += (size_t)Lcap + (size_t)xs_cap;    // tgs, xs
   d += 1 + 24;                           // mbar, sprof
   d += (sizeof(KFrame) + 7) / 8;         // the shared frame
   size_t bytes = d * 8;
