@@ -182,6 +182,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line (NCCL prints its version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import omc_b200
     omc = omc_b200
