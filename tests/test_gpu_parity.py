@@ -251,3 +251,66 @@ def test_tracked_projection_matches_exact_projection_on_frontier_nodes(omc):
         assert np.linalg.eigvalsh(np.eye(50) - Y).min() >= -1e-6 and np.linalg.eigvalsh(Y - U @ U.T).min() >= -1e-6
     assert prof[:, 13].sum() + prof[:, 14].sum() >= 0.98 * (prof[:, 13].sum() + prof[:, 14].sum() + prof[:, 15].sum())   # tracker (incl. idle) did >= 98 % of the projections
     p.close()
+
+
+def test_alternating_minimization_matches_oracle(omc):
+    """K7+K8 against oracle/altmin.py (OMC.jl:1979-2279) on the config 1-3 shapes, from +U0 and -U0 (the reference does
+    not normalise the SVD sign, OMC.jl:522-524) and with a cut: same sweep count, same convergence flag, same iterates."""
+    from oracle import altmin as AM
+    from oracle.datagen import config_instance, CONFIGS
+    from oracle.cuts import LABELS
+    for cfg in ("C1", "C2", "C3"):
+        k, A, mask, g = config_instance(cfg, 0)
+        n = A.shape[0]
+        ct = CONFIGS[cfg]["cut_type"]
+        p = omc.Problem(k, A, mask, g, ct)
+        U0 = np.linalg.svd(np.where(mask, A, 0.0))[0][:, :k]
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal(n); x /= np.linalg.norm(x); Uh = 0.3 * rng.standard_normal((n, k))
+        dirs = [LABELS[ct][-1]] * k
+        cid = p.add_cut(x, Uh)
+        for Ui, gc, oc in ((U0, None, ()), (-U0, None, ()), (U0, [omc.Cut(cid, x, Uh, dirs)], [(x, Uh, dirs)])):
+            r = omc.alternating_minimization(p, Ui, gc)
+            ro = AM.alternating_minimization(A, n, k, mask, g, True, ct, Ui, oc)
+            assert r["converged"] == ro["converged"] and r["n_iters"] == ro["n_iters"], (cfg, r["n_iters"], ro["n_iters"])
+            assert np.abs(r["U"] - ro["U"]).max() <= 1e-8 and np.abs(r["V"] - ro["V"]).max() <= 1e-7
+            assert np.allclose(r["objectives"], ro["objectives"], rtol=1e-8, atol=0)     # inner U-step ADMM tolerance 1e-9
+            assert abs(p.objective_mse(r["U"] @ r["V"])[0] - r["objectives"][-1]) <= 1e-9 * abs(r["objectives"][-1])   # a6 agrees
+        p.close()
+
+
+def test_branch_and_bound_certifies_config2_and_brackets_config1(omc):
+    """The host loop (mirror of OMC.jl:700-1073).  Config 2 certifies gap <= 1e-4 in a few nodes: the incumbent's objective
+    is evaluate_objective of the returned rank-k X (OMC.jl:2330-2359) and is bracketed by the oracle's root relaxation.
+    Config 1 (50 of 100 entries observed) needs thousands of nodes, so it is run for a bounded number of steps under two
+    node selections and two frontier batch sizes: every run's lower bound must stay below every run's incumbent, bounds
+    must be monotone, and batching must not change the first pops (frontier_batch = 1 is the reference's sequence)."""
+    from oracle import relaxation as R
+    from oracle.datagen import config_instance
+    k, A, mask, g = config_instance("C2", 0)
+    root = R.solve_relaxation(A, mask, g, k, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8))
+    sol, printlist, inst = omc.matrix_completion_branchandbound(k, A, mask, g, node_selection="bestfirst", disjunctive_cuts_type="linear",
+                                                                disjunctive_cuts_breakpoints="smallest_1_eigvec", time_limit=120, verbosity=0)
+    assert inst["tree"].now_gap <= 1e-4 + 1e-12
+    assert root["objective"] * (1 - 1e-6) <= sol["objective"]
+    p = omc.Problem(k, A, mask, g, "linear")
+    assert abs(p.objective_mse(sol["X"])[0] - sol["objective"]) <= 1e-9 * abs(sol["objective"])
+    assert np.linalg.matrix_rank(sol["X"], tol=1e-8) <= k
+    p.close()
+    k, A, mask, g = config_instance("C1", 0)
+    root = R.solve_relaxation(A, mask, g, k, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8))
+    runs = []
+    for kw in (dict(node_selection="bestfirst", frontier_batch=16), dict(node_selection="breadthfirst", frontier_batch=16),
+               dict(node_selection="bestfirst", frontier_batch=1, max_steps=12)):
+        kw.setdefault("max_steps", 160)
+        sol, printlist, inst = omc.matrix_completion_branchandbound(k, A, mask, g, disjunctive_cuts_type="linear",
+                                                                    disjunctive_cuts_breakpoints="smallest_1_eigvec",
+                                                                    use_max_steps=True, time_limit=120, verbosity=0, **kw)
+        tree = inst["tree"]
+        lbs = [row[3] for row in inst["run_log"]]                                          # (explored, counter, remaining, LB, ...)
+        assert all(b2 >= b1 - 1e-9 for b1, b2 in zip(lbs, lbs[1:]))                         # OMC.jl:1213-1216: LB never decreases
+        runs.append((tree.best_lower_bound, sol["objective"], tree.now_gap))
+        assert sol["objective"] >= root["objective"] * (1 - 1e-6)
+    los = [r[0] for r in runs if r[0] is not None and np.isfinite(r[0])]
+    ups = [r[1] for r in runs]
+    assert not los or max(los) <= min(ups) * (1 + 1e-6), runs                               # any lower bound <= any incumbent

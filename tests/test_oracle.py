@@ -245,3 +245,31 @@ def test_admm_with_tracked_projection_reaches_the_same_bound():
     assert lr > 20 * full
     cert = R.certificate(b, A, mask, g, k)
     assert cert["dual_cone"] <= 1e-9 and cert["primal_psd1"] >= -1e-7 and abs(cert["gap"]) <= 1e-6
+
+
+def test_altmin_oracle_vstep_exact_ustep_matches_slsqp_and_stopping_rule():
+    """oracle/altmin.py restates OMC.jl:1979-2279: the V-step is the exact minimiser in V (OMC.jl:2192-2209), the
+    constrained U-step agrees with an independent SLSQP solve (OMC.jl:2212-2229 incl. the box, ball and pair-norm
+    constraints), objectives[i] is the value after the i-th U-step and the stopping rule is OMC.jl:2232-2245."""
+    from oracle import altmin as AM
+    for cfg, eps_v in (("C1", 1e-9), ("C3", 1e-9)):
+        k, A, mask, g = config_instance(cfg, 0)
+        n, m = A.shape
+        U0 = np.linalg.svd(np.where(mask, A, 0.0))[0][:, :k]
+        V = AM.v_step(U0, A, mask, g)
+        f0 = AM.objective(U0, V, A, mask, g)
+        rng = np.random.default_rng(3)
+        for _ in range(5):                                    # exact minimiser of a strictly convex quadratic in V
+            assert AM.objective(U0, V + 1e-4 * rng.standard_normal(V.shape), A, mask, g) > f0
+        U1, f1, it, _ = AM.u_step(U0, V, A, mask, g)
+        Us, fs = AM.ustep_slsqp(U0, V, A, mask, g)
+        assert abs(f1 - fs) <= 1e-6 * abs(fs) and f1 <= f0 + 1e-12
+        assert U1.max() <= 1 + 1e-8 and np.sqrt((U1 * U1).sum(axis=0)).max() <= 1 + 1e-7              # OMC.jl:2024, 2164-2171
+        for j in range(k):
+            assert U1[n - k + j:, j].min() >= -1e-8                                                        # OMC.jl:1989-1996
+        r = AM.alternating_minimization(A, n, k, mask, g, True, "linear", U0)
+        assert r["n_iters"] == len(r["objectives"]) <= r["max_iters"]
+        ob = r["objectives"]
+        if r["converged"] and len(ob) >= 2:
+            rel = abs((ob[-1] - ob[-2]) / ob[-2])
+            assert rel < 1e-5 or (len(ob) > 5 and all(ob[-1 - i] > ob[-6] for i in range(5)))
