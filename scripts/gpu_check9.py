@@ -13,7 +13,7 @@ def run(nodes_, label, **kw):
     f = omc_b200.Frontier(p, nodes_); ms = f.relax(omc_b200.default_opts(**kw)); out = f.fetch(False); prof = f.profile(); f.close()
     pm = prof.sum(axis=0); tot = pm[:6].sum()
     print(f"{label}: {ms:.1f} ms nodes {len(nodes_)} iters {pm[7]:.0f} cyc/iter {tot/pm[7]:.0f}", " ".join(f"{nm}={pm[q]/pm[7]/1e3:.1f}k" for q, nm in enumerate(names)),
-          f"| lr proj {pm[14]:.0f} idle {pm[13]:.0f} full proj {pm[15]:.0f} sweeps {pm[6]:.0f}", flush=True)
+          f"| lr proj {pm[14]:.0f} (pair steps {pm[12]:.0f}) idle {pm[13]:.0f} full proj {pm[15]:.0f} sweeps {pm[6]:.0f}", flush=True)
     if pm[14] > 0:
         print("    lr step cycles/proj:", " ".join(f"{nm}={pm[16+q]/pm[14]/1e3:.2f}k" for q, nm in enumerate(lrn)), f"total={pm[16:24].sum()/pm[14]/1e3:.1f}k", flush=True)
         wn = ["X,T loops", "Y,U loops", "dense rows", "woodbury", "corrections"]
