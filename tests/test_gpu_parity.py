@@ -314,3 +314,38 @@ def test_branch_and_bound_certifies_config2_and_brackets_config1(omc):
     los = [r[0] for r in runs if r[0] is not None and np.isfinite(r[0])]
     ups = [r[1] for r in runs]
     assert not los or max(los) <= min(ups) * (1 + 1e-6), runs                               # any lower bound <= any incumbent
+
+
+def test_config3_shape_rank2_linear2_tracked_vs_oracle(omc):
+    """BASELINE config 3 shape without the Shor rows (k = 2, 30 x 30, linear2 cuts: 9 children per split): root and three
+    children, default (tracked) path vs the oracle's exact-projection ADMM to the north-star tolerance, and vs the GPU's own
+    exact path; child bounds dominate the parent's."""
+    from oracle import relaxation as R
+    from oracle.datagen import config_instance
+    from omc_b200.host import BBNode, create_matrix_cut_child_nodes
+    k, A, mask, g = config_instance("C3", 0)
+    p = omc.Problem(k, A, mask, g, "linear2")
+    root = p.relax_batch([[]])[0]
+    ro = R.solve_relaxation(A, mask, g, k, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8))
+    assert root["status_code"] == 0 and abs(root["objective"] - ro["objective"]) <= REL_BOUND * abs(ro["objective"])
+    lam, vec, bp, feas = omc.smallest_eigvecs_batch(root["Y"][None], root["U"][None], 1)
+    assert not feas[0]
+    kids = create_matrix_cut_child_nodes(p, BBNode(node_id=1, parent_id=0, LB=root["objective"], depth=0), bp[0], root["U"], 1, root["objective"])
+    assert len(kids) == 9                                                     # P^k children, OMC.jl:2481-2491
+    pick = [kids[i] for i in (0, 2, 4, 8)]
+    nconv = 0
+    rt = p.relax_batch([kd.disjunctive_cuts for kd in pick], omc.default_opts(max_iter=8000))
+    re_ = p.relax_batch([kd.disjunctive_cuts for kd in pick], omc.default_opts(max_iter=8000, exact_projection=1))
+    for kd, a, b in zip(pick, rt, re_):
+        cuts_o = [(c.x, c.Uhat, c.directions) for c in kd.disjunctive_cuts]
+        o = R.solve_relaxation(A, mask, g, k, "linear2", cuts_o, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=8000))
+        # at the root U = 0, so vhat = 0 and the "middle" region of linear2 is the single point v = 0 (SURVEY appendix G.4):
+        # that child is degenerate for any first-order method and may stop at max_iter on all three paths alike
+        assert a["status_code"] == b["status_code"] == o["status"], (kd.disjunctive_cuts[0].directions, a["status_code"], b["status_code"], o["status"])
+        if a["status_code"] == 0:            # iterates cut off by max_iter are not comparable between implementations
+            assert abs(a["objective"] - o["objective"]) <= REL_BOUND * abs(o["objective"]), (a["objective"], o["objective"])
+            assert abs(a["objective"] - b["objective"]) <= 3e-7 * abs(b["objective"])
+            nconv += 1
+        assert a["objective"] >= root["objective"] * (1 - 1e-6)
+    assert nconv >= 2
+    p.close()
