@@ -138,6 +138,13 @@ int32_t omc_smallest_eigvecs_batch(int32_t n, int32_t k, int32_t B, const double
 int32_t omc_altmin(omc_problem* p, const double* U_initial, int32_t ncuts, const int32_t* cut_ids,
                    const uint8_t* cut_dirs, double eps, int32_t max_iters, double time_limit_s, double* U,
                    double* V, int32_t* converged, int32_t* n_iters, double* objectives, double* solve_time);
+/* The same heuristic for B instances of one problem in ONE launch (one CTA per instance): the reference's extra root
+ * restarts U_initial + max|U_initial| randn (OMC.jl:529-538) and the alt-min calls of a popped batch of nodes
+ * (OMC.jl:867-927).  U_initial / U: [B][n*k] column-major; V: [B][k*m]; objectives: [B][max_iters]; converged, n_iters: [B];
+ * instance b applies the cuts cut_ptr[b] .. cut_ptr[b+1] of (cut_ids, cut_dirs).  solve_time is the whole batch. */
+int32_t omc_altmin_batch(omc_problem* p, int32_t B, const double* U_initial, const int32_t* cut_ptr, const int32_t* cut_ids,
+                         const uint8_t* cut_dirs, double eps, int32_t max_iters, double time_limit_s, double* U, double* V,
+                         int32_t* converged, int32_t* n_iters, double* objectives, double* solve_time);
 
 /* ---- fused objective + MSE: replaces evaluate_objective (OMC.jl:2330-2359) and compute_MSE
  * (OMC.jl:2373-2409).  X column-major n*m.  out[0] objective, out[1] MSE in, out[2] MSE out, out[3] MSE all */

@@ -52,6 +52,7 @@ SIGNATURES = {
                                _pi32, _pf64, _pf64, _pf64, _pf64, _pf64, _pf32]),
     "omc_smallest_eigvecs_batch": (_i32, [_i32, _i32, _i32, _pf64, _pf64, _i32, _pf64, _pf64, _pf64, _pi32]),
     "omc_altmin": (_i32, [_vp, _pf64, _i32, _pi32, _pu8, _f64, _i32, _f64, _pf64, _pf64, _pi32, _pi32, _pf64, _pf64]),
+    "omc_altmin_batch": (_i32, [_vp, _i32, _pf64, _pi32, _pi32, _pu8, _f64, _i32, _f64, _pf64, _pf64, _pi32, _pi32, _pf64, _pf64]),
     "omc_objective_mse": (_i32, [_vp, _pf64, _pf64]),
     "omc_debug_psd_project_batch": (_i32, [_i32, _i32, _pf64, _pf64, _pf64, _pi32, _pf32]),
     "omc_measure_fp64_peak": (_i32, [_pf64]),

@@ -33,6 +33,10 @@ struct AltminArgs {
   double* ws;                // workspace (doubles), layout below
   double* objectives;        // [max_iters]
   int* out_int;              // [0] converged, [1] n_iters, [2] total inner iterations
+  // batch (one CTA per problem instance: same A / mask / gamma, own U_initial and cut list): block b uses
+  // U + b n k, V + b k m, ws + b ws_stride, objectives + b max_iters, out_int + 4 b and cuts cut_ptr[b] .. cut_ptr[b+1]
+  const int* cut_ptr;        // [B+1] or nullptr (single instance: the fields above as they are)
+  size_t ws_stride;
 };
 
 // workspace layout (doubles)
@@ -104,7 +108,20 @@ __device__ __forceinline__ void inv_small(double* M, int k) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 1) altmin_kernel(const AltminArgs P) {
+__global__ void __launch_bounds__(NT, 1) altmin_kernel(const AltminArgs P0) {
+  AltminArgs P = P0;
+  if (P0.cut_ptr != nullptr) {
+    const size_t b = blockIdx.x;
+    const int c0 = P0.cut_ptr[b];
+    P.L = P0.cut_ptr[b + 1] - c0;
+    P.cut_ids = P0.cut_ids + c0;
+    P.cut_dirs = P0.cut_dirs + (size_t)c0 * P0.k;
+    P.U = P0.U + b * (size_t)P0.n * P0.k;
+    P.V = P0.V + b * (size_t)P0.k * P0.m;
+    P.ws = P0.ws + b * P0.ws_stride;
+    P.objectives = P0.objectives + b * (size_t)P0.max_iters;
+    P.out_int = P0.out_int + 4 * b;
+  }
   __shared__ double red[32];
   __shared__ double kk1[ALT_MAXK * ALT_MAXK];  // U'U/gamma or VV'/gamma
   __shared__ double kk2[ALT_MAXK * ALT_MAXK];

@@ -509,7 +509,7 @@ void omc_relax_default_opts(omc_relax_opts* o) {
   o->alpha = 1.6;
   o->cutoff = INFINITY;
   o->time_limit_s = 0.0;
-  o->jacobi_tol = 1e-5;
+  o->jacobi_tol = 1e-3;   /* cap only: the tolerance follows the ADMM residual (1e-2 x relative residual) */
   o->reortho_every = 0;
 }
 
@@ -819,56 +819,78 @@ int32_t omc_smallest_eigvecs_batch(int32_t n, int32_t k, int32_t B, const double
   return OMC_OK;
 }
 
-int32_t omc_altmin(omc_problem* p, const double* U_initial, int32_t ncuts, const int32_t* cut_ids,
-                   const uint8_t* cut_dirs, double eps, int32_t max_iters, double time_limit_s, double* U, double* V,
-                   int32_t* converged, int32_t* n_iters, double* objectives, double* solve_time) {
+int32_t omc_altmin_batch(omc_problem* p, int32_t B, const double* U_initial, const int32_t* cut_ptr, const int32_t* cut_ids,
+                         const uint8_t* cut_dirs, double eps, int32_t max_iters, double time_limit_s, double* U, double* V,
+                         int32_t* converged, int32_t* n_iters, double* objectives, double* solve_time) {
   NEED_INIT();
-  if (!p || !U_initial || !U || !V || !converged || !n_iters || !objectives) return fail(OMC_ERR_ARG, "null argument");
-  if (ncuts < 0 || (ncuts > 0 && (!cut_ids || !cut_dirs))) return fail(OMC_ERR_ARG, "bad cut list");
+  if (!p || !U_initial || !cut_ptr || !U || !V || !converged || !n_iters || !objectives) return fail(OMC_ERR_ARG, "null argument");
+  if (B <= 0) return fail(OMC_ERR_ARG, "B must be positive");
   if (max_iters <= 0) return fail(OMC_ERR_ARG, "max_iters must be positive");
   if (p->k > omc::ALT_MAXK) return fail(OMC_ERR_UNSUPPORTED, "k = %d > %d", p->k, omc::ALT_MAXK);
-  const int n = p->n, m = p->m, k = p->k, L = ncuts;
-  for (int l = 0; l < L; ++l)
-    if (cut_ids[l] < 0 || cut_ids[l] >= p->pool_size) return fail(OMC_ERR_ARG, "cut id out of range");
-  const omc::AltminWs W = omc::make_altmin_ws(n, m, k, L);
+  const int n = p->n, m = p->m, k = p->k;
+  const int E = cut_ptr[B];
+  if (cut_ptr[0] != 0 || E < 0 || (E > 0 && (!cut_ids || !cut_dirs))) return fail(OMC_ERR_ARG, "bad cut list");
+  int Lmax = 0;
+  for (int b = 0; b < B; ++b) {
+    const int L = cut_ptr[b + 1] - cut_ptr[b];
+    if (L < 0) return fail(OMC_ERR_ARG, "cut_ptr not monotone at instance %d", b);
+    if (L > Lmax) Lmax = L;
+  }
+  for (int e = 0; e < E; ++e)
+    if (cut_ids[e] < 0 || cut_ids[e] >= p->pool_size) return fail(OMC_ERR_ARG, "cut id out of range");
+  const omc::AltminWs W = omc::make_altmin_ws(n, m, k, Lmax);
+  const size_t ws_stride = (W.total + 1) & ~(size_t)1;
   DevBuf<double> dU, dV, dws, dobj;
-  DevBuf<int> dids, dout;
+  DevBuf<int> dids, dout, dptr;
   DevBuf<uint8_t> ddirs;
-  CU(dU.alloc((size_t)n * k)); CU(dV.alloc((size_t)k * m)); CU(dws.alloc(W.total)); CU(dobj.alloc(max_iters));
-  CU(dids.alloc(L > 0 ? L : 1)); CU(ddirs.alloc(L > 0 ? (size_t)L * k : 1)); CU(dout.alloc(4));
+  CU(dU.alloc((size_t)B * n * k)); CU(dV.alloc((size_t)B * k * m)); CU(dws.alloc((size_t)B * ws_stride)); CU(dobj.alloc((size_t)B * max_iters));
+  CU(dids.alloc(E > 0 ? E : 1)); CU(ddirs.alloc(E > 0 ? (size_t)E * k : 1)); CU(dout.alloc(4 * (size_t)B)); CU(dptr.alloc(B + 1));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   CU(cudaEventRecord(e0, g_stream));
-  CU(cudaMemcpyAsync(dU.p, U_initial, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-  if (L > 0) {
-    CU(cudaMemcpyAsync(dids.p, cut_ids, L * sizeof(int), cudaMemcpyHostToDevice, g_stream));
-    CU(cudaMemcpyAsync(ddirs.p, cut_dirs, (size_t)L * k, cudaMemcpyHostToDevice, g_stream));
+  CU(cudaMemcpyAsync(dU.p, U_initial, (size_t)B * n * k * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  CU(cudaMemcpyAsync(dptr.p, cut_ptr, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+  if (E > 0) {
+    CU(cudaMemcpyAsync(dids.p, cut_ids, E * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMemcpyAsync(ddirs.p, cut_dirs, (size_t)E * k, cudaMemcpyHostToDevice, g_stream));
   }
-  CU(cudaMemsetAsync(dobj.p, 0, max_iters * sizeof(double), g_stream));
+  CU(cudaMemsetAsync(dobj.p, 0, (size_t)B * max_iters * sizeof(double), g_stream));
   omc::AltminArgs a;
   memset(&a, 0, sizeof a);
-  a.n = n; a.m = m; a.k = k; a.L = L; a.cut_type = p->cut_type; a.fix3 = 0;
+  a.n = n; a.m = m; a.k = k; a.L = 0; a.cut_type = p->cut_type; a.fix3 = 0;
   a.gamma = p->gamma; a.eps = eps; a.inner_eps = 1e-9; a.sigma = 1e-6; a.alpha = 1.6; a.time_limit_s = time_limit_s;
   a.max_iters = max_iters; a.inner_max = 20000;
   a.A = p->A.p; a.rowptr = p->rowptr.p; a.colidx = p->colidx.p; a.colptr = p->colptr.p; a.rowidx = p->rowidx.p;
   a.pool_x = p->pool_x.p; a.pool_vhat = p->pool_vhat.p; a.cut_ids = dids.p; a.cut_dirs = ddirs.p;
   a.U = dU.p; a.V = dV.p; a.ws = dws.p; a.objectives = dobj.p; a.out_int = dout.p;
-  omc::altmin_kernel<1024><<<1, 1024, 0, g_stream>>>(a);
+  a.cut_ptr = dptr.p; a.ws_stride = ws_stride;
+  omc::altmin_kernel<1024><<<B, 1024, 0, g_stream>>>(a);
   CU(cudaGetLastError());
-  int oi[4] = {0, 0, 0, 0};
-  CU(cudaMemcpyAsync(U, dU.p, (size_t)n * k * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
-  CU(cudaMemcpyAsync(V, dV.p, (size_t)k * m * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
-  CU(cudaMemcpyAsync(objectives, dobj.p, max_iters * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
-  CU(cudaMemcpyAsync(oi, dout.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-  CU(cudaEventRecord(e1, g_stream));
-  CU(cudaStreamSynchronize(g_stream));
+  int* oi = (int*)malloc(4 * (size_t)B * sizeof(int));
+  if (!oi) return fail(OMC_ERR_ARG, "out of host memory");
+  cudaError_t ce = cudaMemcpyAsync(U, dU.p, (size_t)B * n * k * sizeof(double), cudaMemcpyDeviceToHost, g_stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(V, dV.p, (size_t)B * k * m * sizeof(double), cudaMemcpyDeviceToHost, g_stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(objectives, dobj.p, (size_t)B * max_iters * sizeof(double), cudaMemcpyDeviceToHost, g_stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(oi, dout.p, 4 * (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, g_stream);
+  if (ce == cudaSuccess) ce = cudaEventRecord(e1, g_stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(g_stream);
   float ms = 0.f;
-  CU(cudaEventElapsedTime(&ms, e0, e1));
+  if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  *converged = oi[0];
-  *n_iters = oi[1];
+  if (ce != cudaSuccess) { free(oi); return fail(OMC_ERR_CUDA, "alt-min batch failed: %s", cudaGetErrorString(ce)); }
+  for (int b = 0; b < B; ++b) { converged[b] = oi[4 * b]; n_iters[b] = oi[4 * b + 1]; }
+  free(oi);
   if (solve_time) *solve_time = ms * 1e-3;
   return OMC_OK;
+}
+
+int32_t omc_altmin(omc_problem* p, const double* U_initial, int32_t ncuts, const int32_t* cut_ids,
+                   const uint8_t* cut_dirs, double eps, int32_t max_iters, double time_limit_s, double* U, double* V,
+                   int32_t* converged, int32_t* n_iters, double* objectives, double* solve_time) {
+  if (ncuts < 0) return fail(OMC_ERR_ARG, "bad cut list");
+  const int32_t ptr[2] = {0, ncuts};
+  return omc_altmin_batch(p, 1, U_initial, ptr, cut_ids, cut_dirs, eps, max_iters, time_limit_s, U, V, converged, n_iters,
+                          objectives, solve_time);
 }
 
 }  // extern "C"

@@ -304,6 +304,38 @@ def alternating_minimization(problem: Problem, U_initial: np.ndarray, disjunctiv
             "n_iters": nit.value, "max_iters": max_iters, "objectives": [float(v) for v in obj[: nit.value]]}
 
 
+def alternating_minimization_batch(problem: Problem, U_initials, disjunctive_cuts_list=None, eps: float = 1e-5,
+                                   max_iters: int = 100, time_limit: float = 3600.0):
+    """B alt-min runs of one problem in one launch (one CTA per instance): the reference's extra root restarts
+    (OMC.jl:529-538) or the alt-min calls of a popped batch of nodes.  Returns a list of the reference's result dicts."""
+    B = len(U_initials)
+    cl = disjunctive_cuts_list if disjunctive_cuts_list is not None else [[] for _ in range(B)]
+    if len(cl) != B:
+        raise ValueError("one cut list per instance")
+    n, m, k = problem.n, problem.m, problem.k
+    Ui = np.zeros((B, k, n))
+    for b, U0 in enumerate(U_initials):
+        if U0.shape != (n, k):
+            raise ValueError("U_initial must have size (n, k)")
+        Ui[b] = np.asarray(U0, dtype=np.float64).T
+    lab = LABELS[problem.cut_type]
+    ptr = np.zeros(B + 1, np.int32)
+    ids, dirs = [], []
+    for b, cuts in enumerate(cl):
+        ids += [c.cut_id for c in cuts]
+        dirs += [lab.index(d) for c in cuts for d in c.directions]
+        ptr[b + 1] = len(ids)
+    ids = np.asarray(ids or [0], np.int32); dirs = np.asarray(dirs or [0], np.uint8)
+    U = np.zeros((B, k, n)); V = np.zeros((B, m, k)); obj = np.zeros((B, max_iters))
+    conv = np.zeros(B, np.int32); nit = np.zeros(B, np.int32); st = C.c_double()
+    check(problem.lib.omc_altmin_batch(problem.handle, B, _ptr(Ui, C.c_double), _ptr(ptr, C.c_int32), _ptr(ids, C.c_int32),
+                                       _ptr(dirs, C.c_uint8), float(eps), int(max_iters), float(time_limit),
+                                       _ptr(U, C.c_double), _ptr(V, C.c_double), _ptr(conv, C.c_int32), _ptr(nit, C.c_int32),
+                                       _ptr(obj, C.c_double), C.byref(st)))
+    return [{"converged": bool(conv[b]), "U": U[b].T.copy(), "V": V[b].T.copy(), "solve_time": st.value, "n_iters": int(nit[b]),
+             "max_iters": max_iters, "objectives": [float(v) for v in obj[b, : nit[b]]]} for b in range(B)]
+
+
 def psd_project_batch(V: np.ndarray):
     """Eigensolver self-test entry: V (B,N,N) symmetric -> (P, lam, sweeps, kernel_ms)."""
     lib = init()

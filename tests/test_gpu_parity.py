@@ -349,3 +349,24 @@ def test_config3_shape_rank2_linear2_tracked_vs_oracle(omc):
         assert a["objective"] >= root["objective"] * (1 - 1e-6)
     assert nconv >= 2
     p.close()
+
+
+def test_alternating_minimization_batch_equals_single_runs(omc):
+    """omc_altmin_batch (one CTA per instance: the reference's extra root restarts OMC.jl:529-538, or a popped batch of
+    nodes) returns exactly what the single-instance entry returns for every instance, with and without cuts."""
+    from oracle.datagen import config_instance
+    k, A, mask, g = config_instance("C3", 0)
+    n = A.shape[0]
+    p = omc.Problem(k, A, mask, g, "linear2")
+    U0 = np.linalg.svd(np.where(mask, A, 0.0))[0][:, :k]
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(n); x /= np.linalg.norm(x); Uh = 0.3 * rng.standard_normal((n, k))
+    cut = omc.Cut(p.add_cut(x, Uh), x, Uh, ["left", "right"])
+    starts = [U0, -U0, U0 + np.abs(U0).max() * rng.standard_normal((n, k)), U0]            # OMC.jl:538 restart
+    cutl = [[], [], [], [cut]]
+    batch = omc.alternating_minimization_batch(p, starts, cutl)
+    for Ui, cl, rb in zip(starts, cutl, batch):
+        rs = omc.alternating_minimization(p, Ui, cl)
+        assert rb["converged"] == rs["converged"] and rb["n_iters"] == rs["n_iters"]
+        assert np.array_equal(rb["U"], rs["U"]) and np.array_equal(rb["V"], rs["V"]) and rb["objectives"] == rs["objectives"]
+    p.close()
