@@ -161,6 +161,31 @@ function alternating_minimization(p::Problem; U_initial::Matrix{Float64}, disjun
                 "max_iters" => max_iters, "objectives" => objectives[1:nit[]])
 end
 
+"""`alternating_minimization` for B instances of one problem in ONE launch (`omc_altmin_batch`, one CTA per instance): the
+extra root restarts `U_initial + maximum(abs.(U_initial)) * randn(n, k)` (OMC.jl:529-538) or the alt-min calls of a popped
+batch of nodes (OMC.jl:867-927).  Returns one reference-style Dict per instance."""
+function alternating_minimization_batch(p::Problem, U_initials::Vector{Matrix{Float64}}, cut_lists::Vector;
+                                        ϵ::Float64 = 1e-5, max_iters::Int = 100, time_limit::Real = 3600)
+    B = length(U_initials)
+    ptr = zeros(Int32, B + 1); ids = Int32[]; dirs = UInt8[]
+    for (b, cuts) in enumerate(cut_lists)
+        for (x, Û, directions) in cuts
+            push!(ids, cut_id!(p, x, Û)); append!(dirs, UInt8[findfirst(isequal(d), LABELS[p.cut_type]) - 1 for d in directions])
+        end
+        ptr[b + 1] = length(ids)
+    end
+    isempty(ids) && (push!(ids, 0); push!(dirs, 0))
+    Uin = cat(U_initials...; dims = 3)                       # n x k x B, column-major per instance
+    U = zeros(p.n, p.k, B); V = zeros(p.k, p.m, B); objectives = zeros(max_iters, B)
+    conv = zeros(Int32, B); nit = zeros(Int32, B); st = Ref{Float64}(0)
+    check(ccall((:omc_altmin_batch, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{UInt8}, Float64, Int32, Float64, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ref{Float64}),
+                p.handle, B, Uin, ptr, ids, dirs, ϵ, max_iters, Float64(time_limit), U, V, conv, nit, objectives, st))
+    return [Dict("converged" => conv[b] == 1, "U" => U[:, :, b], "V" => V[:, :, b], "solve_time" => st[],
+                 "n_iters" => Int(nit[b]), "max_iters" => max_iters, "objectives" => objectives[1:nit[b], b]) for b in 1:B]
+end
+
 """Fused `evaluate_objective` (OMC.jl:2330-2359) + `compute_MSE` (OMC.jl:2373-2409): (objective, in, out, all)."""
 function objective_mse(p::Problem, X::Matrix{Float64})
     out = zeros(4)
