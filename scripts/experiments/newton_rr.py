@@ -1,0 +1,72 @@
+"""Scratch: replace the 2p x 2p Rayleigh-Ritz of the tracking step by one Newton step of the Riccati equation for the graph
+[I; P] of the top subspace of H2 = [H X; X' C], CholQR of Z + R~P and an eigendecomposition of the p x p Ritz matrix only."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np, bench
+from oracle import relaxation as R, lowrank as LR
+A, mask = bench.c2_instance(0)
+cuts = bench.load_frontier_fixture(8)
+MODE = os.environ.get("MODE", "newton"); PMAXN = float(os.environ.get("PMAXN", 0.3)); SW = int(os.environ.get("SW", 99))
+stats = {"newton": 0, "jacobi": 0, "pn": []}
+def step(Vs, Z, pm):
+    N, p = Z.shape
+    W = Vs @ Z; H = Z.T @ W; H = 0.5 * (H + H.T)
+    Rm = W - Z @ H; Rm = Rm - Z @ (Z.T @ Rm)
+    Rt, valid, ill = LR.cholqr_guarded(Rm, 1e-10)
+    if ill:
+        Rt = Rt - Z @ (Z.T @ Rt); Rt, valid, _ = LR.cholqr_guarded(Rt, 1e-24, valid)
+    Rt = Rt[:, valid]
+    WR = Vs @ Rt; X = Z.T @ WR; C = Rt.T @ WR; C = 0.5 * (C + C.T)
+    # Newton step of P H - C P = X' with diag(H):  column a: (h_aa I - C) p_a = X'[:, a] - (P offdiag(H))[:, a]  (one defect correction)
+    h = np.diag(H)
+    ok = True
+    P = np.zeros((Rt.shape[1], p))
+    try:
+        for sweep in range(int(os.environ.get("NPASS", 2))):
+            rhs = X.T - P @ (H - np.diag(h))
+            for a in range(p):
+                P[:, a] = np.linalg.solve(h[a] * np.eye(C.shape[0]) - C, rhs[:, a])
+    except np.linalg.LinAlgError:
+        ok = False
+    if MODE == "newton" and ok and np.abs(P).max() < PMAXN and Rt.shape[1] > 0:
+        stats["newton"] += 1; stats["pn"].append(np.abs(P).max())
+        B = Z + Rt @ P
+        Gp = P.T @ P
+        if os.environ.get("SERIES"):
+            T = np.eye(p) - 0.5 * Gp + 0.375 * Gp @ Gp        # (I + P'P)^(-1/2) to second order
+            Zn = B @ T
+            Hn = T.T @ (H + X @ P + P.T @ X.T + P.T @ C @ P) @ T
+        else:
+            L = np.linalg.cholesky(np.eye(p) + Gp)
+            Zn = np.linalg.solve(L, B.T).T
+            Hn = np.linalg.solve(L, np.linalg.solve(L, (H + X @ P + P.T @ X.T + P.T @ C @ P).T).T)
+        Hn = 0.5 * (Hn + Hn.T)
+        if SW >= 99:
+            th, Gn = np.linalg.eigh(Hn)
+        else:
+            Hp = Hn if p % 2 == 0 else np.block([[Hn, np.zeros((p, 1))], [np.zeros((1, p)), -1e30 * np.ones((1, 1))]])
+            th, Gn = LR.jacobi_sweeps(Hp, SW); th = th[:p]; Gn = Gn[:p, :p]
+        order = np.argsort(-th, kind="stable")
+        r = int((th > 0).sum())
+        if r + LR.BUF <= p:                          # the full guard band is still there: accept (p can only shrink here)
+            pn = r + LR.BUF
+            sel = order[:pn]
+            return Zn @ Gn[:, sel], th[sel], r, False
+        stats["newton"] -= 1                          # the side grows: let the 2p Rayleigh-Ritz pick new guard vectors
+    stats["jacobi"] += 1
+    return orig(Vs, Z, pm)
+orig = LR.lowrank_step
+LR.lowrank_step = step
+for ni in (0, 3, 5):
+    stats.update(newton=0, jacobi=0, pn=[])
+    t0 = time.time()
+    r = R.solve_relaxation(A, mask, 80.0, 1, "linear", cuts[ni], opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=6000, projection="tracked"))
+    print(MODE, "node", ni, "iters", r["iters"], "st", r["status"], "obj %.9f" % r["objective"], "proj (lr, full)", r["projections"], "newton", stats["newton"], "jacobi", stats["jacobi"],
+          "max|P| median %.1e" % (np.median(stats["pn"]) if stats["pn"] else 0), "%.0fs" % (time.time() - t0), flush=True)
+
+# Results (round 1, config-2 fixture nodes 0 / 3 / 5; baseline = 2p x 2p Jacobi Rayleigh-Ritz: 1276 / 1826 / 1526 iterations):
+#   MODE=newton (exact p x p eigh, two passes, Cholesky, |P| < 0.3):            same iterations, objectives to 1e-9, 99.4 % Newton steps
+#   MODE=newton SW=1 NPASS=1 SERIES=1 PMAXN=1e-2 (what a kernel would do):      same iterations, objectives to 1e-9, 87 / 93 / 62 % Newton
+#       steps, full eigendecompositions 22 / 21 / 69 (baseline 22 / 21 / 34)
+#   PMAXN=1e-3:                                                                  66 / 82 / 53 % Newton steps, full 22 / 21 / 163
+# A Newton step must be refused when fewer than BUF non-positive Ritz values remain (the p-dimensional basis cannot grow).
