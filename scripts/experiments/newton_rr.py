@@ -70,3 +70,7 @@ for ni in (0, 3, 5):
 #       steps, full eigendecompositions 22 / 21 / 69 (baseline 22 / 21 / 34)
 #   PMAXN=1e-3:                                                                  66 / 82 / 53 % Newton steps, full 22 / 21 / 163
 # A Newton step must be refused when fewer than BUF non-positive Ritz values remain (the p-dimensional basis cannot grow).
+# Kernel attempt (newton_rr_kernel_r01.patch, not merged): correct (same iterations / objectives on the fixture nodes), 87 % of
+# the tracking steps took the Newton path, but the Rayleigh-Ritz stage stayed at 54.6 k cycles per projection (2p x 2p Jacobi:
+# 55 k): the warp-level Gaussian elimination by shuffles (16 x 16, fully unrolled) + eight small GEMM barriers + the p x p
+# Jacobi sweep cost as much as the two sweeps they replace.  Needs per-sub-phase cycle counters before a second attempt.
