@@ -146,6 +146,14 @@ int32_t omc_altmin_batch(omc_problem* p, int32_t B, const double* U_initial, con
                          const uint8_t* cut_dirs, double eps, int32_t max_iters, double time_limit_s, double* U, double* V,
                          int32_t* converged, int32_t* n_iters, double* objectives, double* solve_time);
 
+/* Shor 2x2-minor index enumeration, replaces generate_rank1_matrix_completion_Shor_constraints_indexes (OMC.jl:2545-2612,
+ * called at OMC.jl:648-651) and the SOC coordinate list derived from it (OMC.jl:656-665, for fraction = 1.0).  present_list:
+ * the reference's Shor_valid_inequalities_noisy_rank1_num_entries_present (values in 0..4, processed in the order given).
+ * *count receives the number of minors; with tuples == NULL (and soc == nsoc == NULL) the call only counts.  tuples:
+ * [count][4] = (i1, i2, j1, j2), 0-based, in exactly the order the reference pushes them; soc: [*nsoc][2] = (i, j), 0-based,
+ * the coordinates covered by no minor in column-major order (i fastest).  Bit-exact integer work. */
+int32_t omc_shor_indexes(omc_problem* p, const int32_t* present_list, int32_t nlist, int64_t* count, int32_t* tuples,
+                         int64_t cap, int32_t* soc, int64_t* nsoc);
 /* ---- fused objective + MSE: replaces evaluate_objective (OMC.jl:2330-2359) and compute_MSE
  * (OMC.jl:2373-2409).  X column-major n*m.  out[0] objective, out[1] MSE in, out[2] MSE out, out[3] MSE all */
 int32_t omc_objective_mse(omc_problem* p, const double* X, double* out4);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "omc_altmin": (_i32, [_vp, _pf64, _i32, _pi32, _pu8, _f64, _i32, _f64, _pf64, _pf64, _pi32, _pi32, _pf64, _pf64]),
     "omc_altmin_batch": (_i32, [_vp, _i32, _pf64, _pi32, _pi32, _pu8, _f64, _i32, _f64, _pf64, _pf64, _pi32, _pi32, _pf64, _pf64]),
     "omc_objective_mse": (_i32, [_vp, _pf64, _pf64]),
+    "omc_shor_indexes": (_i32, [_vp, _pi32, _i32, _p(C.c_int64), _pi32, _i64, _pi32, _p(C.c_int64)]),
     "omc_debug_psd_project_batch": (_i32, [_i32, _i32, _pf64, _pf64, _pf64, _pi32, _pf32]),
     "omc_measure_fp64_peak": (_i32, [_pf64]),
 }

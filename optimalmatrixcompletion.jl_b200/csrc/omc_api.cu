@@ -16,6 +16,7 @@
 #include "omc_relax.cuh"
 #include "omc_eigsep.cuh"
 #include "omc_altmin.cuh"
+#include "omc_shor.cuh"
 
 namespace {
 
@@ -891,6 +892,87 @@ int32_t omc_altmin(omc_problem* p, const double* U_initial, int32_t ncuts, const
   const int32_t ptr[2] = {0, ncuts};
   return omc_altmin_batch(p, 1, U_initial, ptr, cut_ids, cut_dirs, eps, max_iters, time_limit_s, U, V, converged, n_iters,
                           objectives, solve_time);
+}
+
+int32_t omc_shor_indexes(omc_problem* p, const int32_t* present_list, int32_t nlist, int64_t* count, int32_t* tuples,
+                         int64_t cap, int32_t* soc, int64_t* nsoc) {
+  NEED_INIT();
+  if (!p || !present_list || nlist <= 0 || !count) return fail(OMC_ERR_ARG, "null argument");
+  const int n = p->n, m = p->m;
+  const int W = (m + 63) / 64;
+  if (W > omc::SHOR_MAXW) return fail(OMC_ERR_UNSUPPORTED, "m = %d exceeds %d columns", m, 64 * omc::SHOR_MAXW);
+  if (n < 2) { *count = 0; if (nsoc) *nsoc = 0; return OMC_OK; }
+  int phases_h[2 * 16];
+  int nphase = 0;
+  if (nlist > 16) return fail(OMC_ERR_ARG, "num_entries_present list too long");
+  for (int q = 0; q < nlist; ++q) {
+    switch (present_list[q]) {
+      case 4: phases_h[nphase++] = 0; break;
+      case 3: phases_h[nphase++] = 1; break;
+      case 2: phases_h[nphase++] = 2; phases_h[nphase++] = 3; break;
+      case 1: phases_h[nphase++] = 4; break;
+      case 0: phases_h[nphase++] = 5; break;
+      default: return fail(OMC_ERR_ARG, "num_entries_present must be in 0..4");
+    }
+  }
+  const long long npairs = (long long)n * (n - 1) / 2;
+  const size_t nitems = (size_t)nphase * (size_t)npairs;
+  DevBuf<unsigned long long> rowbits;
+  DevBuf<long long> dcounts;
+  DevBuf<int> dphases;
+  CU(rowbits.alloc((size_t)n * W)); CU(dcounts.alloc(nitems)); CU(dphases.alloc(nphase));
+  CU(cudaMemcpyAsync(dphases.p, phases_h, nphase * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+  omc::shor_rowmask_kernel<<<(n * W + 255) / 256, 256, 0, g_stream>>>(p->Mk.p, n, m, W, rowbits.p);
+  omc::shor_count_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, g_stream>>>(rowbits.p, n, m, W, dphases.p, nphase, npairs, dcounts.p);
+  CU(cudaGetLastError());
+  long long* hc = (long long*)malloc(nitems * sizeof(long long));
+  if (!hc) return fail(OMC_ERR_ARG, "out of host memory");
+  cudaError_t ce = cudaMemcpyAsync(hc, dcounts.p, nitems * sizeof(long long), cudaMemcpyDeviceToHost, g_stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(g_stream);
+  if (ce != cudaSuccess) { free(hc); return fail(OMC_ERR_CUDA, "Shor count failed: %s", cudaGetErrorString(ce)); }
+  long long total = 0;
+  for (size_t e = 0; e < nitems; ++e) { const long long c_ = hc[e]; hc[e] = total; total += c_; }   // exclusive scan, phase-major
+  *count = total;
+  const bool want_soc = (soc != nullptr) || (nsoc != nullptr);
+  if (!tuples && !want_soc) { free(hc); return OMC_OK; }
+  if (tuples && cap < total) { free(hc); return fail(OMC_ERR_ARG, "tuple buffer holds %lld, need %lld", (long long)cap, total); }
+  if (total > (1ll << 28)) { free(hc); return fail(OMC_ERR_UNSUPPORTED, "%lld minors do not fit this build", total); }
+  DevBuf<int> dtuples, dsoc;
+  DevBuf<unsigned int> dcov;
+  DevBuf<long long> dnsoc;
+  const long long ncoord = (long long)n * m;
+  ce = dtuples.alloc((size_t)(total > 0 ? 4 * total : 4));
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(dcounts.p, hc, nitems * sizeof(long long), cudaMemcpyHostToDevice, g_stream);
+  if (ce == cudaSuccess && want_soc) {
+    ce = dcov.alloc((size_t)((ncoord + 31) / 32));
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(dcov.p, 0, (size_t)((ncoord + 31) / 32) * sizeof(unsigned int), g_stream);
+    if (ce == cudaSuccess) ce = dsoc.alloc((size_t)(2 * ncoord));
+    if (ce == cudaSuccess) ce = dnsoc.alloc(1);
+  }
+  free(hc);
+  if (ce != cudaSuccess) return fail(OMC_ERR_CUDA, "Shor allocation failed: %s", cudaGetErrorString(ce));
+  if (total > 0) {
+    const int wpb = 8;
+    const size_t smem = (size_t)wpb * 3 * m * sizeof(int);
+    long long blocks = ((long long)nitems + wpb - 1) / wpb;
+    if (blocks > (long long)g_sm_count * 16) blocks = (long long)g_sm_count * 16;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(omc::shor_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    omc::shor_fill_kernel<<<(unsigned)blocks, wpb * 32, smem, g_stream>>>(rowbits.p, n, m, W, dphases.p, nphase, npairs, dcounts.p, dtuples.p,
+                                                                        want_soc ? dcov.p : nullptr, m);
+    CU(cudaGetLastError());
+    if (tuples) CU(cudaMemcpyAsync(tuples, dtuples.p, (size_t)(4 * total) * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  }
+  if (want_soc) {
+    omc::shor_soc_kernel<<<1, 1024, 0, g_stream>>>(dcov.p, ncoord, n, dsoc.p, dnsoc.p);
+    CU(cudaGetLastError());
+    long long hn = 0;
+    CU(cudaMemcpyAsync(&hn, dnsoc.p, sizeof(long long), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    if (nsoc) *nsoc = hn;
+    if (soc && hn > 0) CU(cudaMemcpyAsync(soc, dsoc.p, (size_t)(2 * hn) * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  }
+  CU(cudaStreamSynchronize(g_stream));
+  return OMC_OK;
 }
 
 }  // extern "C"

@@ -336,6 +336,19 @@ def alternating_minimization_batch(problem: Problem, U_initials, disjunctive_cut
              "max_iters": max_iters, "objectives": [float(v) for v in obj[b, : nit[b]]]} for b in range(B)]
 
 
+def shor_constraint_indexes(problem: Problem, num_entries_present_list, with_soc: bool = True):
+    """generate_rank1_matrix_completion_Shor_constraints_indexes (OMC.jl:2545-2612) and the SOC coordinate list (OMC.jl:656-665)
+    on the GPU.  Returns (tuples (N, 4) int32, soc (M, 2) int32), both 0-BASED (add 1 for the reference's 1-based tuples)."""
+    pl = np.asarray(list(num_entries_present_list), np.int32)
+    cnt = C.c_int64(0); nsoc = C.c_int64(0)
+    check(problem.lib.omc_shor_indexes(problem.handle, _ptr(pl, C.c_int32), len(pl), C.byref(cnt), None, 0, None, None))
+    tuples = np.zeros((max(1, cnt.value), 4), np.int32)
+    soc = np.zeros((problem.n * problem.m, 2), np.int32) if with_soc else None
+    check(problem.lib.omc_shor_indexes(problem.handle, _ptr(pl, C.c_int32), len(pl), C.byref(cnt), _ptr(tuples, C.c_int32), cnt.value,
+                                       _ptr(soc, C.c_int32) if with_soc else None, C.byref(nsoc) if with_soc else None))
+    return tuples[: cnt.value], (soc[: nsoc.value] if with_soc else None)
+
+
 def psd_project_batch(V: np.ndarray):
     """Eigensolver self-test entry: V (B,N,N) symmetric -> (P, lam, sweeps, kernel_ms)."""
     lib = init()

@@ -186,6 +186,19 @@ function alternating_minimization_batch(p::Problem, U_initials::Vector{Matrix{Fl
                  "n_iters" => Int(nit[b]), "max_iters" => max_iters, "objectives" => objectives[1:nit[b], b]) for b in 1:B]
 end
 
+"""`generate_rank1_matrix_completion_Shor_constraints_indexes` (OMC.jl:2545-2612) and the SOC coordinate list of OMC.jl:656-665
+on the GPU; returns 1-based `Vector{NTuple{4,Int}}` and `Vector{Tuple{Int,Int}}` exactly as the reference builds them."""
+function shor_constraint_indexes(p::Problem, num_entries_present_list::Vector{Int})
+    pl = Int32.(num_entries_present_list)
+    cnt = Ref{Int64}(0); nsoc = Ref{Int64}(0)
+    check(ccall((:omc_shor_indexes, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ref{Int64}, Ptr{Int32}, Int64, Ptr{Int32}, Ptr{Int64}),
+                p.handle, pl, length(pl), cnt, C_NULL, 0, C_NULL, C_NULL))
+    tuples = zeros(Int32, 4, max(1, cnt[])); soc = zeros(Int32, 2, p.n * p.m)
+    check(ccall((:omc_shor_indexes, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ref{Int64}, Ptr{Int32}, Int64, Ptr{Int32}, Ref{Int64}),
+                p.handle, pl, length(pl), cnt, tuples, cnt[], soc, nsoc))
+    return [ntuple(q -> Int(tuples[q, t]) + 1, 4) for t in 1:cnt[]], [(Int(soc[1, t]) + 1, Int(soc[2, t]) + 1) for t in 1:nsoc[]]
+end
+
 """Fused `evaluate_objective` (OMC.jl:2330-2359) + `compute_MSE` (OMC.jl:2373-2409): (objective, in, out, all)."""
 function objective_mse(p::Problem, X::Matrix{Float64})
     out = zeros(4)

@@ -402,3 +402,33 @@ def test_alternating_minimization_config5_size_properties(omc):
         lhs = U0[I].T @ U0[I] + G0
         assert np.abs(lhs @ V1[:, j] - U0[I].T @ A[I, j]).max() <= 1e-9 * max(1.0, np.abs(A[I, j]).max())
     p.close()
+
+
+def test_shor_minor_indexes_bit_exact(omc):
+    """Row a10: the Shor minor index list and the SOC coordinate list (OMC.jl:2545-2612, 648-665) from the GPU equal the
+    oracle's restatement element for element -- same tuples in the same order -- on random masks (empty, full, ragged), on
+    every ordering of the num_entries_present list, and on the config 3 mask (180 k minors)."""
+    from oracle import shor as S
+    from oracle.datagen import config_instance
+    rng = np.random.default_rng(7)
+    cases = [(2, 2, 1.0), (3, 5, 0.0), (4, 7, 0.5), (7, 9, 0.3), (9, 13, 0.8), (12, 70, 0.5), (6, 6, 1.0)]
+    lists = ([4], [3], [2], [1], [0], [1, 2, 3, 4], [4, 3, 2, 1, 0], [2, 4, 2])
+    for n, m, dens in cases:
+        mask = rng.random((n, m)) < dens
+        p = omc.Problem(1, rng.standard_normal((n, m)), mask, 80.0)
+        for pl in lists:
+            tg, sg = omc.shor_constraint_indexes(p, pl)
+            want = np.array(S.shor_constraint_indexes(mask, pl), dtype=np.int64).reshape(-1, 4) - 1
+            assert tg.shape == want.shape and np.array_equal(tg, want), (n, m, dens, pl)
+            cov = np.zeros((n, m), bool)
+            for i1, i2, j1, j2 in want:
+                cov[i1, j1] = cov[i1, j2] = cov[i2, j1] = cov[i2, j2] = True
+            soc_want = np.array([(i, j) for j in range(m) for i in range(n) if not cov[i, j]], dtype=np.int64).reshape(-1, 2)
+            assert np.array_equal(sg, soc_want), (n, m, dens, pl)
+        p.close()
+    k, A, mask, g = config_instance("C3", 0)
+    p = omc.Problem(k, A, mask, g, "linear2")
+    tg, sg = omc.shor_constraint_indexes(p, [1, 2, 3, 4])
+    want = np.array(S.shor_constraint_indexes(mask, [1, 2, 3, 4]), dtype=np.int64).reshape(-1, 4) - 1
+    assert len(want) > 100000 and np.array_equal(tg, want)
+    p.close()
