@@ -312,7 +312,7 @@ __device__ __forceinline__ void small_jacobi(double* M, double* G, int n, int ld
 // side of V, -1 the negative side (the positive side of -V).  lp (optional, 8 slots): cycles per sub-phase.
 // Returns need_full (uniform over the CTA).
 template <int PM>
-__device__ __noinline__ int lowrank_step(const double* V, int ldv, bool vglobal, int N, int NP, double side, double* P0, double* P1, double* P2,
+__device__ __forceinline__ int lowrank_step(const double* V, int ldv, bool vglobal, int N, int NP, double side, double* P0, double* P1, double* P2,
                                    int p, LrSmall<PM>& S, double vscale, long long* lp, double** Zout) {
   constexpr int LD = LrSmall<PM>::LD, LD2 = LrSmall<PM>::LD2;
   const int tid = threadIdx.x, nt = blockDim.x;

@@ -470,7 +470,7 @@ __device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
 
 // phase 1a: X and Theta rows of the w-update (own function: its register-staged loads must not compete with the rest)
 template <int NT, int KMAX, int PM>
-__device__ __noinline__ void relax_p1_xt(const RelaxArgs& P, KFrame& F) {
+__device__ __forceinline__ void relax_p1_xt(const RelaxArgs& P, KFrame& F) {
   const int tid = threadIdx.x;
   const int n = P.n, m = P.m;
   const StateLayout& SL = P.SL;
@@ -536,7 +536,7 @@ __device__ __noinline__ void relax_p1_xt(const RelaxArgs& P, KFrame& F) {
 
 // phase 1b: Y and U rows of the w-update into shared memory (before the dense-row correction)
 template <int NT, int KMAX, int PM>
-__device__ __noinline__ void relax_p1_yu(const RelaxArgs& P, KFrame& F) {
+__device__ __forceinline__ void relax_p1_yu(const RelaxArgs& P, KFrame& F) {
   const int tid = threadIdx.x;
   const int n = P.n, k = P.k;
   const StateLayout& SL = P.SL;
