@@ -48,7 +48,7 @@ def node_iter_flops(n, m, k, L):
 
 
 def c2_instance(seed=0):
-    from oracle.datagen import generate_matrix_completion_data  # data generator only (synthetic inputs)
+    from omc_b200.synthetic import generate_matrix_completion_data  # host-side data generator of the package (not the oracle)
     return generate_matrix_completion_data(1, 50, 50, 1250, seed)
 
 
@@ -297,7 +297,7 @@ def run_b200(args):
             sol, _, inst = omc.matrix_completion_branchandbound(k, A, mask, 80.0, node_selection="bestfirst", disjunctive_cuts_type="linear",
                                                                  disjunctive_cuts_breakpoints="smallest_1_eigvec", time_limit=120, verbosity=0)
             t_gap = time.perf_counter() - t0
-            from oracle.datagen import generate_matrix_completion_data
+            from omc_b200.synthetic import generate_matrix_completion_data
             A5, m5 = generate_matrix_completion_data(5, 1000, 1000, 200000, 0)
             p5 = omc.Problem(5, A5, m5, 80.0, "linear")
             U5 = np.linalg.svd(np.where(m5, A5, 0.0))[0][:, :5]

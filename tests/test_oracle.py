@@ -273,3 +273,13 @@ def test_altmin_oracle_vstep_exact_ustep_matches_slsqp_and_stopping_rule():
         if r["converged"] and len(ob) >= 2:
             rel = abs((ob[-1] - ob[-2]) / ob[-2])
             assert rel < 1e-5 or (len(ob) > 5 and all(ob[-1 - i] > ob[-6] for i in range(5)))
+
+
+def test_package_generator_equals_oracle_generator():
+    """bench.py feeds the engine from the package's own generator (the product never imports oracle/): same stream, same data."""
+    from omc_b200 import synthetic as PS
+    from oracle import datagen as OD
+    for args in ((1, 10, 10, 50, 0), (2, 30, 30, 450, 1), (1, 50, 50, 1250, 0)):
+        A1, m1 = PS.generate_matrix_completion_data(*args)
+        A2, m2 = OD.generate_matrix_completion_data(*args)
+        assert np.array_equal(A1, A2) and np.array_equal(m1, m2)
