@@ -43,6 +43,8 @@ extern "C" {
 #define OMC_STATUS_TIME_LIMIT 3      /* MOI.TIME_LIMIT with values                                */
 #define OMC_STATUS_CUTOFF 4          /* certified lower bound > opts.cutoff: objective := that bound,
                                         reported as MOI.OPTIMAL; the host prunes it at OMC.jl:797  */
+#define OMC_STATUS_NUMERICAL 5       /* a non-finite iterate was met: the glue raises "unexpected termination
+                                        status" like the reference's final else branch (OMC.jl:1936-1940)  */
 
 /* disjunctive_cuts_type (OMC.jl:1581,1603,1635) */
 #define OMC_CUT_LINEAR 0

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libomc_b200.so")
 
 OK = 0
-STATUS_OPTIMAL, STATUS_ITERATION_LIMIT, STATUS_INFEASIBLE, STATUS_TIME_LIMIT, STATUS_CUTOFF = 0, 1, 2, 3, 4
+STATUS_OPTIMAL, STATUS_ITERATION_LIMIT, STATUS_INFEASIBLE, STATUS_TIME_LIMIT, STATUS_CUTOFF, STATUS_NUMERICAL = 0, 1, 2, 3, 4, 5
 CUT_TYPES = {"linear": 0, "linear2": 1, "linear3": 2}
 
 

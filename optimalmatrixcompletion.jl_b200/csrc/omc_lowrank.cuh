@@ -421,6 +421,7 @@ __device__ __forceinline__ int lowrank_step(const double* V, int ldv, bool vglob
     if (pn > nlive) pn = nlive;
     int need_full = 0;
     if (r + 1 > PM || r >= nlive) need_full = 1;   // no guard band left: the minority side may be larger than tracked
+    if (2 * (r + OMC_LR_BUF) > N) need_full = 1;  // [Z R~] must fit the block: the residual needs p free directions
     if (pn > PM) pn = PM;
     if (lane < nlive && rank < pn) {
       S.sel[rank] = lane;

@@ -409,8 +409,9 @@ __device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
 
     // ---- Gram matrix of the dense rows: G = R R'  (row 0 trace, 1+l*k+j the v rows, 1+L*k+l the aggregated rows)
     {
-      // C[l][l'] = x_l . x_l' staged in buf0 (L*L <= bufsz is guaranteed by the host)
-      double* C = buf0;
+      // C[l][l'] = x_l . x_l' staged in buf0, or in the (not yet built) Minv slot of the scratch record when a small
+      // problem carries more cuts than buf0 holds (r * r > L * L doubles there)
+      double* C = ((size_t)L * L <= bufsz) ? buf0 : c.Minv;
       for (int e = warp; e < L * L; e += NW) {
         const int l1 = e / L, l2 = e - l1 * L;
         double d = 0.0;
@@ -886,7 +887,10 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
             __syncthreads();
           }
           OMC_TICK(2)
-          nsweeps += jacobi_sym(B0, B1, NP, ld, exact_iter ? fmin(jtol, 1e-10) : jtol, 40, jcs, jsn, jrot, red, 1, jskip, &ish[4],
+          // a cold solve (first iteration, re-orthogonalisation, tracker fallback) runs to the tight tolerance: the loose jtol is
+          // only sound for warm solves, whose error is coherent from one iteration to the next (with cold solves every
+          // projection carries an independent O(jtol) error and the residual stalls at ~100 jtol: seen on 6 x 6 blocks)
+          nsweeps += jacobi_sym(B0, B1, NP, ld, (exact_iter || !warm_now) ? fmin(jtol, 1e-10) : jtol, 40, jcs, jsn, jrot, red, 1, jskip, &ish[4],
                                 P.prof ? (P.prof + (size_t)node * OMC_PROF_STRIDE + 8 + 3 * (b == 0 ? 0 : 1)) : nullptr);
           OMC_SETBIT(have_basis_bits, b, 1);
           OMC_TICK(3)
@@ -947,7 +951,8 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
 #endif
           // switch to the low-rank projection when the minority side (plus guard band) fits the panel: the tracked
           // basis = the minority-side eigenvectors and the OMC_LR_BUF eigenvectors next to them across zero
-          if (!P.o.exact_projection && ish[5] + OMC_LR_BUF <= PM && ish[5] + OMC_LR_BUF <= N) {
+          // (only when the Rayleigh-Ritz space [Z R~] of 2 p directions fits the block: small blocks stay on the full solver)
+          if (!P.o.exact_projection && ish[5] + OMC_LR_BUF <= PM && 2 * (ish[5] + OMC_LR_BUF) <= N) {
             const int side = ish[2], pz = ish[5] + OMC_LR_BUF;
             if (tid < 16) jrot[tid] = -1;
             __syncthreads();
@@ -1173,7 +1178,10 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
           lbound = obj_d - rd * w1;
         }
         bool stop = false;
-        if (rp <= P.o.eps_abs + P.o.eps_rel * np_ && rd <= P.o.eps_abs + P.o.eps_rel * nd_) {
+        if (!(fabs(obj_p) < 1e300 && fabs(obj_d) < 1e300 && rp < 1e300 && rd < 1e300)) {  // NaN / overflow (fmax drops NaN)
+          status = OMC_STATUS_NUMERICAL;
+          stop = true;
+        } else if (rp <= P.o.eps_abs + P.o.eps_rel * np_ && rd <= P.o.eps_abs + P.o.eps_rel * nd_) {
           if (provisional && it < P.o.max_iter) {
             exact_iter = true;
             force_check = true;
@@ -1301,11 +1309,14 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const __grid_consta
   double* buf0 = reinterpret_cast<double*>(smem_raw);
   double* buf1 = buf0 + bufsz;
   const size_t bufsz1 = region1_doubles<PM>(gfit, g1.NP);
-  double* lam = buf1 + bufsz1;             // [NP1]
-  double* wgt = lam + g1.NP;               // [NP1]
-  double* jcs = wgt + g1.NP;               // [NP1/2]
-  double* jsn = jcs + g1.NP / 2;           // [NP1/2]
-  double* red = jsn + g1.NP / 2;           // [32]
+  // the per-index arrays hold at least 16 entries: the tracker's panel bookkeeping (idx / wgt / jrot[0..16)) is sized
+  // by the panel, not by the block (blocks of 8 rows overflowed them: seen as a stalled ADMM on 3 x 3 and 4 x 4 inputs)
+  const int NPI = g1.NP < 16 ? 16 : g1.NP;
+  double* lam = buf1 + bufsz1;             // [NPI]
+  double* wgt = lam + NPI;                 // [NPI]
+  double* jcs = wgt + NPI;                 // [NPI/2]
+  double* jsn = jcs + NPI / 2;             // [NPI/2]
+  double* red = jsn + NPI / 2;             // [32]
   double* rhs = red + 32;                  // [rmax]
   double* cw = rhs + P.rmax;               // [rmax]
   double* gc = cw + P.rmax;                // [rmax]
@@ -1319,10 +1330,10 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const __grid_consta
   uint64_t* mbar = reinterpret_cast<uint64_t*>(cxp + P.Lcap);           // [1]
   long long* sprof = reinterpret_cast<long long*>(mbar + 1);            // [24] cycle counters (thread 0 accumulates)
   KFrame& F = *reinterpret_cast<KFrame*>(sprof + 24);                   // the shared frame
-  int* jrot = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(&F) + ((sizeof(KFrame) + 7) & ~(size_t)7));  // [3*NP1/2]
-  int* idx = jrot + 3 * (g1.NP / 2);                                    // [NP1]
-  int* jskip = idx + g1.NP;                                             // [NP1] projection-mode skip flags
-  int* ish = jskip + g1.NP;                                             // [8] misc ints
+  int* jrot = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(&F) + ((sizeof(KFrame) + 7) & ~(size_t)7));  // [3*NPI/2]
+  int* idx = jrot + 3 * (NPI / 2);                                      // [NPI]
+  int* jskip = idx + NPI;                                               // [NPI] projection-mode skip flags
+  int* ish = jskip + NPI;                                               // [8] misc ints
 
   if (tid == 0) {
     double* scr = P.scratch + (size_t)blockIdx.x * P.SC.total;
@@ -1395,8 +1406,9 @@ inline size_t relax_smem_bytes(int n, int m, int k, int Lcap, int rmax, int xs_c
   Geo gf = smem_geo(n + m, n + k, n);
   size_t d = 0;
   d += (size_t)gf.NP * gf.ld + region1_doubles<PM>(gf, g1.NP);   // buf0, region 1
-  d += 2 * (size_t)g1.NP;                // lam, wgt
-  d += 2 * (size_t)(g1.NP / 2);          // jcs, jsn
+  const size_t NPI = g1.NP < 16 ? 16 : g1.NP;
+  d += 2 * NPI;                          // lam, wgt
+  d += 2 * (NPI / 2);                    // jcs, jsn
   d += 32;                               // red
   d += 3 * (size_t)rmax;                 // rhs, cw, gc
   d += 3 * (size_t)Lcap * k + Lcap;      // clb, cub, cal, cbe
@@ -1405,7 +1417,7 @@ inline size_t relax_smem_bytes(int n, int m, int k, int Lcap, int rmax, int xs_c
   d += 1 + 24;                           // mbar, sprof
   d += (sizeof(KFrame) + 7) / 8;         // the shared frame
   size_t bytes = d * 8;
-  bytes += sizeof(int) * (3 * ((size_t)g1.NP / 2) + 2 * (size_t)g1.NP + 8);
+  bytes += sizeof(int) * (3 * (NPI / 2) + 2 * NPI + 8);
   return (bytes + 127) & ~(size_t)127;
 }
 

@@ -21,7 +21,7 @@ LABELS = {
     "linear3": ["left", "inner_left", "inner_right", "right"],    # OMC.jl:2490
 }
 # status -> the MOI termination status name the Julia glue reports (OMC.jl:1866-1940)
-MOI_STATUS = {0: "OPTIMAL", 1: "SLOW_PROGRESS", 2: "INFEASIBLE", 3: "TIME_LIMIT", 4: "OPTIMAL"}
+MOI_STATUS = {0: "OPTIMAL", 1: "SLOW_PROGRESS", 2: "INFEASIBLE", 3: "TIME_LIMIT", 4: "OPTIMAL", 5: "NUMERICAL_ERROR"}
 
 _initialised = None
 
@@ -204,6 +204,8 @@ class Frontier:
                                        _ptr(X, C.c_double), _ptr(Y, C.c_double), _ptr(U, C.c_double), None))
         out = []
         for b in range(B):
+            if int(status[b]) == _lib.STATUS_NUMERICAL:               # OMC.jl:1936-1940: the reference errors here too
+                raise RuntimeError(f"unexpected termination status: NUMERICAL_ERROR (node {b} of the batch)")
             r = {
                 "model": None,                                        # OMC.jl:1861 (never read by the host loop)
                 "termination_status": MOI_STATUS[int(status[b])],     # OMC.jl:1863

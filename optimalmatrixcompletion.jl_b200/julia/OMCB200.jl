@@ -116,6 +116,9 @@ function relax_batch(p::Problem, nodes; opts::RelaxOpts = default_opts())
          Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
          Ptr{Float64}, Ref{Float32}),
         p.handle, B, ptr, ids, dirs, C_NULL, C_NULL, opts, status, objective, lower, iters, res, X, Y, U, C_NULL, ms))
+    for b in 1:B   # OMC_STATUS_NUMERICAL: same failure mode as the reference's final else branch (OMC.jl:1936-1940)
+        status[b] == 5 && error("unexpected termination status: NUMERICAL_ERROR (node $b of the batch)")
+    end
     return [Dict{String, Any}(
         "model" => nothing,
         "solve_time" => t / B,

@@ -101,7 +101,7 @@ def lowrank_step(Vs, Z, pm):
     th = th[:nl]
     order = np.argsort(-th, kind="stable")
     r = int((th > 0).sum())
-    need_full = (r + 1 > pm) or (r >= nl)
+    need_full = (r + 1 > pm) or (r >= nl) or (2 * (r + BUF) > Vs.shape[0])
     pn = min(r + BUF, nl, pm)
     sel = order[:pn]
     B = np.hstack([Z, Rt])[:, live]
@@ -122,7 +122,7 @@ class TrackedProjector:
         side = 1 if npos <= nneg else -1
         r = npos if side > 0 else nneg
         N = V.shape[0]
-        if r + BUF <= self.pm and r + BUF <= N:
+        if r + BUF <= self.pm and 2 * (r + BUF) <= N:   # [Z R~] has 2 p directions: small blocks stay exact
             order = np.argsort(-side * lam, kind="stable")
             self.Z = Q[:, order[:r + BUF]]; self.side = side
         else:

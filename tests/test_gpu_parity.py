@@ -432,3 +432,72 @@ def test_shor_minor_indexes_bit_exact(omc):
     want = np.array(S.shor_constraint_indexes(mask, [1, 2, 3, 4]), dtype=np.int64).reshape(-1, 4) - 1
     assert len(want) > 100000 and np.array_equal(tg, want)
     p.close()
+
+
+def test_edge_shapes_smallest_full_mask_and_k_equal_n(omc):
+    """Smallest sizes, fully observed masks, k = n and k = 2 with tall-thin A: bound vs oracle, 1e-6 relative."""
+    from oracle import relaxation as R
+    from oracle.datagen import generate_matrix_completion_data
+    for (n, m, k, nobs) in [(2, 2, 1, 4), (2, 3, 2, 5), (3, 7, 2, 10), (5, 5, 1, 25), (4, 9, 4, 20), (3, 3, 1, 7), (4, 4, 1, 12)]:
+        A, mask = generate_matrix_completion_data(k, n, m, nobs, 3)
+        p = omc.Problem(k, A, mask, 20.0, "linear")
+        r = p.relax_batch([[]], omc.default_opts(eps_abs=1e-8, eps_rel=1e-8, max_iter=200000))[0]
+        ro = R.solve_relaxation(A, mask, 20.0, k, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=200000))
+        assert r["termination_status"] == "OPTIMAL", (n, m, k)
+        assert abs(r["objective"] - ro["objective"]) <= REL_BOUND * abs(ro["objective"]) + 1e-9, (n, m, k, r["objective"], ro["objective"])
+        assert r["lower_bound"] <= ro["objective"] * (1 + 1e-6) + 1e-9
+        p.close()
+
+
+def test_ragged_frontier_zero_to_capacity_cuts(omc):
+    """One batch holding nodes with 0, 1, 5 and 64 (the capacity) cuts: batch == singles, the 5-cut node equals the
+    oracle, bounds grow along a nested cut chain, and capacity + 1 cuts is refused."""
+    from oracle import relaxation as R
+    from oracle.datagen import config_instance
+    k, A, mask, g = config_instance("C1", 0)
+    n = A.shape[0]
+    p = omc.Problem(k, A, mask, g, "linear")
+    rng = np.random.default_rng(17)
+    ustar = rng.standard_normal(n); ustar /= np.linalg.norm(ustar)
+    chain, ocuts = [], []
+    for _ in range(65):
+        x = rng.standard_normal(n); x /= np.linalg.norm(x)
+        Uh = rng.uniform(-0.5, 0.5) * x[:, None]                   # vhat = Uh' x in (-0.5, 0.5)
+        d = ["left"] if float(x @ ustar) <= float(Uh[:, 0] @ x) else ["right"]   # u* stays feasible down the chain
+        chain.append(omc.Cut(p.add_cut(x, Uh), x, Uh, d)); ocuts.append((x, Uh, d))
+    opts = omc.default_opts(eps_abs=1e-8, eps_rel=1e-8, max_iter=200000)
+    nodes = [chain[:0], chain[:1], chain[:5], chain[:64]]
+    batch = p.relax_batch(nodes, opts)
+    for b, nd in enumerate(nodes):
+        assert batch[b]["termination_status"] == "OPTIMAL", b
+        assert batch[b]["objective"] == p.relax_batch([nd], opts)[0]["objective"]
+        if b:
+            assert batch[b]["objective"] >= batch[b - 1]["objective"] * (1 - 1e-6)
+    ro = R.solve_relaxation(A, mask, g, k, "linear", ocuts[:5], opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=200000))
+    assert abs(batch[2]["objective"] - ro["objective"]) <= REL_BOUND * ro["objective"]
+    # the rank-1 point built from u* is feasible for every node: it bounds all of them from above
+    uu = ustar[:, None]
+    Xs = uu @ (uu.T @ np.where(mask, A, 0.0))
+    assert batch[3]["objective"] <= p.objective_mse(Xs)[0] * (1 + 1e-9)
+    with pytest.raises(Exception, match="exceeds the supported"):
+        p.relax_batch([chain[:65]], opts)
+    p.close()
+
+
+def test_tracked_equals_exact_projection_over_a_sweep_of_small_shapes(omc):
+    """61 shapes from 2 x 2 to 24 x 72, k = 1..4: the default (tracked) path and the exact-projection path both reach
+    OPTIMAL with bounds within 1e-6 relative and comparable iteration counts.  (This sweep found three defects that the
+    BASELINE shapes never touch: per-index scratch sized by an 8-row block, the cut Gram staging of a small problem with
+    more than sqrt(buf0) cuts, and cold eigensolves run at the loose warm-start tolerance.)"""
+    import itertools
+    from oracle.datagen import generate_matrix_completion_data
+    shapes = [(2, 2, 1), (2, 3, 2), (3, 7, 2), (5, 5, 1), (4, 9, 4), (3, 3, 1), (4, 4, 1)]
+    shapes += [(n, n * mm, k) for n, mm, k in itertools.product((6, 8, 10, 12, 16, 24), (1, 2, 3), (1, 2, 3))]
+    for (n, m, k) in shapes:
+        A, mask = generate_matrix_completion_data(k, n, m, min(max(n + m, int(0.6 * n * m)), n * m), 3)
+        p = omc.Problem(k, A, mask, 20.0, "linear")
+        rt, re_ = [p.relax_batch([[]], omc.default_opts(eps_abs=1e-8, eps_rel=1e-8, max_iter=30000, exact_projection=ex))[0] for ex in (0, 1)]
+        assert rt["termination_status"] == re_["termination_status"] == "OPTIMAL", (n, m, k)
+        assert abs(rt["objective"] - re_["objective"]) <= REL_BOUND * abs(re_["objective"]), (n, m, k, rt["objective"], re_["objective"])
+        assert rt["iters"] <= 1.5 * re_["iters"] + 50, (n, m, k, rt["iters"], re_["iters"])
+        p.close()
