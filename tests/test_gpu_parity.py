@@ -501,3 +501,52 @@ def test_tracked_equals_exact_projection_over_a_sweep_of_small_shapes(omc):
         assert abs(rt["objective"] - re_["objective"]) <= REL_BOUND * abs(re_["objective"]), (n, m, k, rt["objective"], re_["objective"])
         assert rt["iters"] <= 1.5 * re_["iters"] + 50, (n, m, k, rt["iters"], re_["iters"])
         p.close()
+
+
+def _cut_region(ct, v, h):
+    a = abs(h)
+    if ct == "linear":
+        return "left" if v <= h else "right"
+    if ct == "linear2":
+        return "left" if v <= -a else ("middle" if v <= a else "right")
+    return "left" if v <= -a else ("inner_left" if v <= 0 else ("inner_right" if v <= a else "right"))
+
+
+def _feasible_chain(ct, n, k, L, rng):
+    """L cuts whose regions all contain one hidden rank-k factor (orthonormal columns, bottom k x k block a positive
+    diagonal so that the sign normalisation OMC.jl:1442-1449 holds)."""
+    W, _ = np.linalg.qr(rng.standard_normal((n - k, k)))
+    th = rng.uniform(0.3, 1.2, size=k)
+    Us = np.vstack([W * np.cos(th), np.diag(np.sin(th))])
+    out = []
+    for _ in range(L):
+        x = rng.standard_normal(n); x /= np.linalg.norm(x)
+        Uh = rng.uniform(-0.4, 0.4, size=(1, k)) * x[:, None]
+        out.append((x, Uh, [_cut_region(ct, float(x @ Us[:, j]), float(Uh[:, j] @ x)) for j in range(k)]))
+    return out
+
+
+def test_cut_chains_of_every_type_and_rank_against_the_oracle(omc):
+    """k = 1..3, all three disjunctive cut types (OMC.jl:1580-1683), chains of 3 and 10 cuts: bound of the tracked and
+    of the exact path vs the oracle, 1e-6 relative.  Chains on which the oracle itself does not reach OPTIMAL (linear3 /
+    right carries the reference's quirk Q1 and can make a node infeasible) are skipped."""
+    import itertools
+    from oracle import relaxation as R
+    from oracle.datagen import generate_matrix_completion_data
+    checked = 0
+    for (n, m, k), ct, L in itertools.product([(4, 4, 1), (6, 9, 2), (8, 8, 3)], ("linear", "linear2", "linear3"), (3, 10)):
+        rng = np.random.default_rng(100 * n + 10 * k + L)
+        A, mask = generate_matrix_completion_data(k, n, m, max(n + m, int(0.6 * n * m)), 5)
+        cuts = _feasible_chain(ct, n, k, L, rng)
+        ro = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000))
+        if ro["status"] != R.STATUS_OPTIMAL:
+            continue
+        p = omc.Problem(k, A, mask, 20.0, ct)
+        gc = [omc.Cut(p.add_cut(x, Uh), x, Uh, d) for x, Uh, d in cuts]
+        for ex in (0, 1):
+            r = p.relax_batch([gc], omc.default_opts(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000, exact_projection=ex))[0]
+            assert r["termination_status"] == "OPTIMAL", (n, m, k, ct, L, ex)
+            assert abs(r["objective"] - ro["objective"]) <= REL_BOUND * abs(ro["objective"]), (n, m, k, ct, L, ex, r["objective"], ro["objective"])
+        p.close()
+        checked += 1
+    assert checked >= 15
