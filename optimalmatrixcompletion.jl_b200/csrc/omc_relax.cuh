@@ -57,6 +57,8 @@ __host__ __device__ inline StateLayout make_state_layout(int n, int m, int k, in
 // Largest PSD block that is diagonalised in shared memory (two NP x ld FP64 buffers must fit in 227 KB):
 // blocks with NP > OMC_SMEM_NP_MAX run through the same device functions on an L2-resident global buffer.
 #define OMC_SMEM_NP_MAX 104
+#define OMC_EPS_INF 1e-6    // relative tolerance of the primal infeasibility certificate (oracle: Options.eps_inf)
+#define OMC_EPS_INF_LOOSE 1e-3
 #define OMC_PROF_STRIDE 32  // doubles of per-node profile counters (omc_frontier_fetch_profile)
 #define OMC_XS_CAP 3072  // doubles of shared memory reserved for a node's cut vectors (L * n <= 3072 are cached)
 __host__ __device__ inline Geo smem_geo(int N1, int N2, int N3) {
@@ -70,7 +72,7 @@ __host__ __device__ inline Geo smem_geo(int N1, int N2, int N3) {
 }
 
 struct ScratchLayout {
-  size_t wt, Q1, Q2, Q3, Z1, Z2, Z3, G, Minv, state, big0, total;
+  size_t wt, Q1, Q2, Q3, Z1, Z2, Z3, G, Minv, state, big0, mold, total;
 };
 __host__ __device__ inline ScratchLayout make_scratch_layout(const StateLayout& S, int rmax) {
   ScratchLayout C;
@@ -90,6 +92,10 @@ __host__ __device__ inline ScratchLayout make_scratch_layout(const StateLayout& 
   o = (o + 1) & ~(size_t)1;
   C.big0 = o;
   if (g1.NP > OMC_SMEM_NP_MAX) o += (size_t)g1.NP * g1.ld;   // working matrix of a block too large for shared memory
+  o = (o + 1) & ~(size_t)1;
+  // multipliers of the previous iteration (infeasibility certificate): image of the record's span [s1, scal + 8), of
+  // which only the mu parts are written
+  C.mold = o; o += S.scal + 8 - S.s1;
   C.total = (o + 1) & ~(size_t)1;
   return C;
 }
@@ -273,6 +279,7 @@ struct KFrame {
   // per-node iteration state
   unsigned have_basis_bits;   // bit b: a full eigenvector basis of block b is stored
   unsigned lr_mode_bits;      // bit b: the block's minority side is tracked by the low-rank projection
+  int node_exact;             // the node looked infeasible under tracked projections: exact projections from then on
   unsigned lr_neg_bits;       // bit b: the NEGATIVE side of V is the tracked one
   unsigned lr_p_pack;         // byte b: columns of the tracked basis
   int exact_iter;             // this iteration runs exact (full) projections on every block
@@ -456,7 +463,7 @@ __device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
     if (warm >= 0 && !P.o.exact_projection) {   // the parent's tracked bases came with its record
       F.lr_mode_bits = (unsigned)c.scal[5]; F.lr_neg_bits = (unsigned)c.scal[6]; F.lr_p_pack = (unsigned)c.scal[7];
     }
-    F.exact_iter = 0; F.force_check = 0;
+    F.exact_iter = 0; F.force_check = 0; F.node_exact = 0;
     // Eigensolver tolerance follows the ADMM residual: off(S) <= jtol ||S||_F with jtol two orders below the
     // current relative residual, inside [1e-13, jacobi_tol].
     F.jtol = P.o.jacobi_tol;
@@ -748,7 +755,8 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
         const int N = g.N, NP = g.NP, ld = g.ld;
         const uint32_t qbytes = (uint32_t)((size_t)NP * ld * sizeof(double));
         const bool fits = (size_t)NP * ld <= bufsz;             // else: L2-resident working buffers
-        const bool use_lr = OMC_BIT(lr_mode_bits, b) && !exact_iter && !P.o.exact_projection;
+        const bool node_exact = F.node_exact != 0;
+        const bool use_lr = OMC_BIT(lr_mode_bits, b) && !exact_iter && !P.o.exact_projection && !node_exact;
         const bool warmQ = OMC_BIT(have_basis_bits, b) && !reortho && !exact_iter && !use_lr;
         double* B0 = fits ? buf0 : (scr + P.SC.big0);
         double* B1 = fits ? buf1 : OMC_QG(b);
@@ -890,7 +898,17 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
           // a cold solve (first iteration, re-orthogonalisation, tracker fallback) runs to the tight tolerance: the loose jtol is
           // only sound for warm solves, whose error is coherent from one iteration to the next (with cold solves every
           // projection carries an independent O(jtol) error and the residual stalls at ~100 jtol: seen on 6 x 6 blocks)
-          nsweeps += jacobi_sym(B0, B1, NP, ld, (exact_iter || !warm_now) ? fmin(jtol, 1e-10) : jtol, 40, jcs, jsn, jrot, red, 1, jskip, &ish[4],
+          double tol_here = (exact_iter || !warm_now) ? fmin(jtol, 1e-10) : jtol;
+          // nodes with cuts can be infeasible: their iterates diverge, ||V|| grows and a tolerance relative to ||V|| alone
+          // would freeze the warm basis (the step falls below it), spoiling d mu = mu_it - mu_(it-1) of the certificate.
+          // Resolve the step itself to 1e-4; a node already under suspicion runs at full accuracy.
+          if (node_exact) {
+            tol_here = 1e-13;
+          } else if (L > 0 && fits) {
+            const double vs_ = sqrt(block_sum(vsq, red)), ds_ = al * sqrt(block_sum(dsq, red));
+            tol_here = fmin(tol_here, fmax(1e-13, 1e-4 * ds_ / fmax(vs_, 1e-300)));
+          }
+          nsweeps += jacobi_sym(B0, B1, NP, ld, tol_here, 40, jcs, jsn, jrot, red, 1, jskip, &ish[4],
                                 P.prof ? (P.prof + (size_t)node * OMC_PROF_STRIDE + 8 + 3 * (b == 0 ? 0 : 1)) : nullptr);
           OMC_SETBIT(have_basis_bits, b, 1);
           OMC_TICK(3)
@@ -952,7 +970,7 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
           // switch to the low-rank projection when the minority side (plus guard band) fits the panel: the tracked
           // basis = the minority-side eigenvectors and the OMC_LR_BUF eigenvectors next to them across zero
           // (only when the Rayleigh-Ritz space [Z R~] of 2 p directions fits the block: small blocks stay on the full solver)
-          if (!P.o.exact_projection && ish[5] + OMC_LR_BUF <= PM && 2 * (ish[5] + OMC_LR_BUF) <= N) {
+          if (!P.o.exact_projection && !node_exact && ish[5] + OMC_LR_BUF <= PM && 2 * (ish[5] + OMC_LR_BUF) <= N) {
             const int side = ish[2], pz = ish[5] + OMC_LR_BUF;
             if (tid < 16) jrot[tid] = -1;
             __syncthreads();
@@ -1052,7 +1070,8 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
         tk = clock64();
         // a termination decision taken on tracked (low-rank) projections is only provisional: it is re-taken right
         // after one iteration with exact projections on every block (s in the cone and mu in its polar exactly)
-        const bool provisional = !exact_iter && lr_mode_bits != 0u && !P.o.exact_projection;
+        const bool node_exact = F.node_exact != 0;
+        const bool provisional = !exact_iter && lr_mode_bits != 0u && !P.o.exact_projection && !node_exact;
         exact_iter = false;
         force_check = false;
         double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0, sxx = 0.0, sfit = 0.0;
@@ -1216,6 +1235,118 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
           __syncthreads();
           return true;
         }
+        // ---- primal infeasibility certificate (oracle/relaxation.py, COSMO sec. 5.2): d = mu - mu_prev in the polar cone,
+        // A'd ~ 0 and support(d) - b'd < 0.  Only for nodes with cuts (the root is always feasible) whose blocks fit the
+        // shared-memory eigensolver; the eigenvalue test runs only when the cheap conditions hold.
+        if (L > 0 && (size_t)g1.NP * g1.ld <= bufsz) {
+          const double* mo = scr + P.SC.mold;
+          const size_t base = SL.s1;
+#define OMC_DM(off_) (__ldcg(st + (off_)) - __ldcg(mo + ((off_) - base)))
+          double* dvs = cw;   // [L*k] d of the v rows
+          double* dgs = gc;   // [L]   d of the aggregated rows
+          for (int e = tid; e < L * k; e += NT) dvs[e] = OMC_DM(SL.mv + e);
+          for (int l = tid; l < L; l += NT) dgs[l] = OMC_DM(SL.mg + l);
+          __syncthreads();
+          const double d4 = OMC_DM(SL.scal + 1);
+          double nrm = fabs(d4), atn = 0.0, sup = 0.0, bdy = 0.0, cmax = d4;
+          for (int e = tid; e < n * m; e += NT) {  // X
+            const int i = e % n, j = e / n;
+            const double d = OMC_DM(SL.m1 + (size_t)(n + j) * SL.N1 + i);
+            nrm = fmax(nrm, fabs(d));
+            atn = fmax(atn, 2.0 * fabs(d));
+          }
+          for (int e = tid; e < n * n; e += NT) {  // Y
+            const int i = e / n, j = e - i * n;
+            if (j > i) continue;
+            const double d1 = OMC_DM(SL.m1 + (size_t)i * SL.N1 + j), d2 = OMC_DM(SL.m2 + (size_t)i * SL.N2 + j), d3 = OMC_DM(SL.m3 + e);
+            double g = -d1 - d2 + d3 + ((i == j) ? d4 : 0.0);
+            for (int l = 0; l < L; ++l) g += dgs[l] * cxp[l][i] * cxp[l][j];
+            nrm = fmax(nrm, fmax(fabs(d1), fmax(fabs(d2), fabs(d3))));
+            atn = fmax(atn, fabs(g));
+            if (i == j) bdy += c.a * d3;
+          }
+          for (int e = tid; e < m * m; e += NT) {  // Theta
+            const int i = e / m, j = e - i * m;
+            if (j > i) continue;
+            const double d = OMC_DM(SL.m1 + (size_t)(n + i) * SL.N1 + (n + j));
+            nrm = fmax(nrm, fabs(d));
+            atn = fmax(atn, fabs(d));
+          }
+          for (int e = tid; e < n * k; e += NT) {  // U and the box rows
+            const int i = e % n, j = e / n;
+            const double d2 = OMC_DM(SL.m2 + (size_t)(n + j) * SL.N2 + i), d5 = OMC_DM(SL.m5 + e);
+            double g = -2.0 * d2 - d5;
+            for (int l = 0; l < L; ++l) g -= cxp[l][i] * (dvs[l * k + j] + dgs[l] * cal[l * k + j]);
+            nrm = fmax(nrm, fmax(fabs(d2), fabs(d5)));
+            atn = fmax(atn, fabs(g));
+            const double lo5 = (i >= n - k + j) ? 0.0 : -c.sa;
+            sup += (d5 > 0.0) ? c.sa * d5 : lo5 * d5;
+          }
+          for (int e = tid; e < k * k; e += NT) {  // identity corner of the second block
+            const int i = e / k, j = e - i * k;
+            if (j > i) continue;
+            const double d = OMC_DM(SL.m2 + (size_t)(n + i) * SL.N2 + (n + j));
+            nrm = fmax(nrm, fabs(d));
+            if (i == j) bdy += d;
+          }
+          for (int e = tid; e < L * k; e += NT) {
+            const double d = dvs[e];
+            nrm = fmax(nrm, fabs(d));
+            sup += (d > 0.0) ? cub[e] * d : clb[e] * d;
+          }
+          for (int l = tid; l < L; l += NT) {
+            const double d = dgs[l];
+            nrm = fmax(nrm, fabs(d));
+            bdy += cbe[l] * d;
+            cmax = fmax(cmax, d);
+          }
+          if (tid == 0) bdy += c.ktr * d4;
+          nrm = block_max(nrm, red);
+          atn = block_max(atn, red);
+          cmax = block_max(cmax, red);
+          sup = block_sum(sup, red);
+          bdy = block_sum(bdy, red);
+          // tracked projections (and warm eigensolves at the loose tolerance) leave an error floor of ~1e-5 on A'd: a node
+          // that LOOKS infeasible at a loose tolerance finishes on exact projections at full eigensolver accuracy, where the
+          // strict certificate can be met (same rule in the oracle)
+          if (!node_exact && nrm > 1e-14 && atn <= OMC_EPS_INF_LOOSE * nrm && cmax <= OMC_EPS_INF_LOOSE * nrm &&
+              sup - bdy < -OMC_EPS_INF_LOOSE * nrm) {
+            if (tid == 0) F.node_exact = 1;
+          }
+          const double tol = OMC_EPS_INF * nrm;
+          if (nrm > 1e-14 && atn <= tol && cmax <= tol && sup - bdy < -tol) {
+            bool cone_ok = true;
+            for (int b = 0; b < 3 && cone_ok; ++b) {  // lambda_max(d_b) <= tol
+              const Geo g = OMC_GB(b);
+              const size_t mb = (b == 0) ? SL.m1 : ((b == 1) ? SL.m2 : SL.m3);
+              __syncthreads();
+              for (int e = tid; e < g.NP * g.NP; e += NT) {
+                const int rr = e / g.NP, cc = e - rr * g.NP;
+                if (cc <= rr) {
+                  const double d = (rr < g.N) ? OMC_DM(mb + (size_t)rr * g.N + cc) : 0.0;
+                  buf0[(size_t)rr * g.ld + cc] = d;
+                  buf0[(size_t)cc * g.ld + rr] = d;
+                }
+                buf1[(size_t)rr * g.ld + cc] = (rr == cc) ? 1.0 : 0.0;
+              }
+              __syncthreads();
+              jacobi_sym(buf0, buf1, g.NP, g.ld, 1e-12, 40, jcs, jsn, jrot, red);
+              double lmax = -1e300;
+              for (int i = tid; i < g.N; i += NT) lmax = fmax(lmax, buf0[(size_t)i * g.ld + i]);
+              lmax = block_max(lmax, red);
+              if (lmax > tol) cone_ok = false;
+            }
+            if (cone_ok) {
+              if (tid == 0) {
+                F.status = OMC_STATUS_INFEASIBLE; F.res_p = res_p; F.res_d = res_d; F.obj_p = obj_p; F.obj_d = obj_d; F.lbound = lbound;
+                F.exact_iter = 0; F.force_check = 0;
+              }
+              __syncthreads();
+              return true;
+            }
+          }
+#undef OMC_DM
+        }
         {
           const double rel = fmax(rp / fmax(np_, 1.0), rd / fmax(nd_, 1.0));
           jtol = fmin(P.o.jacobi_tol, fmax(1e-13, 1e-2 * rel));
@@ -1235,6 +1366,22 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
   }
   __syncthreads();
   return false;
+}
+
+// mu of the previous iteration, kept for the infeasibility certificate of the next check (d mu = mu_it - mu_(it-1),
+// COSMO sec. 5.2 as restated in oracle/relaxation.py); called only at the top of an iteration that ends with a check.
+template <int NT, int KMAX, int PM>
+__device__ __noinline__ void relax_save_mu(const RelaxArgs& P, KFrame& F) {
+  OMC_FRAME_LOCALS
+  (void)c;
+  double* mo = scr + P.SC.mold;
+  const size_t base = SL.s1;
+  const size_t off[6] = {SL.m1, SL.m2, SL.m3, SL.m5, SL.mv, SL.mg};
+  const size_t len[6] = {(size_t)SL.N1 * SL.N1, (size_t)SL.N2 * SL.N2, (size_t)n * n, (size_t)n * k, (size_t)L * k, (size_t)L};
+  for (int q = 0; q < 6; ++q)
+    for (size_t e = tid; e < len[q]; e += NT) mo[off[q] - base + e] = __ldcg(st + off[q] + e);
+  if (tid == 0) mo[SL.scal + 1 - base] = st[SL.scal + 1];
+  __syncthreads();
 }
 
 template <int NT, int KMAX, int PM>
@@ -1388,6 +1535,7 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const __grid_consta
     for (int it = 1; it <= P.o.max_iter; ++it) {
       if (tid == 0) F.it = it;
       __syncthreads();
+      if (F.c.L > 0 && (it % P.o.check_every == 0 || it == P.o.max_iter || F.force_check)) relax_save_mu<NT, KMAX, PM>(P, F);
       relax_phase12<NT, KMAX, PM>(P, F);
       for (int b = 0; b < 3; ++b) relax_project_block<NT, KMAX, PM>(P, F, b);
       if (it % P.o.check_every == 0 || it == P.o.max_iter || F.force_check) {

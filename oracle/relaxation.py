@@ -55,7 +55,7 @@ def psd_project(V):
 class Options:
     def __init__(self, eps_abs=1e-7, eps_rel=1e-7, max_iter=20000, rho=0.3, sigma=1e-6,
                  alpha=1.6, check_every=25, adapt_every=100, adaptive_rho=True,
-                 eps_inf=1e-6, fix_linear3_right=False, scale=None, verbose=False, projection="exact", pm=16,
+                 eps_inf=1e-6, eps_inf_loose=1e-3, fix_linear3_right=False, scale=None, verbose=False, projection="exact", pm=16,
                  adapt_thresh=5.0):
         self.__dict__.update(locals()); del self.__dict__["self"]
 
@@ -189,6 +189,8 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
         from .lowrank import TrackedProjector
         trackers = [TrackedProjector(o.pm) for _ in range(3)]
     exact_iter = force_check = False
+    node_exact = False      # set when a tracked node looks infeasible: exact projections from then on
+    n_suspect = 0
     for it in range(1, o.max_iter + 1):
         # ---- w-update: (P + sigma I + rho A'A) w~ = sigma w - q + A'(rho (b - s) + mu)
         gX, gY, gT, gU = c.At(st.m1 - rho * st.s1, st.m2 + rho * (c.E2 - st.s2), st.m3 + rho * (c.I3 - st.s3),
@@ -219,7 +221,7 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
         if trackers is None:
             st.s1 = psd_project(v1); st.s2 = psd_project(v2); st.s3 = psd_project(v3)
         else:
-            st.s1, st.s2, st.s3 = (tr.project(v, exact=exact_iter) for tr, v in zip(trackers, (v1, v2, v3)))
+            st.s1, st.s2, st.s3 = (tr.project(v, exact=exact_iter or node_exact) for tr, v in zip(trackers, (v1, v2, v3)))
         st.s4 = max(v4, 0.0)
         st.s5 = np.clip(v5, c.lo, c.hi)
         st.sv = np.clip(vv, c.lb, c.ub); st.sg = np.maximum(vg, 0.0)
@@ -228,7 +230,7 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
         st.mv = rho * (vv - st.sv); st.mg = rho * (vg - st.sg)
 
         if it % o.check_every == 0 or it == o.max_iter or force_check:
-            provisional = trackers is not None and not exact_iter
+            provisional = trackers is not None and not exact_iter and not node_exact
             exact_iter = force_check = False
             w = c.S(st.X, st.Y, st.T, st.U)                                       # b - A w
             sblk = (st.s1, st.s2, st.s3, np.array([st.s4]), st.s5, st.sv, st.sg)
@@ -257,11 +259,17 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
                 if nrm > 1e-14:
                     gX, gY, gT, gU = c.At(d[0], d[1], d[2], float(d[3]), d[4], d[5], d[6])
                     atn = max(np.abs(gX).max(), np.abs(gY).max(), np.abs(gT).max(), np.abs(gU).max())
+                    sup = (np.sum(np.where(d[4] > 0, c.hi * d[4], c.lo * d[4]))
+                           + np.sum(np.where(d[5] > 0, c.ub * d[5], c.lb * d[5])))
+                    bdy = (np.trace(d[1][n:, n:]) + c.a * np.trace(d[2]) + c.ktr * float(d[3])
+                           + float(c.beta @ d[6]))
+                    # tracked projections leave an error floor of ~1e-5 on A'dmu: a node that LOOKS infeasible at a
+                    # loose tolerance finishes on exact projections, where the strict certificate can be met
+                    if (trackers is not None and not node_exact and atn <= o.eps_inf_loose * nrm
+                            and max(float(d[3]), d[6].max()) <= o.eps_inf_loose * nrm and sup - bdy < -o.eps_inf_loose * nrm):
+                        node_exact = True
+                        n_suspect += 1
                     if atn <= o.eps_inf * nrm:
-                        sup = (np.sum(np.where(d[4] > 0, c.hi * d[4], c.lo * d[4]))
-                               + np.sum(np.where(d[5] > 0, c.ub * d[5], c.lb * d[5])))
-                        bdy = (np.trace(d[1][n:, n:]) + c.a * np.trace(d[2]) + c.ktr * float(d[3])
-                               + float(c.beta @ d[6]))
                         cone_ok = (np.linalg.eigvalsh(d[0]).max() <= o.eps_inf * nrm
                                    and np.linalg.eigvalsh(d[1]).max() <= o.eps_inf * nrm
                                    and np.linalg.eigvalsh(d[2]).max() <= o.eps_inf * nrm
@@ -284,7 +292,8 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
             - float(np.sum(np.where(st.mv < 0, st.mv * c.lb, st.mv * c.ub))))
     return dict(status=status, feasible=status != STATUS_INFEASIBLE, objective=obj, dual_objective=dual,
                 X=X, Y=Y, Theta=T, U=U, iters=it, res_p=res_p, res_d=res_d, state=st, rho=rho, consts=c,
-                projections=None if trackers is None else (sum(t.n_lr for t in trackers), sum(t.n_full for t in trackers)))
+                projections=None if trackers is None else (sum(t.n_lr for t in trackers), sum(t.n_full for t in trackers)),
+                suspect=n_suspect)
 
 
 def certificate(res, A, mask, gamma, k):

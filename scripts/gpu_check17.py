@@ -64,7 +64,7 @@ for (n, m, k), ct, L in itertools.product([(4, 4, 1), (6, 9, 2), (8, 8, 3), (10,
     print("A", ("OK " if ok else "BAD") + ("" if ref_ok else " (oracle not optimal)"), *line, flush=True)
 print("A done %.1fs" % (time.time() - t0), flush=True)
 
-if not CPU:
+if not CPU and "--only-a" not in sys.argv:
     # ---- B: warm vs cold
     for (n, m, k) in [(3, 3, 1), (4, 6, 2), (6, 6, 1), (8, 12, 2), (12, 12, 3)]:
         A, mask = generate_matrix_completion_data(k, n, m, max(n + m, int(0.6 * n * m)), 7)

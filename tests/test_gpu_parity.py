@@ -550,3 +550,29 @@ def test_cut_chains_of_every_type_and_rank_against_the_oracle(omc):
         p.close()
         checked += 1
     assert checked >= 15
+
+
+def test_infeasible_node_is_certified_like_the_oracle(omc):
+    """A 10-cut linear3 chain that the reference's `right` quirk (OMC.jl:1675, Q1) makes infeasible: the kernel's
+    certificate (d mu in the polar cone, A'd mu ~ 0, support < 0; oracle/relaxation.py) stops the node as INFEASIBLE
+    (-> feasible = false, OMC.jl:1921-1935) within 10 % of the oracle's iteration count on the exact path and near it on the
+    tracked path; with `fix_linear3_right` the same chain is feasible again."""
+    from oracle import relaxation as R
+    from oracle.datagen import generate_matrix_completion_data
+    n, m, k, ct, L = 6, 9, 2, "linear3", 10
+    rng = np.random.default_rng(100 * n + 10 * k + L)
+    A, mask = generate_matrix_completion_data(k, n, m, max(n + m, int(0.6 * n * m)), 5)
+    cuts = _feasible_chain(ct, n, k, L, rng)
+    ro = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000))
+    assert ro["status"] == R.STATUS_INFEASIBLE and not ro["feasible"]
+    p = omc.Problem(k, A, mask, 20.0, ct)
+    gc = [omc.Cut(p.add_cut(x, Uh), x, Uh, d) for x, Uh, d in cuts]
+    ex = p.relax_batch([gc], omc.default_opts(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000, exact_projection=1))[0]
+    tr = p.relax_batch([gc], omc.default_opts(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000))[0]
+    assert ex["termination_status"] == "INFEASIBLE" and not ex["feasible"] and abs(ex["iters"] - ro["iters"]) <= 0.1 * ro["iters"]
+    assert tr["termination_status"] == "INFEASIBLE" and not tr["feasible"] and tr["iters"] <= 2 * ro["iters"]
+    fixed = p.relax_batch([gc], omc.default_opts(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000, fix_linear3_right=1))[0]
+    rf = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000, fix_linear3_right=True))
+    assert rf["status"] == R.STATUS_OPTIMAL and fixed["termination_status"] == "OPTIMAL"
+    assert abs(fixed["objective"] - rf["objective"]) <= REL_BOUND * rf["objective"]
+    p.close()
