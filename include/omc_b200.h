@@ -77,6 +77,12 @@ int32_t omc_init(int32_t device);
 int32_t omc_shutdown(void);
 const char* omc_last_error(void);
 int32_t omc_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* free_bytes);
+/* compile-time options of this build; callable before omc_init().  Bit 0: the relaxation kernel tests nodes with cuts
+ * for a primal infeasibility certificate and can return OMC_STATUS_INFEASIBLE (make EXTRA=-DOMC_INFEASIBILITY_CERTIFICATE;
+ * off by default: it costs ~10 % of the kernel, and inside branch-and-bound infeasible children already end through
+ * `cutoff`).  The reference has no counterpart (Mosek reports MOI.INFEASIBLE by itself, OMC.jl:1921-1935). */
+#define OMC_BUILD_INFEASIBILITY_CERTIFICATE 1
+int32_t omc_build_flags(void);
 /* stream the library launches on (a cudaStream_t), so a host can bracket launches with its own events */
 void* omc_stream(void);
 

@@ -4,7 +4,7 @@ Import as ``import omc_b200`` (the repo-root shim registers this directory, whos
 ``optimalmatrixcompletion.jl_b200`` is not a valid Python identifier, under that name).
 """
 from . import _lib  # noqa: F401
-from .engine import (Problem, Frontier, Cut, default_opts, init, bitmatrix_chunks,  # noqa: F401
+from .engine import (Problem, Frontier, Cut, default_opts, init, build_flags, bitmatrix_chunks,  # noqa: F401
                      matrix_completion_SDP_relaxation, evaluate_objective, compute_MSE,
                      matrix_completion_master_feasible, smallest_eigvecs_batch, psd_project_batch,
                      measure_fp64_peak, alternating_minimization, alternating_minimization_batch, shor_constraint_indexes, LABELS, MOI_STATUS)

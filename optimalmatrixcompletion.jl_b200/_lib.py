@@ -36,6 +36,7 @@ SIGNATURES = {
     "omc_shutdown": (_i32, []),
     "omc_last_error": (C.c_char_p, []),
     "omc_device_info": (_i32, [_pi32, _pi32, _pi32, _p(C.c_int64)]),
+    "omc_build_flags": (_i32, []),
     "omc_stream": (_vp, []),
     "omc_problem_create": (_i32, [_i32, _i32, _i32, _pf64, _pu64, _f64, _i32, _i32, _p(_vp)]),
     "omc_problem_destroy": (_i32, [_vp]),

@@ -364,6 +364,14 @@ int32_t omc_shutdown(void) {
 
 void* omc_stream(void) { return (void*)g_stream; }
 
+int32_t omc_build_flags(void) {
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
+  return OMC_BUILD_INFEASIBILITY_CERTIFICATE;
+#else
+  return 0;
+#endif
+}
+
 int32_t omc_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* free_bytes) {
   NEED_INIT();
   cudaDeviceProp prop;

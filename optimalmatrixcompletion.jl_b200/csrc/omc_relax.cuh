@@ -72,7 +72,11 @@ __host__ __device__ inline Geo smem_geo(int N1, int N2, int N3) {
 }
 
 struct ScratchLayout {
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
   size_t wt, Q1, Q2, Q3, Z1, Z2, Z3, G, Minv, state, big0, mold, total;
+#else
+  size_t wt, Q1, Q2, Q3, Z1, Z2, Z3, G, Minv, state, big0, total;
+#endif
 };
 __host__ __device__ inline ScratchLayout make_scratch_layout(const StateLayout& S, int rmax) {
   ScratchLayout C;
@@ -92,10 +96,12 @@ __host__ __device__ inline ScratchLayout make_scratch_layout(const StateLayout& 
   o = (o + 1) & ~(size_t)1;
   C.big0 = o;
   if (g1.NP > OMC_SMEM_NP_MAX) o += (size_t)g1.NP * g1.ld;   // working matrix of a block too large for shared memory
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
   o = (o + 1) & ~(size_t)1;
   // multipliers of the previous iteration (infeasibility certificate): image of the record's span [s1, scal + 8), of
   // which only the mu parts are written
   C.mold = o; o += S.scal + 8 - S.s1;
+#endif
   C.total = (o + 1) & ~(size_t)1;
   return C;
 }
@@ -279,7 +285,9 @@ struct KFrame {
   // per-node iteration state
   unsigned have_basis_bits;   // bit b: a full eigenvector basis of block b is stored
   unsigned lr_mode_bits;      // bit b: the block's minority side is tracked by the low-rank projection
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
   int node_exact;             // the node looked infeasible under tracked projections: exact projections from then on
+#endif
   unsigned lr_neg_bits;       // bit b: the NEGATIVE side of V is the tracked one
   unsigned lr_p_pack;         // byte b: columns of the tracked basis
   int exact_iter;             // this iteration runs exact (full) projections on every block
@@ -463,7 +471,10 @@ __device__ __noinline__ void relax_node_setup(const RelaxArgs& P, KFrame& F) {
     if (warm >= 0 && !P.o.exact_projection) {   // the parent's tracked bases came with its record
       F.lr_mode_bits = (unsigned)c.scal[5]; F.lr_neg_bits = (unsigned)c.scal[6]; F.lr_p_pack = (unsigned)c.scal[7];
     }
-    F.exact_iter = 0; F.force_check = 0; F.node_exact = 0;
+    F.exact_iter = 0; F.force_check = 0;
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
+    F.node_exact = 0;
+#endif
     // Eigensolver tolerance follows the ADMM residual: off(S) <= jtol ||S||_F with jtol two orders below the
     // current relative residual, inside [1e-13, jacobi_tol].
     F.jtol = P.o.jacobi_tol;
@@ -755,8 +766,12 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
         const int N = g.N, NP = g.NP, ld = g.ld;
         const uint32_t qbytes = (uint32_t)((size_t)NP * ld * sizeof(double));
         const bool fits = (size_t)NP * ld <= bufsz;             // else: L2-resident working buffers
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
         const bool node_exact = F.node_exact != 0;
         const bool use_lr = OMC_BIT(lr_mode_bits, b) && !exact_iter && !P.o.exact_projection && !node_exact;
+#else
+        const bool use_lr = OMC_BIT(lr_mode_bits, b) && !exact_iter && !P.o.exact_projection;
+#endif
         const bool warmQ = OMC_BIT(have_basis_bits, b) && !reortho && !exact_iter && !use_lr;
         double* B0 = fits ? buf0 : (scr + P.SC.big0);
         double* B1 = fits ? buf1 : OMC_QG(b);
@@ -898,6 +913,7 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
           // a cold solve (first iteration, re-orthogonalisation, tracker fallback) runs to the tight tolerance: the loose jtol is
           // only sound for warm solves, whose error is coherent from one iteration to the next (with cold solves every
           // projection carries an independent O(jtol) error and the residual stalls at ~100 jtol: seen on 6 x 6 blocks)
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
           double tol_here = (exact_iter || !warm_now) ? fmin(jtol, 1e-10) : jtol;
           // nodes with cuts can be infeasible: their iterates diverge, ||V|| grows and a tolerance relative to ||V|| alone
           // would freeze the warm basis (the step falls below it), spoiling d mu = mu_it - mu_(it-1) of the certificate.
@@ -908,6 +924,9 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
             const double vs_ = sqrt(block_sum(vsq, red)), ds_ = al * sqrt(block_sum(dsq, red));
             tol_here = fmin(tol_here, fmax(1e-13, 1e-4 * ds_ / fmax(vs_, 1e-300)));
           }
+#else
+          const double tol_here = (exact_iter || !warm_now) ? fmin(jtol, 1e-10) : jtol;
+#endif
           nsweeps += jacobi_sym(B0, B1, NP, ld, tol_here, 40, jcs, jsn, jrot, red, 1, jskip, &ish[4],
                                 P.prof ? (P.prof + (size_t)node * OMC_PROF_STRIDE + 8 + 3 * (b == 0 ? 0 : 1)) : nullptr);
           OMC_SETBIT(have_basis_bits, b, 1);
@@ -970,7 +989,11 @@ __device__ __noinline__ void relax_project_block(const RelaxArgs& P, KFrame& F, 
           // switch to the low-rank projection when the minority side (plus guard band) fits the panel: the tracked
           // basis = the minority-side eigenvectors and the OMC_LR_BUF eigenvectors next to them across zero
           // (only when the Rayleigh-Ritz space [Z R~] of 2 p directions fits the block: small blocks stay on the full solver)
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
           if (!P.o.exact_projection && !node_exact && ish[5] + OMC_LR_BUF <= PM && 2 * (ish[5] + OMC_LR_BUF) <= N) {
+#else
+          if (!P.o.exact_projection && ish[5] + OMC_LR_BUF <= PM && 2 * (ish[5] + OMC_LR_BUF) <= N) {
+#endif
             const int side = ish[2], pz = ish[5] + OMC_LR_BUF;
             if (tid < 16) jrot[tid] = -1;
             __syncthreads();
@@ -1070,8 +1093,12 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
         tk = clock64();
         // a termination decision taken on tracked (low-rank) projections is only provisional: it is re-taken right
         // after one iteration with exact projections on every block (s in the cone and mu in its polar exactly)
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
         const bool node_exact = F.node_exact != 0;
         const bool provisional = !exact_iter && lr_mode_bits != 0u && !P.o.exact_projection && !node_exact;
+#else
+        const bool provisional = !exact_iter && lr_mode_bits != 0u && !P.o.exact_projection;
+#endif
         exact_iter = false;
         force_check = false;
         double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0, sxx = 0.0, sfit = 0.0;
@@ -1235,6 +1262,7 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
           __syncthreads();
           return true;
         }
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
         // ---- primal infeasibility certificate (oracle/relaxation.py, COSMO sec. 5.2): d = mu - mu_prev in the polar cone,
         // A'd ~ 0 and support(d) - b'd < 0.  Only for nodes with cuts (the root is always feasible) whose blocks fit the
         // shared-memory eigensolver; the eigenvalue test runs only when the cheap conditions hold.
@@ -1347,6 +1375,7 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
           }
 #undef OMC_DM
         }
+#endif
         {
           const double rel = fmax(rp / fmax(np_, 1.0), rd / fmax(nd_, 1.0));
           jtol = fmin(P.o.jacobi_tol, fmax(1e-13, 1e-2 * rel));
@@ -1368,6 +1397,7 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
   return false;
 }
 
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
 // mu of the previous iteration, kept for the infeasibility certificate of the next check (d mu = mu_it - mu_(it-1),
 // COSMO sec. 5.2 as restated in oracle/relaxation.py); called only at the top of an iteration that ends with a check.
 template <int NT, int KMAX, int PM>
@@ -1383,6 +1413,7 @@ __device__ __noinline__ void relax_save_mu(const RelaxArgs& P, KFrame& F) {
   if (tid == 0) mo[SL.scal + 1 - base] = st[SL.scal + 1];
   __syncthreads();
 }
+#endif
 
 template <int NT, int KMAX, int PM>
 __device__ __noinline__ void relax_node_output(const RelaxArgs& P, KFrame& F) {
@@ -1535,7 +1566,9 @@ __global__ void __launch_bounds__(NT, MINB) omc_relax_kernel(const __grid_consta
     for (int it = 1; it <= P.o.max_iter; ++it) {
       if (tid == 0) F.it = it;
       __syncthreads();
+#ifdef OMC_INFEASIBILITY_CERTIFICATE
       if (F.c.L > 0 && (it % P.o.check_every == 0 || it == P.o.max_iter || F.force_check)) relax_save_mu<NT, KMAX, PM>(P, F);
+#endif
       relax_phase12<NT, KMAX, PM>(P, F);
       for (int b = 0; b < 3; ++b) relax_project_block<NT, KMAX, PM>(P, F, b);
       if (it % P.o.check_every == 0 || it == P.o.max_iter || F.force_check) {

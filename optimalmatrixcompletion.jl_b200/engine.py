@@ -38,6 +38,11 @@ def init(device: Optional[int] = None):
     return lib
 
 
+def build_flags() -> int:
+    """omc_build_flags: bit 0 = the kernel was built with the primal infeasibility certificate."""
+    return int(_lib.load().omc_build_flags())
+
+
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
