@@ -4,7 +4,7 @@ vectors and size-independent properties.  Bit-exact for integer work; 1e-6 relat
 import numpy as np
 import pytest
 
-from conftest import golden_instance
+from conftest import golden_instance, feasible_chain as _feasible_chain
 
 pytestmark = pytest.mark.gpu
 REL_BOUND = 1e-6
@@ -501,29 +501,6 @@ def test_tracked_equals_exact_projection_over_a_sweep_of_small_shapes(omc):
         assert abs(rt["objective"] - re_["objective"]) <= REL_BOUND * abs(re_["objective"]), (n, m, k, rt["objective"], re_["objective"])
         assert rt["iters"] <= 1.5 * re_["iters"] + 50, (n, m, k, rt["iters"], re_["iters"])
         p.close()
-
-
-def _cut_region(ct, v, h):
-    a = abs(h)
-    if ct == "linear":
-        return "left" if v <= h else "right"
-    if ct == "linear2":
-        return "left" if v <= -a else ("middle" if v <= a else "right")
-    return "left" if v <= -a else ("inner_left" if v <= 0 else ("inner_right" if v <= a else "right"))
-
-
-def _feasible_chain(ct, n, k, L, rng):
-    """L cuts whose regions all contain one hidden rank-k factor (orthonormal columns, bottom k x k block a positive
-    diagonal so that the sign normalisation OMC.jl:1442-1449 holds)."""
-    W, _ = np.linalg.qr(rng.standard_normal((n - k, k)))
-    th = rng.uniform(0.3, 1.2, size=k)
-    Us = np.vstack([W * np.cos(th), np.diag(np.sin(th))])
-    out = []
-    for _ in range(L):
-        x = rng.standard_normal(n); x /= np.linalg.norm(x)
-        Uh = rng.uniform(-0.4, 0.4, size=(1, k)) * x[:, None]
-        out.append((x, Uh, [_cut_region(ct, float(x @ Us[:, j]), float(Uh[:, j] @ x)) for j in range(k)]))
-    return out
 
 
 def test_cut_chains_of_every_type_and_rank_against_the_oracle(omc):

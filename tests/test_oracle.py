@@ -5,7 +5,7 @@ import itertools
 import numpy as np
 import pytest
 
-from conftest import golden_instance
+from conftest import golden_instance, feasible_chain
 from oracle import cuts as C
 from oracle import eigsep as E
 from oracle import kat
@@ -302,3 +302,21 @@ def test_package_generator_equals_oracle_generator():
         A1, m1 = PS.generate_matrix_completion_data(*args)
         A2, m2 = OD.generate_matrix_completion_data(*args)
         assert np.array_equal(A1, A2) and np.array_equal(m1, m2)
+
+
+def test_oracle_certifies_an_infeasible_chain_in_exact_and_tracked_mode():
+    """A 10-cut linear3 chain that the reference's `right` quirk (OMC.jl:1675, Q1) makes infeasible: the primal
+    infeasibility certificate (d mu in the polar cone, A'd mu ~ 0, support < 0) stops it as INFEASIBLE (-> feasible =
+    false, OMC.jl:1921-1935); the tracked mode switches the suspect node to exact projections and stops at the same
+    check; with the valid secant (`fix_linear3_right`) the same chain is feasible."""
+    n, m, k, ct, L = 6, 9, 2, "linear3", 10
+    rng = np.random.default_rng(100 * n + 10 * k + L)
+    A, mask = generate_matrix_completion_data(k, n, m, max(n + m, int(0.6 * n * m)), 5)
+    cuts = feasible_chain(ct, n, k, L, rng)
+    o = dict(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000)
+    ex = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(**o))
+    tr = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(projection="tracked", **o))
+    assert ex["status"] == tr["status"] == R.STATUS_INFEASIBLE and not ex["feasible"] and not tr["feasible"]
+    assert tr["suspect"] == 1 and abs(tr["iters"] - ex["iters"]) <= 0.1 * ex["iters"]
+    ok = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(fix_linear3_right=True, **o))
+    assert ok["status"] == R.STATUS_OPTIMAL and ok["feasible"]
