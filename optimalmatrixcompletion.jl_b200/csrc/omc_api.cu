@@ -365,11 +365,14 @@ int32_t omc_shutdown(void) {
 void* omc_stream(void) { return (void*)g_stream; }
 
 int32_t omc_build_flags(void) {
+  int32_t f = 0;
 #ifdef OMC_INFEASIBILITY_CERTIFICATE
-  return OMC_BUILD_INFEASIBILITY_CERTIFICATE;
-#else
-  return 0;
+  f |= OMC_BUILD_INFEASIBILITY_CERTIFICATE;
 #endif
+#ifdef OMC_INFEASIBLE_BY_BOUND
+  f |= OMC_BUILD_INFEASIBLE_BY_BOUND;
+#endif
+  return f;
 }
 
 int32_t omc_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* free_bytes) {

@@ -1223,6 +1223,18 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
                             (double)n * k * c.sa;
           lbound = obj_d - rd * w1;
         }
+#ifdef OMC_INFEASIBLE_BY_BOUND
+        // Infeasibility by bound (validated in the oracle, Options.infeasible_by_bound; NOT yet run on the GPU, hence behind
+        // a switch): a feasible node has p* <= c0 = 1/2 ||P_Omega(A)||^2 (X = 0, Theta = 0 with any feasible (Y, U)), so
+        // ||w*||_1 <= w1(c0) and a certified bound above c0 contradicts feasibility.  No extra pass; on the infeasible chain
+        // of the tests it fires at iteration 400 where the d mu certificate needs 5 450.
+        double lbound_c0;
+        {
+          const double trTb = P.c0 / c.cT;
+          const double w1 = (double)n * c.ktr + sqrt((double)n * m * c.ktr * trTb) + (double)m * trTb + (double)n * k * c.sa;
+          lbound_c0 = obj_d - rd * w1;
+        }
+#endif
         bool stop = false;
         if (!(fabs(obj_p) < 1e300 && fabs(obj_d) < 1e300 && rp < 1e300 && rd < 1e300)) {  // NaN / overflow (fmax drops NaN)
           status = OMC_STATUS_NUMERICAL;
@@ -1243,6 +1255,16 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
             status = OMC_STATUS_CUTOFF;
             stop = true;
           }
+#ifdef OMC_INFEASIBLE_BY_BOUND
+        } else if (L > 0 && lbound_c0 > P.c0 * (1.0 + 1e-9) + 1e-12) {
+          if (provisional && it < P.o.max_iter) {
+            exact_iter = true;
+            force_check = true;
+          } else {
+            status = OMC_STATUS_INFEASIBLE;
+            stop = true;
+          }
+#endif
         } else if (P.o.time_limit_s > 0.0 &&
                    (double)(globaltimer_ns() - t_start) * 1e-9 > P.o.time_limit_s) {
           if (tid == 0) ish[3] = 1;

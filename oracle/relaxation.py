@@ -55,7 +55,7 @@ def psd_project(V):
 class Options:
     def __init__(self, eps_abs=1e-7, eps_rel=1e-7, max_iter=20000, rho=0.3, sigma=1e-6,
                  alpha=1.6, check_every=25, adapt_every=100, adaptive_rho=True,
-                 eps_inf=1e-6, eps_inf_loose=1e-3, fix_linear3_right=False, scale=None, verbose=False, projection="exact", pm=16,
+                 eps_inf=1e-6, eps_inf_loose=1e-3, infeasible_by_bound=False, fix_linear3_right=False, scale=None, verbose=False, projection="exact", pm=16,
                  adapt_thresh=5.0):
         self.__dict__.update(locals()); del self.__dict__["self"]
 
@@ -191,6 +191,7 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
     exact_iter = force_check = False
     node_exact = False      # set when a tracked node looks infeasible: exact projections from then on
     n_suspect = 0
+    bound_max = -np.inf     # largest certified bound seen at a check (infeasible_by_bound diagnostics)
     for it in range(1, o.max_iter + 1):
         # ---- w-update: (P + sigma I + rho A'A) w~ = sigma w - q + A'(rho (b - s) + mu)
         gX, gY, gT, gU = c.At(st.m1 - rho * st.s1, st.m2 + rho * (c.E2 - st.s2), st.m3 + rho * (c.I3 - st.s3),
@@ -251,6 +252,24 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
                     continue
                 status = STATUS_OPTIMAL
                 break
+            # ---- infeasibility by bound (optional; kernel: -DOMC_INFEASIBLE_BY_BOUND): a feasible node has
+            # p* <= c0 = 1/2 ||P_Omega(A)||^2 (X = 0, Theta = 0 with any feasible (Y, U)), hence ||w*||_1 <= w1(c0); a
+            # certified lower bound  dual - ||r_d||_inf w1(c0)  above c0 contradicts feasibility.  mu must be in the dual
+            # cone: under tracked projections the decision is re-taken after one exact iteration, like OPTIMAL.
+            if o.infeasible_by_bound and L > 0:
+                dual_ = (-0.5 * float(np.sum(Mk * st.X * st.X)) + c.c0
+                         + np.trace(st.m2[n:, n:]) + c.a * np.trace(st.m3) + c.ktr * st.m4 + float(c.beta @ st.mg)
+                         - float(np.sum(np.where(st.m5 < 0, st.m5 * c.lo, st.m5 * c.hi)))
+                         - float(np.sum(np.where(st.mv < 0, st.mv * c.lb, st.mv * c.ub))))
+                trTb = c.c0 / c.cT
+                w1 = n * c.ktr + np.sqrt(n * m * c.ktr * trTb) + m * trTb + n * c.k * c.sa
+                bound_max = max(bound_max, dual_ - rd * w1)
+                if dual_ - rd * w1 > c.c0 * (1.0 + 1e-9) + 1e-12:
+                    if provisional and it < o.max_iter:
+                        exact_iter = force_check = True
+                        continue
+                    status = STATUS_INFEASIBLE
+                    break
             # ---- primal infeasibility (COSMO sec. 5.2): dmu in the polar cone, A'dmu ~ 0, support - b'dmu < 0
             if L > 0:
                 d = [np.asarray(a_) - np.asarray(b_) for a_, b_ in
@@ -293,7 +312,7 @@ def solve_relaxation(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, state
     return dict(status=status, feasible=status != STATUS_INFEASIBLE, objective=obj, dual_objective=dual,
                 X=X, Y=Y, Theta=T, U=U, iters=it, res_p=res_p, res_d=res_d, state=st, rho=rho, consts=c,
                 projections=None if trackers is None else (sum(t.n_lr for t in trackers), sum(t.n_full for t in trackers)),
-                suspect=n_suspect)
+                suspect=n_suspect, bound_max=bound_max, c0=c.c0)
 
 
 def certificate(res, A, mask, gamma, k):

@@ -320,3 +320,24 @@ def test_oracle_certifies_an_infeasible_chain_in_exact_and_tracked_mode():
     assert tr["suspect"] == 1 and abs(tr["iters"] - ex["iters"]) <= 0.1 * ex["iters"]
     ok = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(fix_linear3_right=True, **o))
     assert ok["status"] == R.STATUS_OPTIMAL and ok["feasible"]
+
+
+def test_oracle_infeasibility_by_bound_fires_early_and_never_on_feasible_nodes():
+    """Options.infeasible_by_bound (kernel: -DOMC_INFEASIBLE_BY_BOUND, round-2 candidate): a feasible node has
+    p* <= c0 = 1/2 ||P_Omega(A)||^2, so a certified lower bound above c0 proves infeasibility.  On the infeasible
+    linear3 chain it fires at iteration 400 (d mu certificate: 5450); on feasible chains it never fires, the largest
+    certified bound stays below the optimum and the iteration count is unchanged."""
+    o = dict(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000, infeasible_by_bound=True)
+    n, m, k, ct, L = 6, 9, 2, "linear3", 10
+    A, mask = generate_matrix_completion_data(k, n, m, max(n + m, int(0.6 * n * m)), 5)
+    cuts = feasible_chain(ct, n, k, L, np.random.default_rng(100 * n + 10 * k + L))
+    for proj in ("exact", "tracked"):
+        r = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(projection=proj, **o))
+        assert r["status"] == R.STATUS_INFEASIBLE and r["iters"] <= 500 and r["bound_max"] > r["c0"]
+    for (n, m, k), ct, L in [((6, 9, 2), "linear2", 10), ((8, 8, 3), "linear", 10), ((4, 4, 1), "linear3", 3)]:
+        A, mask = generate_matrix_completion_data(k, n, m, max(n + m, int(0.6 * n * m)), 5)
+        cuts = feasible_chain(ct, n, k, L, np.random.default_rng(100 * n + 10 * k + L))
+        r0 = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000))
+        r1 = R.solve_relaxation(A, mask, 20.0, k, ct, cuts, opts=R.Options(**o))
+        assert r0["status"] == r1["status"] == R.STATUS_OPTIMAL and r0["iters"] == r1["iters"]
+        assert r1["bound_max"] <= r0["objective"] * (1 + 1e-6) + 1e-9 <= r1["c0"] * (1 + 1e-6) + 1e-9
