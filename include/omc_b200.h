@@ -82,7 +82,7 @@ int32_t omc_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
  * off by default: it costs ~10 % of the kernel, and inside branch-and-bound infeasible children already end through
  * `cutoff`).  The reference has no counterpart (Mosek reports MOI.INFEASIBLE by itself, OMC.jl:1921-1935). */
 #define OMC_BUILD_INFEASIBILITY_CERTIFICATE 1
-#define OMC_BUILD_INFEASIBLE_BY_BOUND 2       /* -DOMC_INFEASIBLE_BY_BOUND: INFEASIBLE when the certified bound exceeds 1/2 ||P(A)||^2 (round-2 candidate) */
+#define OMC_BUILD_INFEASIBLE_BY_BOUND 2       /* default build: INFEASIBLE when the certified bound exceeds 1/2 ||P(A)||^2; -DOMC_NO_INFEASIBLE_BY_BOUND removes it */
 int32_t omc_build_flags(void);
 /* stream the library launches on (a cudaStream_t), so a host can bracket launches with its own events */
 void* omc_stream(void);

@@ -11,6 +11,13 @@
 #include "omc_lowrank.cuh"
 #include "../../include/omc_b200.h"
 
+// Infeasibility by bound is part of the default build since round 2: a node whose certified lower bound
+// exceeds 1/2 ||P_Omega(A)||^2 cannot be feasible and is returned as OMC_STATUS_INFEASIBLE (OMC.jl:1921-1935).  It adds no
+// pass to the kernel (one more scalar bound at each residual check); -DOMC_NO_INFEASIBLE_BY_BOUND removes it.
+#if !defined(OMC_NO_INFEASIBLE_BY_BOUND) && !defined(OMC_INFEASIBLE_BY_BOUND)
+#define OMC_INFEASIBLE_BY_BOUND 1
+#endif
+
 namespace omc {
 
 // Layout (in doubles) of one ADMM state record: w = (X, Y, T, U), (s_b, mu_b) for the three PSD
@@ -1224,8 +1231,7 @@ __device__ __noinline__ bool relax_phase4(const RelaxArgs& P, KFrame& F) {
           lbound = obj_d - rd * w1;
         }
 #ifdef OMC_INFEASIBLE_BY_BOUND
-        // Infeasibility by bound (validated in the oracle, Options.infeasible_by_bound; NOT yet run on the GPU, hence behind
-        // a switch): a feasible node has p* <= c0 = 1/2 ||P_Omega(A)||^2 (X = 0, Theta = 0 with any feasible (Y, U)), so
+        // Infeasibility by bound (validated in the oracle, Options.infeasible_by_bound): a feasible node has p* <= c0 = 1/2 ||P_Omega(A)||^2 (X = 0, Theta = 0 with any feasible (Y, U)), so
         // ||w*||_1 <= w1(c0) and a certified bound above c0 contradicts feasibility.  No extra pass; on the infeasible chain
         // of the tests it fires at iteration 400 where the d mu certificate needs 5 450.
         double lbound_c0;

@@ -234,12 +234,16 @@ def prune_dominated_nodes(tree: BBTree):
             break
         new_lb.enqueue(nid, lb)
     tree.lower_bounds = new_lb
+    dropped = []
     for nid in removed:
-        tree.nodes.pop(nid, None)
+        nd = tree.nodes.pop(nid, None)
+        if nd is not None:
+            dropped.append(nd)
     if removed:
         rs = set(removed)
         tree.node_ids = [i for i in tree.node_ids if i not in rs]
     tree.nodes_remaining = len(tree.nodes)
+    return dropped
 
 
 def compute_gap(lower: float, upper: float) -> float:
@@ -258,7 +262,7 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
                                      altmin_root_n_iters: int = 1, use_max_steps: bool = False, max_steps: int = 1000000,
                                      time_limit: int = 3600, update_step: int = 1000, verbosity: int = 0,
                                      # engine knobs (defaults leave the reference's behaviour unchanged)
-                                     frontier_batch: int = 1, relax_opts=None, use_cutoff: bool = False,
+                                     frontier_batch: int = 1, relax_opts=None, use_cutoff: bool = True,
                                      warm_start: bool = False, device: Optional[int] = None, stop_at_open_nodes: int = 0, seed: int = 0):
     """Mirror of OMC.jl:140-1146 (disjunctive path).  Returns (solution, printlist, instance) with the
     reference's keys.  frontier_batch = 1 reproduces the reference's sequence of pops; larger batches pop B
@@ -353,6 +357,16 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
     opts = relax_opts or default_opts()
     free_states = list(range(pool))
     state_refs: Dict[int, int] = {}
+    pool_exhausted = 0
+
+    def release_parent_state(nd: BBNode):
+        """A child that leaves the tree (relaxed, dominated or pruned) gives back its share of the parent's warm-start record."""
+        if nd.warm_id >= 0 and nd.warm_id in state_refs:
+            state_refs[nd.warm_id] -= 1
+            if state_refs[nd.warm_id] == 0:
+                free_states.append(nd.warm_id)
+                del state_refs[nd.warm_id]
+        nd.warm_id = -1
     root_node_timeout = False
     while (tree.now_gap > gap and not (use_max_steps and tree.counter >= max_steps)
            and time.time() - start_time <= time_limit):
@@ -375,18 +389,15 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
             save = None
             if warm_start:
                 save = [free_states.pop() if free_states else -1 for _ in live]
+                pool_exhausted += sum(1 for sid in save if sid < 0)
             res = problem.relax_batch([nd.disjunctive_cuts for nd in live], opts,
                                       warm_ids=[nd.warm_id for nd in live] if warm_start else None, save_ids=save)
             for q, (nd, r) in enumerate(zip(live, res)):
                 r["save_id"] = save[q] if save else -1
                 results[nd.node_id] = r
-            if warm_start:                       # parents' records are no longer needed once their children are relaxed
-                for nd in live:
-                    if nd.warm_id >= 0:
-                        state_refs[nd.warm_id] -= 1
-                        if state_refs[nd.warm_id] == 0:
-                            free_states.append(nd.warm_id)
-                            del state_refs[nd.warm_id]
+        if warm_start:                           # parents' records are no longer needed once their children left the queue
+            for nd in batch:
+                release_parent_state(nd)
         # separation oracle for the whole batch in one launch (OMC.jl:814, 2466-2477)
         eig = {}
         cand = [nd for nd in live if results[nd.node_id]["feasible"]]
@@ -415,6 +426,14 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
                 else:
                     cnt["nodes_relax_feasible"] += 1
                     objective_relax = relax_result["objective"]
+                    if relax_result["termination_status"] != "OPTIMAL":
+                        # SLOW_PROGRESS / TIME_LIMIT: the primal objective of an unconverged first-order iterate is no bound.
+                        # The node keeps the larger of its inherited bound and the kernel's certified lower bound
+                        # (dual objective - ||r_d||_inf ||w*||_1), so pruning and the children's
+                        # bounds never rest on an uncertified value (the reference trusts Mosek's SLOW_PROGRESS point,
+                        # OMC.jl:1871-1877, which is an interior-point iterate at ~1e-8).
+                        cert = min(objective_relax, relax_result["lower_bound"])
+                        objective_relax = max(current_node.LB, cert) if np.isfinite(current_node.LB) else cert
                     current_node.LB = objective_relax
                     if current_node.node_id == 1:
                         tree.best_lower_bound = objective_relax
@@ -469,7 +488,12 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
                 add_nodes_to_tree(tree, kids, objective_relax)
             elif warm_start and relax_result is not None and relax_result.get("save_id", -1) >= 0:
                 free_states.append(relax_result["save_id"])
-            prune_dominated_nodes(tree)
+            elif warm_start and relax_result is None and current_node.node_id in results:
+                sid = results[current_node.node_id].get("save_id", -1)   # relaxed in this batch but dominated before its turn
+                if sid >= 0:
+                    free_states.append(sid)
+            for nd in prune_dominated_nodes(tree):
+                release_parent_state(nd)
             lower_bounds_updated = update_tree_lower_bounds(tree, pending_min)
             important = (lower_bounds_updated or current_node.node_id == 1
                          or tree.counter // update_step > tree.last_updated_counter // update_step
@@ -496,7 +520,8 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
         solve_time_altmin=solve_time_altmin, dict_solve_times_altmin=dict_solve_times_altmin,
         dict_num_iterations_altmin=dict_num_iterations_altmin, solve_time_relaxation_feasibility=0.0,
         solve_time_relaxation=solve_time_relaxation, dict_solve_times_relaxation=dict_solve_times_relaxation,
-        root_node_timeout=root_node_timeout, nodes_explored=tree.nodes_explored, nodes_total=tree.counter, **cnt)
+        root_node_timeout=root_node_timeout, nodes_explored=tree.nodes_explored, nodes_total=tree.counter,
+        warm_start_pool_exhausted=pool_exhausted, **cnt)
     instance["tree"] = tree
     instance["open_nodes"] = [tree.nodes[i] for i in sorted(tree.nodes)]
     instance["problem"] = problem
