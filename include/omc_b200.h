@@ -114,6 +114,17 @@ void omc_relax_default_opts(omc_relax_opts* o);
 int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_ptr, const int32_t* node_cut_ids,
                             const uint8_t* node_cut_dirs, const int32_t* warm_ids, const int32_t* save_ids,
                             omc_frontier** out);
+/* Same with an explicit engine.  OMC_ENGINE_PERSISTENT: one CTA per node, the node's whole ADMM inside one SM (n + m <= 104
+ * in shared memory, <= 208 through an L2 buffer; at most 64 / 32 cuts per node).  OMC_ENGINE_BATCHED: the frontier advances in
+ * lockstep, every ADMM iteration a short sequence of kernels over (tile, node) grids with the node state streaming from
+ * HBM; PSD blocks of any size (OMC.jl:1554-1556 at config 4 / 5 sizes), no cut cap other than shared memory (~100 cuts),
+ * cold starts only.  OMC_ENGINE_AUTO = batched when n + m > 104. */
+#define OMC_ENGINE_AUTO 0
+#define OMC_ENGINE_PERSISTENT 1
+#define OMC_ENGINE_BATCHED 2
+int32_t omc_frontier_create_ex(omc_problem* p, int32_t B, const int32_t* node_cut_ptr, const int32_t* node_cut_ids,
+                               const uint8_t* node_cut_dirs, const int32_t* warm_ids, const int32_t* save_ids,
+                               int32_t engine, omc_frontier** out);
 /* one pass of the hot path over the resident batch; kernel_ms (may be NULL) = CUDA-event time of the
  * fused ADMM kernel on the library stream */
 int32_t omc_frontier_relax(omc_frontier* f, const omc_relax_opts* opts, float* kernel_ms);
@@ -127,6 +138,16 @@ int32_t omc_frontier_fetch(omc_frontier* f, int32_t* status, double* objective, 
  * 14 / 15 = projections done by the low-rank tracker / by the full solver,
  * 16..23 = cycles in the sub-phases of the tracking step (V Z, residual, CholQR2, V R~, Gram, Jacobi, select + combine) */
 int32_t omc_frontier_fetch_profile(omc_frontier* f, double* prof);
+/* out8: [0] engine, [1] kernel launches of the last relax, [2] lockstep iterations, [3] node-iterations, [4] residual checks,
+ * [5] rho changes, [6] bytes of device state per node (batched engine) */
+int32_t omc_frontier_stats(omc_frontier* f, int64_t* out8);
+/* tracker knobs of the batched engine (values <= 0 keep the default): block-LOBPCG steps per projection (max / at the first
+ * iteration and when confirming a termination decision), Ritz-residual tolerances while iterating / when confirming */
+int32_t omc_frontier_set_tuning(omc_frontier* f, int32_t steps_max, int32_t steps_start, double track_tol, double confirm_tol);
+/* diagnostics (tests): one array of a node's record of the batched engine after a relax (scaled variables, row-major).
+ * which: 0..2 V_b, 3..5 Z_b (N_b x 16), 6..8 theta_b (16), 9..11 R_b, 12..14 W_b, 15 X, 16 Y, 17 Theta, 18 U.
+ * Returns the number of doubles written, < 0 on error. */
+int64_t omc_frontier_debug_fetch(omc_frontier* f, int32_t node, int32_t which, double* out, int64_t cap);
 int32_t omc_frontier_destroy(omc_frontier* f);
 /* convenience = create + relax + fetch + destroy (host buffers in, host buffers out) */
 int32_t omc_relax_batch(omc_problem* p, int32_t B, const int32_t* node_cut_ptr, const int32_t* node_cut_ids,

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libomc_b200.so")
 OK = 0
 STATUS_OPTIMAL, STATUS_ITERATION_LIMIT, STATUS_INFEASIBLE, STATUS_TIME_LIMIT, STATUS_CUTOFF, STATUS_NUMERICAL = 0, 1, 2, 3, 4, 5
 CUT_TYPES = {"linear": 0, "linear2": 1, "linear3": 2}
+ENGINES = {"auto": 0, "persistent": 1, "batched": 2}
 
 
 class RelaxOpts(C.Structure):
@@ -45,6 +46,10 @@ SIGNATURES = {
     "omc_cutpool_size": (_i32, [_vp, _pi32]),
     "omc_relax_default_opts": (None, [_p(RelaxOpts)]),
     "omc_frontier_create": (_i32, [_vp, _i32, _pi32, _pi32, _pu8, _pi32, _pi32, _p(_vp)]),
+    "omc_frontier_create_ex": (_i32, [_vp, _i32, _pi32, _pi32, _pu8, _pi32, _pi32, _i32, _p(_vp)]),
+    "omc_frontier_stats": (_i32, [_vp, _p(C.c_int64)]),
+    "omc_frontier_set_tuning": (_i32, [_vp, _i32, _i32, _f64, _f64]),
+    "omc_frontier_debug_fetch": (_i64, [_vp, _i32, _i32, _pf64, _i64]),
     "omc_frontier_relax": (_i32, [_vp, _p(RelaxOpts), _pf32]),
     "omc_frontier_fetch": (_i32, [_vp, _pi32, _pf64, _pf64, _pi32, _pf64, _pf64, _pf64, _pf64, _pf64]),
     "omc_frontier_fetch_profile": (_i32, [_vp, _pf64]),

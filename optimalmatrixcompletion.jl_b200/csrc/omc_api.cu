@@ -17,6 +17,7 @@
 #include "omc_eigsep.cuh"
 #include "omc_altmin.cuh"
 #include "omc_shor.cuh"
+#include "omc_big_host.h"
 
 namespace {
 
@@ -84,6 +85,13 @@ struct omc_problem {
   DevBuf<double> Xdev;  // staging for omc_objective_mse
   omc::StateLayout SL;
   double c0;
+  // row-major copies for the batched large-block engine (omc_big.cu), built on first use
+  double* AMrm = nullptr;
+  unsigned char* Mkrm = nullptr;
+  ~omc_problem() {
+    if (AMrm) cudaFree(AMrm);
+    if (Mkrm) cudaFree(Mkrm);
+  }
 };
 
 struct omc_frontier {
@@ -98,6 +106,8 @@ struct omc_frontier {
   int variant = 0;
   int xs_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  omcbig::BigFrontier* big = nullptr;   // engine 2: batched large-block engine (lockstep over the frontier)
+  omcbig::BigTuning tune;
 };
 
 namespace omc {
@@ -528,8 +538,16 @@ void omc_relax_default_opts(omc_relax_opts* o) {
 int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_ptr, const int32_t* node_cut_ids,
                             const uint8_t* node_cut_dirs, const int32_t* warm_ids, const int32_t* save_ids,
                             omc_frontier** out) {
+  return omc_frontier_create_ex(p, B, node_cut_ptr, node_cut_ids, node_cut_dirs, warm_ids, save_ids, OMC_ENGINE_AUTO, out);
+}
+
+int32_t omc_frontier_create_ex(omc_problem* p, int32_t B, const int32_t* node_cut_ptr, const int32_t* node_cut_ids,
+                               const uint8_t* node_cut_dirs, const int32_t* warm_ids, const int32_t* save_ids,
+                               int32_t engine, omc_frontier** out) {
   NEED_INIT();
   if (!p || !out || B <= 0 || !node_cut_ptr) return fail(OMC_ERR_ARG, "bad argument");
+  if (engine < OMC_ENGINE_AUTO || engine > OMC_ENGINE_BATCHED) return fail(OMC_ERR_ARG, "engine must be 0 (auto), 1 (persistent) or 2 (batched)");
+  if (engine == OMC_ENGINE_AUTO) engine = (p->n + p->m > 104) ? OMC_ENGINE_BATCHED : OMC_ENGINE_PERSISTENT;
   const int E = node_cut_ptr[B];
   if (E < 0 || node_cut_ptr[0] != 0) return fail(OMC_ERR_ARG, "node_cut_ptr must start at 0 and be non-decreasing");
   if (E > 0 && (!node_cut_ids || !node_cut_dirs)) return fail(OMC_ERR_ARG, "cut ids/dirs missing");
@@ -540,7 +558,8 @@ int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_p
     if (L < 0) return fail(OMC_ERR_ARG, "node_cut_ptr not monotone at node %d", b);
     if (L > Lmax) Lmax = L;
   }
-  if (Lmax > p->Lcap) return fail(OMC_ERR_UNSUPPORTED, "node with %d cuts exceeds the supported %d", Lmax, p->Lcap);
+  if (engine == OMC_ENGINE_PERSISTENT && Lmax > p->Lcap)
+    return fail(OMC_ERR_UNSUPPORTED, "node with %d cuts exceeds the %d the persistent engine supports (the batched engine, engine = 2, has no such cap)", Lmax, p->Lcap);
   for (int e = 0; e < E; ++e) {
     if (node_cut_ids[e] < 0 || node_cut_ids[e] >= p->pool_size) return fail(OMC_ERR_ARG, "cut id %d out of range", node_cut_ids[e]);
     for (int j = 0; j < p->k; ++j)
@@ -549,6 +568,31 @@ int32_t omc_frontier_create(omc_problem* p, int32_t B, const int32_t* node_cut_p
   for (int b = 0; b < B; ++b) {
     if (warm_ids && warm_ids[b] >= p->state_cap) return fail(OMC_ERR_ARG, "warm id out of range");
     if (save_ids && save_ids[b] >= p->state_cap) return fail(OMC_ERR_ARG, "save id out of range");
+  }
+  if (engine == OMC_ENGINE_BATCHED) {
+    if (warm_ids || save_ids) {
+      for (int b = 0; b < B; ++b)
+        if ((warm_ids && warm_ids[b] >= 0) || (save_ids && save_ids[b] >= 0))
+          return fail(OMC_ERR_UNSUPPORTED, "the batched engine starts every node cold (warm_ids / save_ids must be -1)");
+    }
+    if (!p->AMrm) {
+      if (omcbig::big_prepare_problem(p->n, p->m, p->A.p, p->Mk.p, &p->AMrm, &p->Mkrm, g_stream) != 0)
+        return fail(OMC_ERR_CUDA, "%s", omcbig::big_last_error());
+    }
+    omc_frontier* f = new omc_frontier();
+    f->p = p; f->B = B; f->E = E; f->Lmax = Lmax;
+    omcbig::big_default_tuning(&f->tune);
+    omcbig::BigProblemView pv;
+    pv.n = p->n; pv.m = p->m; pv.k = p->k; pv.cut_type = p->cut_type; pv.gamma = p->gamma; pv.c0 = p->c0;
+    pv.AMrm = p->AMrm; pv.Mkrm = p->Mkrm; pv.pool_x = p->pool_x.p; pv.pool_vhat = p->pool_vhat.p; pv.stream = g_stream;
+    pv.sm_count = g_sm_count;
+    const int rc = omcbig::big_create(pv, B, node_cut_ptr, node_cut_ids, node_cut_dirs, &f->big);
+    if (rc != 0) {
+      delete f;
+      return fail(rc == -4 ? OMC_ERR_UNSUPPORTED : OMC_ERR_CUDA, "%s", omcbig::big_last_error());
+    }
+    *out = f;
+    return OMC_OK;
   }
   const omc::Geo g1 = omc::make_geo(p->n + p->m);
   const omc::Geo g2 = omc::make_geo(p->n + p->k);
@@ -625,6 +669,10 @@ int32_t omc_frontier_relax(omc_frontier* f, const omc_relax_opts* opts, float* k
   if (o.adapt_every > 0) o.adapt_every = ((o.adapt_every + o.check_every - 1) / o.check_every) * o.check_every;
   if (o.max_iter <= 0) return fail(OMC_ERR_ARG, "max_iter must be positive");
   if (!(o.rho0 > 0) || !(o.sigma > 0) || !(o.alpha > 0 && o.alpha < 2)) return fail(OMC_ERR_ARG, "bad rho0/sigma/alpha");
+  if (f->big) {
+    if (omcbig::big_relax(f->big, &o, &f->tune, kernel_ms) != 0) return fail(OMC_ERR_CUDA, "%s", omcbig::big_last_error());
+    return OMC_OK;
+  }
   omc::RelaxArgs a;
   memset(&a, 0, sizeof a);
   a.n = p->n; a.m = p->m; a.k = p->k; a.cut_type = p->cut_type;
@@ -671,6 +719,11 @@ int32_t omc_frontier_fetch(omc_frontier* f, int32_t* status, double* objective, 
   omc_problem* p = f->p;
   const size_t B = f->B;
   if (Theta) return fail(OMC_ERR_UNSUPPORTED, "Theta is not materialised by this build (only tr Theta enters the objective)");
+  if (f->big) {
+    if (omcbig::big_fetch(f->big, status, objective, lower_bound, iters, res, X, Y, U) != 0)
+      return fail(OMC_ERR_CUDA, "%s", omcbig::big_last_error());
+    return OMC_OK;
+  }
   if (status) CU(cudaMemcpyAsync(status, f->status.p, B * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
   if (iters) CU(cudaMemcpyAsync(iters, f->iters.p, B * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
   if (objective) CU(cudaMemcpyAsync(objective, f->objective.p, B * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
@@ -686,6 +739,10 @@ int32_t omc_frontier_fetch(omc_frontier* f, int32_t* status, double* objective, 
 int32_t omc_frontier_fetch_profile(omc_frontier* f, double* prof) {
   NEED_INIT();
   if (!f || !prof) return fail(OMC_ERR_ARG, "null argument");
+  if (f->big) {   // the batched engine keeps launch statistics instead of per-node cycle counters (omc_frontier_stats)
+    memset(prof, 0, (size_t)f->B * OMC_PROF_STRIDE * sizeof(double));
+    return OMC_OK;
+  }
   CU(cudaMemcpyAsync(prof, f->prof.p, (size_t)f->B * OMC_PROF_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CU(cudaStreamSynchronize(g_stream));
   return OMC_OK;
@@ -696,7 +753,37 @@ int32_t omc_frontier_destroy(omc_frontier* f) {
   if (g_stream) cudaStreamSynchronize(g_stream);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
+  if (f->big) omcbig::big_destroy(f->big);
   delete f;
+  return OMC_OK;
+}
+
+int32_t omc_frontier_stats(omc_frontier* f, int64_t* out8) {
+  if (!f || !out8) return fail(OMC_ERR_ARG, "null argument");
+  for (int q = 0; q < 8; ++q) out8[q] = 0;
+  out8[0] = f->big ? OMC_ENGINE_BATCHED : OMC_ENGINE_PERSISTENT;
+  if (f->big) {
+    const omcbig::BigStats* s = omcbig::big_stats(f->big);
+    out8[1] = s->launches; out8[2] = s->iterations; out8[3] = s->node_iterations; out8[4] = s->checks; out8[5] = s->rho_changes;
+    out8[6] = (int64_t)omcbig::big_node_bytes(f->p->n, f->p->m, f->p->k, f->Lmax);
+  } else {
+    out8[1] = 1;
+  }
+  return OMC_OK;
+}
+
+int64_t omc_frontier_debug_fetch(omc_frontier* f, int32_t node, int32_t which, double* out, int64_t cap) {
+  if (!f || !out || !f->big) { fail(OMC_ERR_ARG, "debug fetch needs a batched-engine frontier"); return -1; }
+  return omcbig::big_debug_fetch(f->big, node, which, out, cap);
+}
+
+int32_t omc_frontier_set_tuning(omc_frontier* f, int32_t steps_max, int32_t steps_start, double track_tol, double confirm_tol) {
+  if (!f) return fail(OMC_ERR_ARG, "null frontier");
+  if (!f->big) return OMC_OK;
+  if (steps_max > 0) f->tune.steps_max = steps_max;
+  if (steps_start > 0) f->tune.steps_start = steps_start;
+  if (track_tol > 0) f->tune.track_tol = track_tol;
+  if (confirm_tol > 0) f->tune.confirm_tol = confirm_tol;
   return OMC_OK;
 }
 

@@ -1,0 +1,1773 @@
+// omc_big.cuh -- the batched large-block relaxation engine (round 2): the node relaxation of
+// matrix_completion_SDP_relaxation (/root/reference/src/OptimalMatrixCompletion.jl:1431-1943, "OMC.jl") for PSD blocks
+// that do not fit one SM's shared memory (config 4: n + m = 200, config 5: n + m = 2000), run in LOCKSTEP over a whole
+// frontier of open nodes: every ADMM iteration is a short sequence of kernels whose grids span (tile, node), so the
+// machine is filled by the frontier, the state of a node streams from HBM once per pass, and nothing about a node has
+// to fit on chip.  CPU restatement with the same steps and constants: oracle/bigblock.py.
+//
+//   v-form ADMM (COSMO/OSQP splitting of oracle/relaxation.py):  v <- v + alpha (z~ - P_K(v)),  mu = rho (v - P_K(v)).
+//   The projection of a PSD-block argument V_b is never formed: the minority spectral side of V_b (positive side of
+//   [Y X; X' Theta] and [Y U; U' I], negative side of aI - Y) is tracked as Z_b diag(theta_b) Z_b' with a panel of
+//   PM = 16 columns refined by block-LOBPCG steps on [Z, R] (R = residual of V Z, explicitly re-projected against Z),
+//   Rayleigh-Ritz on the 32 x 32 projected matrix by a warp-level cyclic Jacobi; every pass over V_b uses V_b and the factor.
+//
+// Kernels (grid.y = active node, grid.z = PSD block where it applies):
+//   k_xt      X and Theta regions: w-update, v-update and w relaxation fused in one pass (these entries meet no dense row)
+//   k_y1      Y and U regions, pass A: diagonal part of the w-update, per-tile partial sums of the dense rows
+//             (trace row, cut rows x'U_j, x'Yx)
+//   k_small   per node: dense-row right-hand side, Woodbury solve (explicit inverse, rebuilt when rho changes), scalar rows
+//   k_y2      Y and U regions, pass B: rank-(1 + L) correction, v-update of the three blocks' Y / U parts, w relaxation
+//   k_prod    W = side * V_b P for a 16-column panel P (FP64 DMMA m8n8k4, V streamed once), partial Gram matrices in the epilogue
+//   k_resid1/2, k_rr, k_update   the rest of a tracker step
+//   k_check + k_decide   residuals, dual objective, certified bound, termination / cut-off / infeasibility, rho adaptation
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/omc_b200.h"
+
+namespace omcbig {
+
+// FP64 tensor-core MMA (DMMA 8x8x4): D(8x8) = A(8x4,row) * B(4x8,col) + C.
+//   lane l: a = A[l>>2][l&3], b = B[l&3][l>>2], c0/c1 = C[l>>2][2*(l&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b, double c0, double c1) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide reductions (scratch >= 32 doubles); result valid in every thread
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  double r = (lane < nw) ? scratch[lane] : 0.0;
+  return warp_sum(r);
+}
+__device__ __forceinline__ double block_max(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  double r = (lane < nw) ? scratch[lane] : -1.0e300;
+  return warp_max(r);
+}
+
+constexpr int PM = 16;        // tracker panel width
+constexpr int TS = 64;        // region tile
+constexpr int NCHK = 16;      // per-tile partials of the residual check
+constexpr int ISTR = 32;      // ints per node
+constexpr int SSTR = 48;      // scalar doubles per node
+// int slots
+enum { I_STATUS = 0, I_L = 1, I_CONFIRM = 2, I_WASCONF = 3, I_MORE = 4 /*3*/, I_Q = 7 /*3*/, I_R = 10 /*3*/, I_ITERS = 13, I_DONE = 14,
+       I_ADAPTED = 15, I_SLOT = 16 };
+// scalar slots
+enum { S_RHO = 0, S_V4 = 1, S_RP = 2, S_RD = 3, S_OBJP = 4, S_OBJD = 5, S_LB = 6, S_CFAC = 7, S_RES = 8 /*3*/, S_NP = 11, S_ND = 12,
+       S_RESID2 = 13 /*3*/, S_HS2 = 16 /*3*/ };
+
+struct Layout {
+  int n, m, k, N[3], p[3], Lcap, rcap, tn, tm, nt[3];   // nt[b] = row tiles of block b
+  int tilesXT, tilesYU, tilesAll;
+  size_t X, Y, T, U, V[3], Yt, Ut, v5, vv, vg, xs, clb, cub, cal, cbe, G, Minv, rhs, cw;
+  size_t Z[3], W[3], R[3], W2[3], th[3], H[3], Q[3], partA[3], partB[3], rows_part, chk_part, scal, total;
+};
+
+inline size_t al4(size_t o) { return (o + 3) & ~(size_t)3; }
+
+inline Layout make_layout(int n, int m, int k, int Lcap) {
+  Layout L;
+  L.n = n; L.m = m; L.k = k; L.Lcap = Lcap; L.rcap = 1 + Lcap * (k + 1);
+  L.N[0] = n + m; L.N[1] = n + k; L.N[2] = n;
+  for (int b = 0; b < 3; ++b) {
+    L.p[b] = L.N[b] / 2 < PM ? (L.N[b] / 2 > 0 ? L.N[b] / 2 : 1) : PM;
+    L.nt[b] = (L.N[b] + TS - 1) / TS;
+  }
+  L.tn = (n + TS - 1) / TS; L.tm = (m + TS - 1) / TS;
+  L.tilesXT = L.tn * L.tm + L.tm * (L.tm + 1) / 2;
+  L.tilesYU = L.tn * (L.tn + 1) / 2 + L.tn;
+  L.tilesAll = L.tilesXT + L.tilesYU;
+  size_t o = 0;
+  auto take = [&](size_t cnt) { size_t r = o; o = al4(o + cnt); return r; };
+  L.X = take((size_t)n * m); L.Y = take((size_t)n * n); L.T = take((size_t)m * m); L.U = take((size_t)n * k);
+  for (int b = 0; b < 3; ++b) L.V[b] = take((size_t)L.N[b] * L.N[b]);
+  L.Yt = take((size_t)n * n); L.Ut = take((size_t)n * k);
+  L.v5 = take((size_t)n * k); L.vv = take((size_t)Lcap * k + 1); L.vg = take((size_t)Lcap + 1);
+  L.xs = take((size_t)Lcap * n + 1); L.clb = take((size_t)Lcap * k + 1); L.cub = take((size_t)Lcap * k + 1);
+  L.cal = take((size_t)Lcap * k + 1); L.cbe = take((size_t)Lcap + 1);
+  L.G = take((size_t)L.rcap * L.rcap); L.Minv = take((size_t)L.rcap * L.rcap); L.rhs = take(L.rcap); L.cw = take(L.rcap);
+  for (int b = 0; b < 3; ++b) {
+    L.Z[b] = take((size_t)L.N[b] * PM); L.W[b] = take((size_t)L.N[b] * PM); L.R[b] = take((size_t)L.N[b] * PM);
+    L.W2[b] = take((size_t)L.N[b] * PM); L.th[b] = take(PM); L.H[b] = take(PM * PM); L.Q[b] = take(2 * PM * PM);
+    L.partA[b] = take((size_t)L.nt[b] * PM * PM); L.partB[b] = take((size_t)L.nt[b] * PM * PM);
+  }
+  L.rows_part = take((size_t)L.tilesYU * L.rcap);
+  L.chk_part = take((size_t)L.tilesAll * NCHK);
+  L.scal = take(SSTR);
+  L.total = o;
+  return L;
+}
+
+struct Opts {
+  double eps_abs, eps_rel, sigma, alpha, rho0, cutoff, track_tol, confirm_tol, adapt_thresh;
+  int max_iter, check_every, adapt_every, steps_max, steps_start, fix_linear3_right, cut_type, infeasible_by_bound;
+};
+
+struct BigArgs {
+  Layout L;
+  double* S;            // node records, stride L.total
+  int* I;               // node ints, stride ISTR
+  const int* active;    // active node slots
+  const double* AM;     // row-major n x m: mask * A
+  const unsigned char* Mk;  // row-major n x m: mask
+  double a, sa, cT, c0, ktr;
+  Opts o;
+  int it;               // current iteration (1-based)
+  int step;             // tracker step within the iteration
+  int force;            // this iteration is followed by an off-schedule check (confirm pending somewhere)
+};
+
+__device__ __forceinline__ double* node_ptr(const BigArgs& a, int slot) { return a.S + (size_t)slot * a.L.total; }
+__device__ __forceinline__ int* node_int(const BigArgs& a, int slot) { return a.I + (size_t)slot * ISTR; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// tile helpers: 64 x 64 tile, 256 threads; thread (ty, tx) owns entries (ty + 16 r, tx + 16 c), r, c = 0..3, so that a
+// half-warp reads / writes 16 consecutive doubles of a row.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int ZLD = PM + 1;
+
+__device__ __forceinline__ double hash_unit(unsigned long long i, unsigned long long j, unsigned long long seed) {
+  unsigned long long h = i * 0x9E3779B97F4A7C15ull + j * 0xC2B2AE3D27D4EB4Full + seed * 0x165667B19E3779F9ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+// stage rows [row0, row0 + 64) of a panel (ld PM) into shared memory, column a scaled by sc[a] (sqrt(theta+) -> the low-rank
+// term becomes a plain inner product, bitwise symmetric in (i, j))
+__device__ __forceinline__ void stage_panel(double* dst, const double* __restrict__ P, int row0, int nrows, const double* sc) {
+  for (int e = threadIdx.x; e < TS * PM; e += blockDim.x) {
+    const int r = e / PM, c = e - r * PM;
+    const int gr = row0 + r;
+    dst[r * ZLD + c] = (gr < nrows) ? P[(size_t)gr * PM + c] * sc[c] : 0.0;
+  }
+}
+__device__ __forceinline__ void lowrank_tile(double (&F)[4][4], const double* Zi, const double* Zj, int ty, int tx) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) F[r][c] = 0.0;
+#pragma unroll 4
+  for (int a = 0; a < PM; ++a) {
+    double zi[4], zj[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) zi[r] = Zi[(ty + 16 * r) * ZLD + a];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) zj[c] = Zj[(tx + 16 * c) * ZLD + a];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) F[r][c] = fma(zi[r], zj[c], F[r][c]);
+  }
+}
+// sqrt(max(theta, 0)) of a block's Ritz values into shared memory
+__device__ __forceinline__ void stage_scale(double* sc, const double* th, int p) {
+  if (threadIdx.x < PM) sc[threadIdx.x] = (threadIdx.x < p && th[threadIdx.x] > 0.0) ? sqrt(th[threadIdx.x]) : 0.0;
+}
+// write the transpose of a register tile through shared memory: dst[(col0 + c) * ld + row0 + r] = v[r][c]
+__device__ __forceinline__ void store_mirror(double* __restrict__ dst, size_t ld, int row0, int col0, int nrows, int ncols,
+                                             const double (&v)[4][4], double* tb, int ty, int tx) {
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tb[(ty + 16 * r) * (TS + 1) + tx + 16 * c] = v[r][c];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int cc = ty + 16 * r, rr = tx + 16 * c;   // (cc, rr): column / row of the ORIGINAL tile
+      if (row0 + rr < nrows && col0 + cc < ncols) dst[(size_t)(col0 + cc) * ld + row0 + rr] = tb[rr * (TS + 1) + cc];
+    }
+}
+__device__ __forceinline__ void lower_tile(int t, int& I, int& J) {
+  I = 0;
+  while ((I + 1) * (I + 2) / 2 <= t) ++I;
+  J = t - I * (I + 1) / 2;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_xt: X region (tiles 0 .. tn*tm-1) and Theta region (lower tiles), one fused pass.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_xt(BigArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const Layout& L = a.L;
+  const int slot = a.active[blockIdx.y];
+  double* S = node_ptr(a, slot);
+  const int n = L.n, m = L.m, N1 = L.N[0];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double* Zi = sm; double* Zj = Zi + TS * ZLD; double* sc = Zj + TS * ZLD; double* tb = sc + PM;
+  const double rho = S[L.scal + S_RHO], sig = a.o.sigma, al = a.o.alpha;
+  stage_scale(sc, S + L.th[0], L.p[0]);
+  __syncthreads();
+  double* V1 = S + L.V[0];
+  const int t = blockIdx.x;
+  double F[4][4];
+  if (t < L.tn * L.tm) {
+    const int I = t / L.tm, J = t - I * L.tm;
+    const int i0 = I * TS, j0 = J * TS;
+    stage_panel(Zi, S + L.Z[0], i0, n, sc);
+    stage_panel(Zj, S + L.Z[0] + (size_t)n * PM, j0, m, sc);
+    __syncthreads();
+    lowrank_tile(F, Zi, Zj, ty, tx);
+    double vnew[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = i0 + ty + 16 * r, j = j0 + tx + 16 * c;
+        vnew[r][c] = 0.0;
+        if (i < n && j < m) {
+          const size_t e = (size_t)i * m + j, ev = (size_t)i * N1 + n + j;
+          const double D = V1[ev], x = S[L.X + e], mk = (double)a.Mk[e], am = a.AM[e];
+          const double gX = -2.0 * rho * (D - 2.0 * F[r][c]);
+          const double xt = (sig * x + am + gX) / (mk + sig + 2.0 * rho);
+          const double vn = D + al * (xt - F[r][c]);
+          V1[ev] = vn;
+          vnew[r][c] = vn;
+          S[L.X + e] = al * xt + (1.0 - al) * x;
+        }
+      }
+    store_mirror(V1 + (size_t)n * N1, N1, i0, j0, n, m, vnew, tb, ty, tx);   // V1[n + j][i]
+  } else {
+    int I, J;
+    lower_tile(t - L.tn * L.tm, I, J);
+    const int i0 = I * TS, j0 = J * TS;
+    stage_panel(Zi, S + L.Z[0] + (size_t)n * PM, i0, m, sc);
+    stage_panel(Zj, S + L.Z[0] + (size_t)n * PM, j0, m, sc);
+    __syncthreads();
+    lowrank_tile(F, Zi, Zj, ty, tx);
+    double vnew[4][4], tnew[4][4];
+    double* T = S + L.T;
+    double* V1T = V1 + (size_t)n * N1 + n;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = i0 + ty + 16 * r, j = j0 + tx + 16 * c;
+        vnew[r][c] = tnew[r][c] = 0.0;
+        if (i < m && j < m) {
+          const size_t e = (size_t)i * m + j, ev = (size_t)i * N1 + j;
+          const double D = V1T[ev], tt0 = T[e];
+          const double gT = -rho * (D - 2.0 * F[r][c]);
+          const double tt = (sig * tt0 - ((i == j) ? a.cT : 0.0) + gT) / (sig + rho);
+          const double vn = D + al * (tt - F[r][c]);
+          const double tn_ = al * tt + (1.0 - al) * tt0;
+          V1T[ev] = vn; T[e] = tn_;
+          vnew[r][c] = vn; tnew[r][c] = tn_;
+        }
+      }
+    if (I != J) {
+      store_mirror(V1T, N1, i0, j0, m, m, vnew, tb, ty, tx);
+      store_mirror(T, m, i0, j0, m, m, tnew, tb, ty, tx);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_y1: Y region (lower tiles) and U region (tn tiles of 64 rows), pass A.  Writes the diagonal-solve values Y~pre, U~pre
+// and the per-tile partial sums of the dense rows  R(Y~, U~) = [tr Y~ ; -x_l'U~_j ; -sum_j alpha_lj x_l'U~_j + x_l'Y~x_l].
+// rows_part[tile][q]: q = 0 trace, 1 + l k + j -> x_l'U~_j, 1 + L k + l -> x_l'Y~x_l  (signs applied in k_small).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+__global__ void __launch_bounds__(256) k_y1(BigArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const Layout& L = a.L;
+  const int slot = a.active[blockIdx.y];
+  double* S = node_ptr(a, slot);
+  const int* NI = node_int(a, slot);
+  const int n = L.n, k = L.k, N1 = L.N[0], N2 = L.N[1];
+  const int Lc = NI[I_L];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* Zi = sm;                      // [3][TS*ZLD]
+  double* Zj = Zi + 3 * TS * ZLD;       // [3][TS*ZLD]
+  double* sc = Zj + 3 * TS * ZLD;       // [3][PM]
+  double* tb = sc + 3 * PM;             // [TS*(TS+1)]
+  double* xi = tb + TS * (TS + 1);      // [Lc][TS]
+  double* xj = xi + (size_t)L.Lcap * TS;
+  double* tgs = xj + (size_t)L.Lcap * TS;   // [Lc] tg/rho of the aggregated rows
+  double* wred = tgs + L.Lcap + 1;      // [8][rcap]
+  const double rho = S[L.scal + S_RHO], sig = a.o.sigma;
+  const double dYU = sig + 3.0 * rho;
+  const int nYt = L.tn * (L.tn + 1) / 2;
+  const int t = blockIdx.x;
+  const int rq = 1 + Lc * (k + 1);
+  for (int e = threadIdx.x; e < 8 * L.rcap; e += 256) wred[e] = 0.0;
+  for (int b = 0; b < 3; ++b) {
+    if (threadIdx.x < PM) {
+      const double th = S[L.th[b] + threadIdx.x];
+      sc[b * PM + threadIdx.x] = (threadIdx.x < L.p[b] && th > 0.0) ? sqrt(th) : 0.0;
+    }
+  }
+  for (int l = threadIdx.x; l < Lc; l += 256) tgs[l] = S[L.vg + l] - 2.0 * fmax(S[L.vg + l], 0.0) + S[L.cbe + l];
+  __syncthreads();
+  double* part = S + L.rows_part + (size_t)t * L.rcap;
+  if (t < nYt) {
+    int I, J;
+    lower_tile(t, I, J);
+    const int i0 = I * TS, j0 = J * TS;
+    for (int b = 0; b < 3; ++b) {
+      stage_panel(Zi + b * TS * ZLD, S + L.Z[b], i0, n, sc + b * PM);
+      stage_panel(Zj + b * TS * ZLD, S + L.Z[b], j0, n, sc + b * PM);
+    }
+    for (int e = threadIdx.x; e < Lc * TS; e += 256) {
+      const int l = e / TS, q = e - l * TS;
+      xi[l * TS + q] = (i0 + q < n) ? S[L.xs + (size_t)l * n + i0 + q] : 0.0;
+      xj[l * TS + q] = (j0 + q < n) ? S[L.xs + (size_t)l * n + j0 + q] : 0.0;
+    }
+    __syncthreads();
+    double F1[4][4], F2[4][4], F3[4][4], yt[4][4];
+    lowrank_tile(F1, Zi, Zj, ty, tx);
+    lowrank_tile(F2, Zi + TS * ZLD, Zj + TS * ZLD, ty, tx);
+    lowrank_tile(F3, Zi + 2 * TS * ZLD, Zj + 2 * TS * ZLD, ty, tx);
+    const double v4 = S[L.scal + S_V4];
+    const double t4 = v4 - 2.0 * fmax(v4, 0.0) + a.ktr;
+    double trp = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int il = ty + 16 * r, jl = tx + 16 * c;
+        const int i = i0 + il, j = j0 + jl;
+        yt[r][c] = 0.0;
+        if (i < n && j < n) {
+          const double D1 = S[L.V[0] + (size_t)i * N1 + j], D2 = S[L.V[1] + (size_t)i * N2 + j], D3 = S[L.V[2] + (size_t)i * n + j];
+          double g = -(D1 - 2.0 * F1[r][c]) - (D2 - 2.0 * F2[r][c]) + (-D3 - 2.0 * F3[r][c]);
+          if (i == j) g += a.a + t4;
+          for (int l = 0; l < Lc; ++l) g = fma(tgs[l], xi[l * TS + il] * xj[l * TS + jl], g);
+          const double y = (sig * S[L.Y + (size_t)i * n + j] + rho * g) / dYU;
+          yt[r][c] = y;
+          S[L.Yt + (size_t)i * n + j] = y;
+          if (i == j) trp += y;
+        }
+      }
+    if (I != J) store_mirror(S + L.Yt, n, i0, j0, n, n, yt, tb, ty, tx);
+    // dense-row partial sums over this tile (off-diagonal tiles count twice in x'Yx)
+    const double wgt = (I != J) ? 2.0 : 1.0;
+    trp = warp_sum(trp);
+    if (lane == 0) wred[warp * L.rcap + 0] = trp;
+    for (int l = 0; l < Lc; ++l) {
+      double q = 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q = fma(xi[l * TS + ty + 16 * r] * xj[l * TS + tx + 16 * c], yt[r][c], q);
+      q = warp_sum(q);
+      if (lane == 0) wred[warp * L.rcap + 1 + Lc * k + l] = wgt * q;
+    }
+  } else {
+    // U tile: rows i0 .. i0+63, columns 0..k-1.  U~pre = (sig U + rho gU) / dYU,
+    // gU/rho = -2 (D2u - 2 F2u) - (v5 - 2 s5) - sum_l x_li (tv_lj + tg_l alpha_lj)
+    const int i0 = (t - nYt) * TS;
+    stage_panel(Zi, S + L.Z[1], i0, n, sc + PM);
+    // the k rows n .. n+k-1 of Z2 (scaled)
+    for (int e = threadIdx.x; e < k * PM; e += 256) {
+      const int j = e / PM, c = e - j * PM;
+      Zj[j * ZLD + c] = S[L.Z[1] + (size_t)(n + j) * PM + c] * sc[PM + c];
+    }
+    for (int e = threadIdx.x; e < Lc * TS; e += 256) {
+      const int l = e / TS, q = e - l * TS;
+      xi[l * TS + q] = (i0 + q < n) ? S[L.xs + (size_t)l * n + i0 + q] : 0.0;
+    }
+    __syncthreads();
+    const double sa = a.sa;
+    for (int e = threadIdx.x; e < TS * k; e += 256) {
+      const int il = e / k, j = e - il * k;
+      const int i = i0 + il;
+      double ut = 0.0;
+      if (i < n) {
+        double F = 0.0;
+        for (int c = 0; c < PM; ++c) F = fma(Zi[il * ZLD + c], Zj[j * ZLD + c], F);
+        const double D = S[L.V[1] + (size_t)i * N2 + n + j];
+        const double v5 = S[L.v5 + (size_t)i * k + j];
+        const double lo5 = (i >= n - k + j) ? 0.0 : -sa;
+        const double s5 = clampd(v5, lo5, sa);
+        double g = -2.0 * (D - 2.0 * F) - (v5 - 2.0 * s5);
+        for (int l = 0; l < Lc; ++l) {
+          const double vv = S[L.vv + (size_t)l * k + j];
+          const double sv = clampd(vv, S[L.clb + (size_t)l * k + j], S[L.cub + (size_t)l * k + j]);
+          g -= xi[l * TS + il] * ((vv - 2.0 * sv) + tgs[l] * S[L.cal + (size_t)l * k + j]);
+        }
+        ut = (sig * S[L.U + (size_t)i * k + j] + rho * g) / dYU;
+        S[L.Ut + (size_t)i * k + j] = ut;
+      }
+      tb[il * (TS + 1) + j] = ut;     // keep the tile for the row sums below
+    }
+    __syncthreads();
+    // x_l'U~_j over the 64 rows of this tile: one (l, j) per thread
+    for (int e = threadIdx.x; e < Lc * k; e += 256) {
+      const int l = e / k, j = e - l * k;
+      double q = 0.0;
+      for (int il = 0; il < TS; ++il) q = fma(xi[l * TS + il], tb[il * (TS + 1) + j], q);
+      part[1 + l * k + j] = q;
+    }
+    if (threadIdx.x == 0) part[0] = 0.0;
+    for (int l = threadIdx.x; l < Lc; l += 256) part[1 + Lc * k + l] = 0.0;
+    return;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < rq; q += 256) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += wred[w * L.rcap + q];
+    part[q] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_small: one CTA per node.  R0 = dense rows of (Y~pre, U~pre); cw = Minv R0; Rf = R0 - G cw = rows of the corrected
+// (Y~, U~); v-updates of the scalar rows (trace row, cut rows).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_small(BigArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const Layout& L = a.L;
+  const int slot = a.active[blockIdx.x];
+  double* S = node_ptr(a, slot);
+  const int* NI = node_int(a, slot);
+  const int k = L.k, Lc = NI[I_L];
+  const int rq = 1 + Lc * (k + 1);
+  double* Rw = sm; double* R0 = Rw + L.rcap; double* cw = R0 + L.rcap; double* Rf = cw + L.rcap;
+  for (int q = threadIdx.x; q < rq; q += 128) {
+    double s = 0.0;
+    for (int t = 0; t < L.tilesYU; ++t) s += S[L.rows_part + (size_t)t * L.rcap + q];
+    Rw[q] = s;
+  }
+  __syncthreads();
+  // R(Y~, U~): [tr ; -x'U ; -sum_j alpha x'U + x'Yx]
+  for (int q = threadIdx.x; q < rq; q += 128) {
+    double v;
+    if (q == 0) v = Rw[0];
+    else if (q < 1 + Lc * k) v = -Rw[q];
+    else {
+      const int l = q - 1 - Lc * k;
+      v = Rw[q];
+      for (int j = 0; j < k; ++j) v -= S[L.cal + (size_t)l * k + j] * Rw[1 + l * k + j];
+    }
+    R0[q] = v;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < rq; q += 128) {
+    double s = 0.0;
+    for (int c = 0; c < rq; ++c) s = fma(S[L.Minv + (size_t)q * L.rcap + c], R0[c], s);
+    cw[q] = s;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < rq; q += 128) {
+    double s = R0[q];
+    for (int c = 0; c < rq; ++c) s -= S[L.G + (size_t)q * L.rcap + c] * cw[c];
+    Rf[q] = s;
+    S[L.cw + q] = cw[q];
+  }
+  __syncthreads();
+  const double al = a.o.alpha;
+  if (threadIdx.x == 0) {
+    const double v4 = S[L.scal + S_V4];
+    const double z4 = a.ktr - Rf[0];
+    S[L.scal + S_V4] = v4 + al * (z4 - fmax(v4, 0.0));
+  }
+  for (int e = threadIdx.x; e < Lc * k; e += 128) {
+    const double vv = S[L.vv + e];
+    const double zv = -Rf[1 + e];
+    S[L.vv + e] = vv + al * (zv - clampd(vv, S[L.clb + e], S[L.cub + e]));
+  }
+  for (int l = threadIdx.x; l < Lc; l += 128) {
+    const double vg = S[L.vg + l];
+    const double zg = S[L.cbe + l] - Rf[1 + Lc * k + l];
+    S[L.vg + l] = vg + al * (zg - fmax(vg, 0.0));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_y2: Y and U regions, pass B.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_y2(BigArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const Layout& L = a.L;
+  const int slot = a.active[blockIdx.y];
+  double* S = node_ptr(a, slot);
+  const int* NI = node_int(a, slot);
+  const int n = L.n, k = L.k, N1 = L.N[0], N2 = L.N[1];
+  const int Lc = NI[I_L];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double* Zi = sm;
+  double* Zj = Zi + 3 * TS * ZLD;
+  double* sc = Zj + 3 * TS * ZLD;
+  double* tb = sc + 3 * PM;
+  double* xi = tb + TS * (TS + 1);
+  double* xj = xi + (size_t)L.Lcap * TS;
+  double* cg = xj + (size_t)L.Lcap * TS;    // [Lc] cw of the aggregated rows
+  const double al = a.o.alpha;
+  const int nYt = L.tn * (L.tn + 1) / 2;
+  const int t = blockIdx.x;
+  for (int b = 0; b < 3; ++b) {
+    if (threadIdx.x < PM) {
+      const double th = S[L.th[b] + threadIdx.x];
+      sc[b * PM + threadIdx.x] = (threadIdx.x < L.p[b] && th > 0.0) ? sqrt(th) : 0.0;
+    }
+  }
+  for (int l = threadIdx.x; l < Lc; l += 256) cg[l] = S[L.cw + 1 + Lc * k + l];
+  __syncthreads();
+  const double cw0 = S[L.cw + 0];
+  if (t < nYt) {
+    int I, J;
+    lower_tile(t, I, J);
+    const int i0 = I * TS, j0 = J * TS;
+    for (int b = 0; b < 3; ++b) {
+      stage_panel(Zi + b * TS * ZLD, S + L.Z[b], i0, n, sc + b * PM);
+      stage_panel(Zj + b * TS * ZLD, S + L.Z[b], j0, n, sc + b * PM);
+    }
+    for (int e = threadIdx.x; e < Lc * TS; e += 256) {
+      const int l = e / TS, q = e - l * TS;
+      xi[l * TS + q] = (i0 + q < n) ? S[L.xs + (size_t)l * n + i0 + q] : 0.0;
+      xj[l * TS + q] = (j0 + q < n) ? S[L.xs + (size_t)l * n + j0 + q] : 0.0;
+    }
+    __syncthreads();
+    double F1[4][4], F2[4][4], F3[4][4], o1[4][4], o2[4][4], o3[4][4], oy[4][4];
+    lowrank_tile(F1, Zi, Zj, ty, tx);
+    lowrank_tile(F2, Zi + TS * ZLD, Zj + TS * ZLD, ty, tx);
+    lowrank_tile(F3, Zi + 2 * TS * ZLD, Zj + 2 * TS * ZLD, ty, tx);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int il = ty + 16 * r, jl = tx + 16 * c;
+        const int i = i0 + il, j = j0 + jl;
+        o1[r][c] = o2[r][c] = o3[r][c] = oy[r][c] = 0.0;
+        if (i < n && j < n) {
+          double cy = (i == j) ? cw0 : 0.0;
+          for (int l = 0; l < Lc; ++l) cy = fma(cg[l], xi[l * TS + il] * xj[l * TS + jl], cy);
+          const double yt = S[L.Yt + (size_t)i * n + j] - cy;
+          const size_t e1 = L.V[0] + (size_t)i * N1 + j, e2 = L.V[1] + (size_t)i * N2 + j, e3 = L.V[2] + (size_t)i * n + j;
+          const double v1 = S[e1] + al * (yt - F1[r][c]);
+          const double v2 = S[e2] + al * (yt - F2[r][c]);
+          const double d3 = S[e3];
+          const double v3 = d3 + al * (((i == j) ? a.a : 0.0) - yt - d3 - F3[r][c]);
+          const size_t ey = L.Y + (size_t)i * n + j;
+          const double yn = al * yt + (1.0 - al) * S[ey];
+          S[e1] = v1; S[e2] = v2; S[e3] = v3; S[ey] = yn;
+          o1[r][c] = v1; o2[r][c] = v2; o3[r][c] = v3; oy[r][c] = yn;
+        }
+      }
+    if (I != J) {
+      store_mirror(S + L.V[0], N1, i0, j0, n, n, o1, tb, ty, tx);
+      store_mirror(S + L.V[1], N2, i0, j0, n, n, o2, tb, ty, tx);
+      store_mirror(S + L.V[2], n, i0, j0, n, n, o3, tb, ty, tx);
+      store_mirror(S + L.Y, n, i0, j0, n, n, oy, tb, ty, tx);
+    }
+  } else {
+    const int i0 = (t - nYt) * TS;
+    stage_panel(Zi, S + L.Z[1], i0, n, sc + PM);
+    for (int e = threadIdx.x; e < k * PM; e += 256) {
+      const int j = e / PM, c = e - j * PM;
+      Zj[j * ZLD + c] = S[L.Z[1] + (size_t)(n + j) * PM + c] * sc[PM + c];
+    }
+    for (int e = threadIdx.x; e < Lc * TS; e += 256) {
+      const int l = e / TS, q = e - l * TS;
+      xi[l * TS + q] = (i0 + q < n) ? S[L.xs + (size_t)l * n + i0 + q] : 0.0;
+    }
+    __syncthreads();
+    const double sa = a.sa;
+    for (int e = threadIdx.x; e < TS * k; e += 256) {
+      const int il = e / k, j = e - il * k;
+      const int i = i0 + il;
+      if (i >= n) continue;
+      double F = 0.0;
+      for (int c = 0; c < PM; ++c) F = fma(Zi[il * ZLD + c], Zj[j * ZLD + c], F);
+      // cU_ij = - sum_l x_li (cv_lj + cg_l alpha_lj);  U~ = U~pre - cU
+      double cu = 0.0;
+      for (int l = 0; l < Lc; ++l) cu -= xi[l * TS + il] * (S[L.cw + 1 + l * k + j] + cg[l] * S[L.cal + (size_t)l * k + j]);
+      const double ut = S[L.Ut + (size_t)i * k + j] - cu;
+      const size_t e2 = L.V[1] + (size_t)i * N2 + n + j, e2t = L.V[1] + (size_t)(n + j) * N2 + i;
+      const double v2 = S[e2] + al * (ut - F);
+      S[e2] = v2; S[e2t] = v2;
+      const double v5 = S[L.v5 + (size_t)i * k + j];
+      const double lo5 = (i >= n - k + j) ? 0.0 : -sa;
+      S[L.v5 + (size_t)i * k + j] = v5 + al * (ut - clampd(v5, lo5, sa));
+      const size_t eu = L.U + (size_t)i * k + j;
+      S[eu] = al * ut + (1.0 - al) * S[eu];
+    }
+    if (t == nYt) {
+      // the k x k identity corner of block 2: z = delta
+      for (int e = threadIdx.x; e < k * k; e += 256) {
+        const int i = e / k, j = e - i * k;
+        double F = 0.0;
+        for (int c = 0; c < PM; ++c) F = fma(Zj[i * ZLD + c], Zj[j * ZLD + c], F);
+        const size_t ev = L.V[1] + (size_t)(n + i) * N2 + n + j;
+        S[ev] = S[ev] + al * (((i == j) ? 1.0 : 0.0) - F);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_prod: Wout = side * V_b P, P a 16-column panel (Z for which = 0, R for which = 1), FP64 DMMA m8n8k4.  One CTA = 64 rows
+// of one (node, block): V streams through shared memory in 64 x 32 chunks (register-prefetched).  Epilogue: partial Gram
+// matrices of this row tile, partA = Z_tile' Wout_tile and (which = 1) partB = R_tile' Wout_tile.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KC = 32, VLD = 36, PLD = 24;
+
+__global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
+  __shared__ __align__(16) double Vs[TS * VLD];
+  __shared__ __align__(16) double Ps[KC * PLD];
+  __shared__ double Ws[TS * ZLD];
+  __shared__ double Ls[TS * ZLD];
+  const Layout& L = a.L;
+  const int b = blockIdx.z;
+  if ((int)blockIdx.x >= L.nt[b]) return;
+  const int slot = a.active[blockIdx.y];
+  const int* NI = node_int(a, slot);
+  if (a.step > 0 && !NI[I_MORE + b]) return;
+  double* S = node_ptr(a, slot);
+  const int N = L.N[b];
+  const double sd = (b == 2) ? -1.0 : 1.0;
+  const double* __restrict__ V = S + L.V[b];
+  const double* __restrict__ P = S + (which ? L.R[b] : L.Z[b]);
+  double* Wout = S + (which ? L.W2[b] : L.W[b]);
+  const int r0 = blockIdx.x * TS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  double c[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  double pv[16], pp[4];
+  auto fetch = [&](int kc) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int idx = q * 128 + tid, row = idx >> 5, col = idx & 31;
+      const int gr = r0 + row, gc = kc + col;
+      pv[q] = (gr < N && gc < N) ? V[(size_t)gr * N + gc] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = q * 128 + tid, row = idx >> 4, col = idx & 15;
+      pp[q] = (kc + row < N) ? P[(size_t)(kc + row) * PM + col] : 0.0;
+    }
+  };
+  fetch(0);
+  for (int kc = 0; kc < N; kc += KC) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int idx = q * 128 + tid, row = idx >> 5, col = idx & 31;
+      Vs[row * VLD + col] = pv[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = q * 128 + tid, row = idx >> 4, col = idx & 15;
+      Ps[row * PLD + col] = pp[q];
+    }
+    __syncthreads();
+    if (kc + KC < N) fetch(kc + KC);
+    const int rb = warp * 16;
+#pragma unroll
+    for (int kk = 0; kk < KC / 4; ++kk) {
+      const double a0 = Vs[(rb + g) * VLD + kk * 4 + t4], a1 = Vs[(rb + 8 + g) * VLD + kk * 4 + t4];
+      const double b0 = Ps[(kk * 4 + t4) * PLD + g], b1 = Ps[(kk * 4 + t4) * PLD + 8 + g];
+      dmma884(c[0][0][0], c[0][0][1], a0, b0, c[0][0][0], c[0][0][1]);
+      dmma884(c[0][1][0], c[0][1][1], a0, b1, c[0][1][0], c[0][1][1]);
+      dmma884(c[1][0][0], c[1][0][1], a1, b0, c[1][0][0], c[1][0][1]);
+      dmma884(c[1][1][0], c[1][1][1], a1, b1, c[1][1][0], c[1][1][1]);
+    }
+  }
+  // epilogue: W tile to shared + global
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int row = warp * 16 + mt * 8 + g, col = nt * 8 + 2 * t4;
+      Ws[row * ZLD + col] = sd * c[mt][nt][0];
+      Ws[row * ZLD + col + 1] = sd * c[mt][nt][1];
+    }
+  __syncthreads();
+  for (int e = tid; e < TS * PM; e += 128) {
+    const int row = e >> 4, col = e & 15;
+    if (r0 + row < N) Wout[(size_t)(r0 + row) * PM + col] = Ws[row * ZLD + col];
+    else Ws[row * ZLD + col] = 0.0;
+  }
+  for (int pass = 0; pass <= which; ++pass) {
+    const double* Lp = S + (pass ? L.R[b] : L.Z[b]);
+    __syncthreads();
+    for (int e = tid; e < TS * PM; e += 128) {
+      const int row = e >> 4, col = e & 15;
+      Ls[row * ZLD + col] = (r0 + row < N) ? Lp[(size_t)(r0 + row) * PM + col] : 0.0;
+    }
+    __syncthreads();
+    double* part = S + (pass ? L.partB[b] : L.partA[b]) + (size_t)blockIdx.x * PM * PM;
+    for (int e = tid; e < PM * PM; e += 128) {
+      const int ai = e >> 4, bi = e & 15;
+      double s = 0.0;
+#pragma unroll 8
+      for (int r = 0; r < TS; ++r) s = fma(Ls[r * ZLD + ai], Ws[r * ZLD + bi], s);
+      part[e] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_resid, pass 0: R = W - Z H (H = sum of partA, or diag(theta) after the first step of an iteration), probe column;
+//                  partB = Z_tile' R_tile.
+//          pass 1: C = sum partB; R -= Z C; partA = Z_tile' R_tile.        (two explicit projections against Z: "twice is
+//          pass 2: C = sum partA; R -= Z C; partB = R_tile' R_tile.         enough", see oracle/bigblock.py)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
+  __shared__ double Hs[PM * ZLD];
+  __shared__ double Zs[TS * ZLD];
+  __shared__ double Rs[TS * ZLD];
+  __shared__ double red[32];
+  const Layout& L = a.L;
+  const int b = blockIdx.z;
+  if ((int)blockIdx.x >= L.nt[b]) return;
+  const int slot = a.active[blockIdx.y];
+  const int* NI = node_int(a, slot);
+  if (a.step > 0 && !NI[I_MORE + b]) return;
+  double* S = node_ptr(a, slot);
+  const int N = L.N[b], tid = threadIdx.x;
+  const int r0 = blockIdx.x * TS;
+  {
+    const int ai = tid >> 4, bi = tid & 15;
+    double s = 0.0;
+    if (pass == 0 && a.step > 0) {
+      s = (ai == bi && ai < L.p[b]) ? S[L.th[b] + ai] : 0.0;   // (dead columns carry a -1e300 sentinel)
+    } else {
+      const double* part = S + ((pass & 1) ? L.partB[b] : L.partA[b]);
+      for (int t = 0; t < L.nt[b]; ++t) s += part[(size_t)t * PM * PM + tid];
+    }
+    Hs[ai * ZLD + bi] = s;
+    if (pass == 0 && blockIdx.x == 0) S[L.H[b] + tid] = s;
+  }
+  const double* src = S + (pass ? L.R[b] : L.W[b]);
+  for (int e = tid; e < TS * PM; e += 256) {
+    const int row = e >> 4, col = e & 15;
+    const bool ok = r0 + row < N;
+    Zs[row * ZLD + col] = ok ? S[L.Z[b] + (size_t)(r0 + row) * PM + col] : 0.0;
+    Rs[row * ZLD + col] = ok ? src[(size_t)(r0 + row) * PM + col] : 0.0;
+  }
+  __syncthreads();
+  // pass 0: the last panel column carries a fresh pseudo-random probe instead of its residual, so that the trial space
+  // [Z, R] stays generic: an eigenvector exactly orthogonal to Z and to every residual (e.g. the identity corner of
+  // [Y U; U' I] at a node without cuts, where U = 0) would otherwise never be found again once it has left the panel
+  double amp = 0.0;
+  if (pass == 0) {
+    double h2 = 0.0;
+    { const int ai = tid >> 4, bi = tid & 15; const double h = Hs[ai * ZLD + bi]; h2 = h * h; }
+    h2 = block_sum(h2, red);
+    amp = 1e-3 * sqrt(h2 / (double)N);
+  }
+  {
+    const int row = tid >> 2, cb = (tid & 3) * 4;
+    double acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = Rs[row * ZLD + cb + q];
+#pragma unroll
+    for (int c = 0; c < PM; ++c) {
+      const double z = Zs[row * ZLD + c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fma(-z, Hs[c * ZLD + cb + q], acc[q]);
+    }
+    if (pass == 0) {
+      const int pc = L.p[b] - 1;
+      if (pc >= cb && pc < cb + 4 && pc > 0)
+        acc[pc - cb] = amp * hash_unit((unsigned long long)(r0 + row), (unsigned long long)(a.it * 64 + a.step * 4 + b), 12345ull);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      Rs[row * ZLD + cb + q] = acc[q];
+      if (r0 + row < N) S[L.R[b] + (size_t)(r0 + row) * PM + cb + q] = acc[q];
+    }
+  }
+  __syncthreads();
+  {
+    const int ai = tid >> 4, bi = tid & 15;
+    const double* Lm = (pass == 2) ? Rs : Zs;
+    double s = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < TS; ++r) s = fma(Lm[r * ZLD + ai], Rs[r * ZLD + bi], s);
+    double* part = S + ((pass & 1) ? L.partA[b] : L.partB[b]) + (size_t)blockIdx.x * PM * PM;
+    part[tid] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_rr: one warp per (node, block).  M = sum partA (after k_resid2) -> guarded Cholesky -> T = L^-T; the second product
+// gave partA = Z'(V R), partB = R'(V R): Xc = (Z'VR) T, C = T'(R'VR) T; Rayleigh-Ritz on [[H, Xc], [Xc', C]] by cyclic
+// Jacobi (round-robin pairs, lanes = pairs / columns); keeps the p largest Ritz pairs; writes Q (2 PM x PM, the
+// bottom half already multiplied by T so that Znew = Z Qtop + R Qbot), theta, and the step control flags.
+// This kernel is launched AFTER the second product; the Cholesky input M was saved by k_chol (below) into H's neighbour.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int JN = 2 * PM, JLD = JN + 1;
+
+__device__ __forceinline__ void jacobi_warp(double* A, double* Q, int lane, double* cs) {
+  // A: JN x JN symmetric (ld JLD), Q: eigenvector accumulator (identity on entry).  Round-robin ordering over JN players.
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int c = 0; c < JN; ++c) {
+      const double v = A[lane * JLD + c];
+      if (c == lane) dg = fmax(dg, fabs(v)); else off = fmax(off, fabs(v));
+    }
+    off = warp_max(off); dg = warp_max(dg);
+    if (off <= 1e-15 * dg || off < 1e-300) break;
+    for (int rnd = 0; rnd < JN - 1; ++rnd) {
+      if (lane < PM) {
+        int p_, q_;
+        if (lane == 0) { p_ = JN - 1; q_ = rnd; }
+        else { p_ = (rnd + lane) % (JN - 1); q_ = (rnd + JN - 1 - lane) % (JN - 1); }
+        if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
+        const double apq = A[p_ * JLD + q_], app = A[p_ * JLD + p_], aqq = A[q_ * JLD + q_];
+        double c_ = 1.0, s_ = 0.0;
+        if (fabs(apq) > 1e-300 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq)) + 1e-300) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t_ = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c_ = 1.0 / sqrt(1.0 + t_ * t_);
+          s_ = t_ * c_;
+        }
+        cs[lane * 4 + 0] = c_; cs[lane * 4 + 1] = s_;
+        cs[lane * 4 + 2] = (double)p_; cs[lane * 4 + 3] = (double)q_;
+      }
+      __syncwarp();
+      // rows: A <- J' A   (lane = column)
+      for (int i = 0; i < PM; ++i) {
+        const double c_ = cs[i * 4], s_ = cs[i * 4 + 1];
+        const int p_ = (int)cs[i * 4 + 2], q_ = (int)cs[i * 4 + 3];
+        const double ap = A[p_ * JLD + lane], aq = A[q_ * JLD + lane];
+        A[p_ * JLD + lane] = c_ * ap - s_ * aq;
+        A[q_ * JLD + lane] = s_ * ap + c_ * aq;
+      }
+      __syncwarp();
+      // columns: A <- A J, Q <- Q J   (lane = row)
+      for (int i = 0; i < PM; ++i) {
+        const double c_ = cs[i * 4], s_ = cs[i * 4 + 1];
+        const int p_ = (int)cs[i * 4 + 2], q_ = (int)cs[i * 4 + 3];
+        const double ap = A[lane * JLD + p_], aq = A[lane * JLD + q_];
+        A[lane * JLD + p_] = c_ * ap - s_ * aq;
+        A[lane * JLD + q_] = s_ * ap + c_ * aq;
+        const double qp = Q[lane * JLD + p_], qq = Q[lane * JLD + q_];
+        Q[lane * JLD + p_] = c_ * qp - s_ * qq;
+        Q[lane * JLD + q_] = s_ * qp + c_ * qq;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// guarded Cholesky-QR factor of the PM x PM Gram matrix M (ld ZLD) by one warp.  Columns are equilibrated first
+// (M~ = D^-1 M D^-1, D = sqrt(diag M)) so that the guards do not depend on the relative scale of the columns: a column is
+// dropped when its squared norm is <= floor2 or when its pivot in M~ is <= piv_rel (nearly dependent on earlier columns).
+// Tm = D^-1 L~^-T with zero columns for dropped ones: P Tm is orthonormal on the kept columns.
+__device__ __forceinline__ void chol_guard_warp(double* M, double* Lm, double* Tm, int* valid, int lane, double piv_rel, double floor2,
+                                                int pcols, double rel_small = 0.0, int probe = -1) {
+  __shared__ double dscale[PM];
+  {
+    // a column is also dropped when its squared norm is <= rel_small * the largest one (the probe column is exempt and
+    // does not count for the largest)
+    const double d = (lane < PM) ? M[lane * ZLD + lane] : 0.0;
+    const double dmax = fmax(warp_max((lane < pcols && lane != probe) ? d : 0.0), 0.0);
+    if (lane < PM) {
+      const bool ok = (lane < pcols) && (d > floor2) && (d > 0.0) && (d > rel_small * dmax || lane == probe);
+      dscale[lane] = ok ? 1.0 / sqrt(d) : 0.0;
+    }
+  }
+  for (int e = lane; e < PM * ZLD; e += 32) { Lm[e] = 0.0; Tm[e] = 0.0; }
+  __syncwarp();
+  for (int e = lane; e < PM * PM; e += 32) {
+    const int i = e >> 4, j = e & 15;
+    M[i * ZLD + j] *= dscale[i] * dscale[j];
+  }
+  __syncwarp();
+  for (int j = 0; j < PM; ++j) {
+    double v = M[j * ZLD + j];
+    for (int c = 0; c < j; ++c) v -= Lm[j * ZLD + c] * Lm[j * ZLD + c];
+    const bool ok = (dscale[j] > 0.0) && (v > piv_rel);
+    if (lane == 0) valid[j] = ok ? 1 : 0;
+    if (ok) {
+      const double d = sqrt(v);
+      if (lane > j && lane < PM) {
+        double sacc = M[lane * ZLD + j];
+        for (int c = 0; c < j; ++c) sacc -= Lm[lane * ZLD + c] * Lm[j * ZLD + c];
+        Lm[lane * ZLD + j] = sacc / d;
+      }
+      if (lane == j) Lm[j * ZLD + j] = d;
+    } else {
+      if (lane == j) Lm[j * ZLD + j] = 1.0;       // dropped column: unit pivot, zero column
+    }
+    __syncwarp();
+  }
+  for (int j = 0; j < PM; ++j) {
+    if (!valid[j]) for (int c = lane; c < j; c += 32) Lm[j * ZLD + c] = 0.0;
+  }
+  __syncwarp();
+  // L~inv by forward substitution, one column per lane; Tm[c][i] = dscale[c] * L~inv[i][c]
+  if (lane < PM) {
+    const int cidx = lane;
+    double x[PM];
+#pragma unroll
+    for (int i = 0; i < PM; ++i) {
+      double sacc = (i == cidx) ? 1.0 : 0.0;
+#pragma unroll
+      for (int c = 0; c < PM; ++c) if (c < i) sacc -= Lm[i * ZLD + c] * x[c];
+      x[i] = (i >= cidx) ? sacc / Lm[i * ZLD + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < PM; ++i) Tm[cidx * ZLD + i] = (valid[i] && valid[cidx]) ? dscale[cidx] * x[i] : 0.0;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) k_rr(BigArgs a) {
+  __shared__ double A[JN * JLD];
+  __shared__ double Q[JN * JLD];
+  __shared__ double M[PM * ZLD], Lm[PM * ZLD], Tm[PM * ZLD], X0[PM * ZLD], C0[PM * ZLD], Hh[PM * ZLD];
+  __shared__ double cs[PM * 4];
+  __shared__ double lam[JN];
+  __shared__ int valid[PM], sel[PM];
+  const Layout& L = a.L;
+  const int b = blockIdx.y;
+  const int slot = a.active[blockIdx.x];
+  int* NI = node_int(a, slot);
+  if (a.step > 0 && !NI[I_MORE + b]) return;
+  double* S = node_ptr(a, slot);
+  const int lane = threadIdx.x, p = L.p[b];
+  // Gram matrices: M was reduced and stored in Q-area slot by k_chol? (no: reduce here) -- partials layout:
+  //   after k_resid(pass 1): partA = R'R per tile;   after k_prod(which 1): partA = Z'W2, partB = R'W2.
+  // k_prod overwrites partA, so M is reduced by k_resid2's successor kernel k_gram (below) into L.Q[b] before k_prod runs.
+  for (int e = lane; e < PM * PM; e += 32) {
+    const int i = e >> 4, j = e & 15;
+    M[i * ZLD + j] = S[L.Q[b] + e];           // M saved by k_gram
+    double sx = 0.0, sc_ = 0.0;
+    for (int t = 0; t < L.nt[b]; ++t) {
+      sx += S[L.partA[b] + (size_t)t * PM * PM + e];
+      sc_ += S[L.partB[b] + (size_t)t * PM * PM + e];
+    }
+    X0[i * ZLD + j] = sx; C0[i * ZLD + j] = sc_;
+    Hh[i * ZLD + j] = S[L.H[b] + e];
+  }
+  __syncwarp();
+  // residual of the minority columns (before this step) and the scale of H
+  double res2 = 0.0, hs2 = 0.0;
+  if (lane < PM) {
+    if (lane < p - 1 && S[L.th[b] + lane] > 0.0) res2 = M[lane * ZLD + lane];   // (column p - 1 holds the probe)
+    double h = 0.0;
+    for (int i = 0; i < PM; ++i) h += Hh[i * ZLD + lane] * Hh[i * ZLD + lane];
+    hs2 = h;
+  }
+  res2 = warp_sum(res2); hs2 = warp_max(hs2);
+  chol_guard_warp(M, Lm, Tm, valid, lane, 1e-10, 1e-20 * hs2, p, 1e-10, (p > 1) ? p - 1 : -1);
+  // A = [[sym(H), X0 T], [., T' C0 T]]
+  for (int e = lane; e < JN * JLD; e += 32) { A[e] = 0.0; Q[e] = 0.0; }
+  __syncwarp();
+  for (int e = lane; e < PM * PM; e += 32) {
+    const int i = e >> 4, j = e & 15;
+    A[i * JLD + j] = 0.5 * (Hh[i * ZLD + j] + Hh[j * ZLD + i]);
+    double s = 0.0;
+    for (int c = 0; c < PM; ++c) s = fma(X0[i * ZLD + c], Tm[c * ZLD + j], s);     // (X0 T)[i][j], T[c][j] = Tm[c][j]
+    A[i * JLD + PM + j] = s; A[(PM + j) * JLD + i] = s;
+  }
+  __syncwarp();
+  // C = T' C0 T: first Y = C0 T into M (reuse), then T' Y
+  for (int e = lane; e < PM * PM; e += 32) {
+    const int i = e >> 4, j = e & 15;
+    double s = 0.0;
+    for (int c = 0; c < PM; ++c) s = fma(C0[i * ZLD + c], Tm[c * ZLD + j], s);
+    M[i * ZLD + j] = s;
+  }
+  __syncwarp();
+  for (int e = lane; e < PM * PM; e += 32) {
+    const int i = e >> 4, j = e & 15;
+    double s = 0.0;
+    for (int c = 0; c < PM; ++c) s = fma(Tm[c * ZLD + i], M[c * ZLD + j], s);
+    X0[i * ZLD + j] = s;
+  }
+  __syncwarp();
+  double amax = 0.0;
+  for (int e = lane; e < PM * PM; e += 32) {
+    const int i = e >> 4, j = e & 15;
+    A[(PM + i) * JLD + PM + j] = 0.5 * (X0[i * ZLD + j] + X0[j * ZLD + i]);
+  }
+  __syncwarp();
+  for (int e = lane; e < JN * JN; e += 32) amax = fmax(amax, fabs(A[(e / JN) * JLD + (e % JN)]));
+  amax = warp_max(amax);
+  const double big = 64.0 * (amax + 1.0);
+  // dead columns of Z (index >= p) and dropped residual columns sink to the bottom of the spectrum
+  if (lane < PM) {
+    if (lane >= p) {
+      for (int c = 0; c < JN; ++c) { A[lane * JLD + c] = 0.0; A[c * JLD + lane] = 0.0; }
+    }
+  }
+  __syncwarp();
+  if (lane < PM) {
+    if (!valid[lane]) {
+      for (int c = 0; c < JN; ++c) { A[(PM + lane) * JLD + c] = 0.0; A[c * JLD + PM + lane] = 0.0; }
+    }
+  }
+  __syncwarp();
+  if (lane < PM) {
+    if (lane >= p) A[lane * JLD + lane] = -big;
+    if (!valid[lane]) A[(PM + lane) * JLD + PM + lane] = -big;
+  }
+  Q[lane * JLD + lane] = 1.0;
+  __syncwarp();
+  jacobi_warp(A, Q, lane, cs);
+  lam[lane] = A[lane * JLD + lane];
+  __syncwarp();
+  // rank by value (descending, ties by index)
+  {
+    const double li = lam[lane];
+    int rank = 0;
+    for (int j = 0; j < JN; ++j) rank += (lam[j] > li || (lam[j] == li && j < lane)) ? 1 : 0;
+    if (rank < PM) sel[rank] = lane;
+  }
+  __syncwarp();
+  // Q' (2 PM x PM): column c = eigenvector sel[c], sign: largest-|.| component positive; bottom half multiplied by T
+  double thn = -1e300;
+  if (lane < PM) {
+    const int c = lane, src = sel[c];
+    if (c < p) {
+      double best = 0.0, sg = 1.0;
+      for (int i = 0; i < JN; ++i) {
+        const double v = Q[i * JLD + src];
+        if (fabs(v) > best) { best = fabs(v); sg = (v < 0.0) ? -1.0 : 1.0; }
+      }
+      for (int i = 0; i < PM; ++i) S[L.Q[b] + (size_t)i * PM + c] = sg * Q[i * JLD + src];
+      for (int i = 0; i < PM; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < PM; ++j) s = fma(Tm[i * ZLD + j], Q[(PM + j) * JLD + src], s);
+        S[L.Q[b] + (size_t)(PM + i) * PM + c] = sg * s;
+      }
+      thn = lam[src];
+    } else {
+      for (int i = 0; i < JN; ++i) S[L.Q[b] + (size_t)i * PM + c] = 0.0;
+    }
+  }
+  double tn2 = (lane < p) ? thn * thn : 0.0;
+  tn2 = warp_sum(tn2);
+  int rpos = (lane < p && thn > 0.0) ? 1 : 0;
+  rpos = __reduce_add_sync(0xffffffffu, rpos);
+  if (lane < PM) S[L.th[b] + lane] = (lane < p) ? thn : -1e300;
+  if (lane == 0) {
+    const double res = sqrt(fmax(res2, 0.0)) / fmax(sqrt(tn2), 1e-300);
+    S[L.scal + S_RES + b] = res;
+    const int q = (a.step == 0) ? 1 : NI[I_Q + b] + 1;
+    NI[I_Q + b] = q;
+    NI[I_R + b] = rpos;
+    const int confirm = NI[I_CONFIRM] || (a.it >= a.o.max_iter);
+    const int ns = (a.it == 1) ? a.o.steps_start : 1;
+    const double tol = confirm ? a.o.confirm_tol : a.o.track_tol;
+    const int qmax = confirm ? a.o.steps_start : a.o.steps_max;
+    const bool stop = (q >= ns) && (res <= tol || q >= qmax);
+    NI[I_MORE + b] = stop ? 0 : 1;
+  }
+}
+
+// k_gram: M = sum over tiles of partB (R'R, written by k_resid pass 2) saved to L.Q[b] before k_prod(which = 1) reuses it.
+__global__ void __launch_bounds__(256) k_gram(BigArgs a) {
+  const Layout& L = a.L;
+  const int b = blockIdx.y;
+  const int slot = a.active[blockIdx.x];
+  const int* NI = node_int(a, slot);
+  if (a.step > 0 && !NI[I_MORE + b]) return;
+  double* S = node_ptr(a, slot);
+  double s = 0.0;
+  for (int t = 0; t < L.nt[b]; ++t) s += S[L.partB[b] + (size_t)t * PM * PM + threadIdx.x];
+  S[L.Q[b] + threadIdx.x] = s;
+}
+
+// k_update: Z <- Z Qtop + R Qbot, W <- W Qtop + W2 Qbot (rows of one tile, in place).
+__global__ void __launch_bounds__(256) k_update(BigArgs a) {
+  __shared__ double Qs[JN * ZLD];
+  __shared__ double Zs[TS * ZLD], Rs[TS * ZLD];
+  const Layout& L = a.L;
+  const int b = blockIdx.z;
+  if ((int)blockIdx.x >= L.nt[b]) return;
+  const int slot = a.active[blockIdx.y];
+  const int* NI = node_int(a, slot);
+  // NOTE: I_MORE was rewritten by k_rr for THIS step; the update must run for every (node, block) that ran the step,
+  // i.e. those with q advanced in this step: k_rr stores q; a block that did not run keeps MORE = 0 and q unchanged.
+  if (a.step > 0 && NI[I_Q + b] != a.step + 1) return;
+  double* S = node_ptr(a, slot);
+  const int N = L.N[b], tid = threadIdx.x, r0 = blockIdx.x * TS;
+  for (int e = tid; e < JN * PM; e += 256) Qs[(e >> 4) * ZLD + (e & 15)] = S[L.Q[b] + e];
+  for (int pass = 0; pass < 2; ++pass) {
+    double* A0 = S + (pass ? L.W[b] : L.Z[b]);
+    const double* A1 = S + (pass ? L.W2[b] : L.R[b]);
+    __syncthreads();
+    for (int e = tid; e < TS * PM; e += 256) {
+      const int row = e >> 4, col = e & 15;
+      const bool ok = r0 + row < N;
+      Zs[row * ZLD + col] = ok ? A0[(size_t)(r0 + row) * PM + col] : 0.0;
+      Rs[row * ZLD + col] = ok ? A1[(size_t)(r0 + row) * PM + col] : 0.0;
+    }
+    __syncthreads();
+    const int row = tid >> 2, cb = (tid & 3) * 4;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < PM; ++c) {
+      const double z = Zs[row * ZLD + c], r = Rs[row * ZLD + c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fma(z, Qs[c * ZLD + cb + q], fma(r, Qs[(PM + c) * ZLD + cb + q], acc[q]));
+    }
+    if (r0 + row < N) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) A0[(size_t)(r0 + row) * PM + cb + q] = acc[q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CholQR of a panel by one CTA (start bases, periodic re-orthonormalisation of Z): P <- P L^-T, twice if asked.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ void cholqr_cta(double* P, int N, int pcols, double* sm /* >= 4*PM*ZLD + 32 doubles */, int* ism /* PM ints */) {
+  double* M = sm; double* Lm = M + PM * ZLD; double* Tm = Lm + PM * ZLD; double* red = Tm + PM * ZLD;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  // Gram: thread (a, b) pairs strided over rows by row-groups
+  const int ai = (tid & 255) >> 4, bi = tid & 15;
+  double s = 0.0;
+  if (tid < 256) for (int i = 0; i < N; ++i) s = fma(P[(size_t)i * PM + ai], P[(size_t)i * PM + bi], s);
+  if (tid < 256) M[ai * ZLD + bi] = s;
+  __syncthreads();
+  if (tid < 32) chol_guard_warp(M, Lm, Tm, ism, tid, 1e-14, 0.0, pcols);
+  __syncthreads();
+  (void)red;
+  for (int i = tid; i < N; i += nthr) {
+    double row[PM], out[PM];
+#pragma unroll
+    for (int c = 0; c < PM; ++c) row[c] = P[(size_t)i * PM + c];
+#pragma unroll
+    for (int j = 0; j < PM; ++j) {
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < PM; ++c) v = fma(row[c], Tm[c * ZLD + j], v);
+      out[j] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < PM; ++c) P[(size_t)i * PM + c] = out[c];
+  }
+  __syncthreads();
+}
+
+
+// start bases of the three blocks (same for every node): base[b] = CholQR2(hash panel); block 2 carries the k unit vectors
+// of the identity corner first.  grid = 3.
+__global__ void __launch_bounds__(256) k_start_basis(Layout L, double* base0, double* base1, double* base2, int seed) {
+  __shared__ double sm[4 * PM * ZLD + 32];
+  __shared__ int ism[PM];
+  const int b = blockIdx.x;
+  double* P = (b == 0) ? base0 : ((b == 1) ? base1 : base2);
+  const int N = L.N[b], p = L.p[b], n = L.n;
+  const int q = (b == 1) ? (L.k < p ? L.k : p) : 0;
+  for (int e = threadIdx.x; e < N * PM; e += 256) {
+    const int i = e / PM, j = e - i * PM;
+    double v = (j < p) ? hash_unit((unsigned long long)i, (unsigned long long)j, (unsigned long long)(seed + b)) : 0.0;
+    if (b == 1) {
+      if (i >= n && i < n + q) v = 0.0;
+      if (j < q) v = (i == n + j) ? 1.0 : 0.0;
+    }
+    P[e] = v;
+  }
+  __syncthreads();
+  cholqr_cta(P, N, p, sm, ism);
+  cholqr_cta(P, N, p, sm, ism);
+}
+
+__global__ void __launch_bounds__(256) k_reorth(BigArgs a) {
+  __shared__ double sm[4 * PM * ZLD + 32];
+  __shared__ int ism[PM];
+  const Layout& L = a.L;
+  const int b = blockIdx.y;
+  const int slot = a.active[blockIdx.x];
+  const int* NI = node_int(a, slot);
+  const bool scheduled = (a.it % a.o.check_every == 0) || (a.it >= a.o.max_iter);
+  if (!scheduled && !NI[I_CONFIRM]) return;    // this node takes no part in an off-schedule check
+  double* S = node_ptr(a, slot);
+  cholqr_cta(S + L.Z[b], L.N[b], L.p[b], sm, ism);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// node setup: cut table (OMC.jl:1581-1676), gathered cut vectors, Gram matrix of the dense rows, cold
+// start (oracle/bigblock.py: BigState).  One CTA per node.
+// ------------------------------------------------------------------------------------------------------------------
+struct SetupArgs {
+  const double* pool_x; const double* pool_vhat;
+  const int* cut_ptr; const int* cut_ids; const unsigned char* cut_dirs;
+  const double* base[3];
+};
+
+__device__ __forceinline__ void cut_coeffs(int cut_type, int dir, double h, int fix3, double& lb, double& ub, double& al, double& be) {
+  const double ab = fabs(h);
+  if (cut_type == OMC_CUT_LINEAR) {
+    if (dir == 0) { lb = -1.0; ub = h; al = h - 1.0; be = h; }
+    else { lb = h; ub = 1.0; al = h + 1.0; be = -h; }
+  } else if (cut_type == OMC_CUT_LINEAR2) {
+    if (dir == 0) { lb = -1.0; ub = -ab; al = -(1.0 + ab); be = -ab; }
+    else if (dir == 1) { lb = -ab; ub = ab; al = 0.0; be = h * h; }
+    else { lb = ab; ub = 1.0; al = 1.0 + ab; be = -ab; }
+  } else {
+    if (dir == 0) { lb = -1.0; ub = -ab; al = -(1.0 + ab); be = -ab; }
+    else if (dir == 1) { lb = -ab; ub = 0.0; al = -ab; be = 0.0; }
+    else if (dir == 2) { lb = 0.0; ub = ab; al = ab; be = 0.0; }
+    else if (fix3) { lb = ab; ub = 1.0; al = 1.0 + ab; be = -ab; }
+    else { lb = ab; ub = 1.0; al = ab; be = 0.0; }          // OMC.jl:1675 (reference quirk Q1)
+  }
+}
+
+__global__ void __launch_bounds__(256) k_node_init(BigArgs a, SetupArgs sa_) {
+  extern __shared__ __align__(16) double sm[];   // XX [Lc][Lc]
+  const Layout& L = a.L;
+  const int slot = blockIdx.x;
+  double* S = node_ptr(a, slot);
+  int* NI = node_int(a, slot);
+  const int n = L.n, m = L.m, k = L.k, tid = threadIdx.x;
+  const int e0 = sa_.cut_ptr[slot], Lc = sa_.cut_ptr[slot + 1] - e0;
+  const int rq = 1 + Lc * (k + 1);
+  // (the record was zeroed by a memset on the host side)
+  for (int i = tid; i < k; i += 256) S[L.V[1] + (size_t)(n + i) * L.N[1] + n + i] = 1.0;    // E2
+  for (int i = tid; i < n; i += 256) S[L.V[2] + (size_t)i * n + i] = a.a;                   // a I
+  for (int b = 0; b < 3; ++b) {
+    for (int e = tid; e < L.N[b] * PM; e += 256) S[L.Z[b] + e] = sa_.base[b][e];
+    for (int c = tid; c < PM; c += 256) {
+      double th = (c < L.p[b]) ? 0.0 : -1e300;
+      if (b == 1 && c < k && c < L.p[b]) th = 1.0;
+      S[L.th[b] + c] = th;
+    }
+  }
+  // cuts
+  for (int e = tid; e < Lc * n; e += 256) {
+    const int l = e / n, i = e - l * n;
+    S[L.xs + e] = sa_.pool_x[(size_t)sa_.cut_ids[e0 + l] * n + i];
+  }
+  for (int e = tid; e < Lc * k; e += 256) {
+    const int l = e / k, j = e - l * k;
+    const double h = sa_.pool_vhat[(size_t)sa_.cut_ids[e0 + l] * k + j];
+    double lb, ub, al, be;
+    cut_coeffs(a.o.cut_type, sa_.cut_dirs[(size_t)(e0 + l) * k + j], h, a.o.fix_linear3_right, lb, ub, al, be);
+    S[L.clb + e] = a.sa * lb; S[L.cub + e] = a.sa * ub; S[L.cal + e] = a.sa * al;
+    S[L.rhs + e] = a.a * be;     // per-column beta, summed below
+  }
+  __syncthreads();
+  for (int l = tid; l < Lc; l += 256) {
+    double be = 0.0;
+    for (int j = 0; j < k; ++j) be += S[L.rhs + (size_t)l * k + j];
+    S[L.cbe + l] = be;
+  }
+  __syncthreads();
+  // v-form rows of a cold start: U = 0, Y = 0 -> vv = clip(0), vg = max(beta, 0)
+  for (int e = tid; e < Lc * k; e += 256) S[L.vv + e] = clampd(0.0, S[L.clb + e], S[L.cub + e]);
+  for (int l = tid; l < Lc; l += 256) S[L.vg + l] = fmax(S[L.cbe + l], 0.0);
+  // XX = x x'
+  for (int e = tid; e < Lc * Lc; e += 256) {
+    const int l1 = e / Lc, l2 = e - l1 * Lc;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s = fma(S[L.xs + (size_t)l1 * n + i], S[L.xs + (size_t)l2 * n + i], s);
+    sm[e] = s;
+  }
+  __syncthreads();
+  // G (rq x rq, ld rcap): rows/cols: 0 trace; 1 + l k + j: v_lj; 1 + L k + l: g_l
+  const int ld = L.rcap;
+  for (int e = tid; e < rq * rq; e += 256) {
+    const int r = e / rq, c = e - r * rq;
+    auto kind = [&](int q, int& l, int& j) { if (q == 0) return 0; if (q < 1 + Lc * k) { l = (q - 1) / k; j = (q - 1) - l * k; return 1; } l = q - 1 - Lc * k; j = 0; return 2; };
+    int l1 = 0, j1 = 0, l2 = 0, j2 = 0;
+    const int k1 = kind(r, l1, j1), k2 = kind(c, l2, j2);
+    double v = 0.0;
+    if (k1 == 0 && k2 == 0) v = (double)n;
+    else if (k1 == 0 && k2 == 2) v = sm[l2 * Lc + l2];
+    else if (k1 == 2 && k2 == 0) v = sm[l1 * Lc + l1];
+    else if (k1 == 1 && k2 == 1) v = (j1 == j2) ? sm[l1 * Lc + l2] : 0.0;
+    else if (k1 == 1 && k2 == 2) v = S[L.cal + (size_t)l2 * k + j1] * sm[l1 * Lc + l2];
+    else if (k1 == 2 && k2 == 1) v = S[L.cal + (size_t)l1 * k + j2] * sm[l1 * Lc + l2];
+    else if (k1 == 2 && k2 == 2) {
+      double s = 0.0;
+      for (int j = 0; j < k; ++j) s += S[L.cal + (size_t)l1 * k + j] * S[L.cal + (size_t)l2 * k + j];
+      const double xx = sm[l1 * Lc + l2];
+      v = s * xx + xx * xx;
+    }
+    S[L.G + (size_t)r * ld + c] = v;
+  }
+  if (tid == 0) {
+    S[L.scal + S_RHO] = a.o.rho0; S[L.scal + S_V4] = a.ktr; S[L.scal + S_CFAC] = 1.0;
+    S[L.scal + S_LB] = -1e300; S[L.scal + S_RP] = 1e300; S[L.scal + S_RD] = 1e300;
+    for (int q = 0; q < ISTR; ++q) NI[q] = 0;
+    NI[I_STATUS] = -1; NI[I_L] = Lc; NI[I_SLOT] = slot;
+  }
+  (void)m;
+}
+
+// Minv = ((sigma + 3 rho)/rho I + G)^-1 by Gauss-Jordan in global memory (one CTA per node; rebuilt when rho changes).
+__global__ void __launch_bounds__(256) k_minv(BigArgs a, int only_adapted) {
+  const Layout& L = a.L;
+  const int slot = a.active[blockIdx.x];
+  double* S = node_ptr(a, slot);
+  int* NI = node_int(a, slot);
+  if (only_adapted && !NI[I_ADAPTED]) return;
+  const int Lc = NI[I_L], k = L.k, rq = 1 + Lc * (k + 1), ld = L.rcap, tid = threadIdx.x;
+  const double rho = S[L.scal + S_RHO];
+  const double dg = (a.o.sigma + 3.0 * rho) / rho;
+  double* M = S + L.Minv;
+  for (int e = tid; e < rq * rq; e += 256) {
+    const int r = e / rq, c = e - r * rq;
+    M[(size_t)r * ld + c] = S[L.G + (size_t)r * ld + c] + ((r == c) ? dg : 0.0);
+  }
+  __syncthreads();
+  for (int p = 0; p < rq; ++p) {
+    const double inv = 1.0 / M[(size_t)p * ld + p];
+    __syncthreads();
+    for (int j = tid; j < rq; j += 256) if (j != p) M[(size_t)p * ld + j] *= inv;
+    __syncthreads();
+    for (int e = tid; e < rq * rq; e += 256) {
+      const int i = e / rq, j = e - i * rq;
+      if (i != p && j != p) M[(size_t)i * ld + j] -= M[(size_t)i * ld + p] * M[(size_t)p * ld + j];
+    }
+    __syncthreads();
+    for (int i = tid; i < rq; i += 256) if (i != p) M[(size_t)i * ld + p] *= -inv;
+    if (tid == 0) M[(size_t)p * ld + p] = inv;
+    __syncthreads();
+  }
+  if (tid == 0) NI[I_ADAPTED] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_check: residuals and objective pieces, per tile.  chk_part[tile][q]:
+//   0 rp (max), 1 rd (max), 2 n_p (max), 3 n_d (max), 4 sum Mk X^2, 5 sum Mk (X - A)^2, 6 tr T, 7 tr mu2 corner / rho,
+//   8 tr(F3) (-> a tr mu3 = -rho a tr F3), 9 box dual sum / rho.   rows_part gets the dense rows of the CURRENT (Y, U).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_check(BigArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const Layout& L = a.L;
+  const int slot = a.active[blockIdx.y];
+  double* S = node_ptr(a, slot);
+  const int* NI = node_int(a, slot);
+  const int n = L.n, m = L.m, k = L.k, N1 = L.N[0], N2 = L.N[1];
+  const int Lc = NI[I_L];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* Zi = sm;
+  double* Zj = Zi + 3 * TS * ZLD;
+  double* sc = Zj + 3 * TS * ZLD;
+  double* tb = sc + 3 * PM;
+  double* xi = tb + TS * (TS + 1);
+  double* xj = xi + (size_t)L.Lcap * TS;
+  double* mgs = xj + (size_t)L.Lcap * TS;   // [Lc] mg / rho
+  double* wred = mgs + L.Lcap + 1;          // [8][rcap]
+  double* red = wred + 8 * (size_t)L.rcap;  // [32]
+  const double rho = S[L.scal + S_RHO];
+  const int t = blockIdx.x;
+  const int nX = L.tn * L.tm, nT = L.tm * (L.tm + 1) / 2, nYt = L.tn * (L.tn + 1) / 2;
+  for (int e = threadIdx.x; e < 8 * L.rcap; e += 256) wred[e] = 0.0;
+  for (int b = 0; b < 3; ++b) {
+    if (threadIdx.x < PM) {
+      const double th = S[L.th[b] + threadIdx.x];
+      sc[b * PM + threadIdx.x] = (threadIdx.x < L.p[b] && th > 0.0) ? sqrt(th) : 0.0;
+    }
+  }
+  for (int l = threadIdx.x; l < Lc; l += 256) mgs[l] = S[L.vg + l] - fmax(S[L.vg + l], 0.0);
+  __syncthreads();
+  double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0, s8 = 0.0, s9 = 0.0;
+  double F[4][4];
+  double* part = S + L.chk_part + (size_t)t * NCHK;
+  if (t < nX) {
+    const int I = t / L.tm, J = t - I * L.tm, i0 = I * TS, j0 = J * TS;
+    stage_panel(Zi, S + L.Z[0], i0, n, sc);
+    stage_panel(Zj, S + L.Z[0] + (size_t)n * PM, j0, m, sc);
+    __syncthreads();
+    lowrank_tile(F, Zi, Zj, ty, tx);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = i0 + ty + 16 * r, j = j0 + tx + 16 * c;
+        if (i < n && j < m) {
+          const size_t e = (size_t)i * m + j;
+          const double x = S[L.X + e], mk = (double)a.Mk[e], am = a.AM[e];
+          const double mu = rho * (S[L.V[0] + (size_t)i * N1 + n + j] - F[r][c]);
+          rp = fmax(rp, fabs(x - F[r][c]));
+          np_ = fmax(np_, fabs(F[r][c]));
+          const double gX = -2.0 * mu;
+          rd = fmax(rd, fabs(mk * x - am - gX));
+          nd_ = fmax(nd_, fmax(fabs(mk * x), fmax(fabs(am), fabs(gX))));
+          s4 += mk * x * x;
+          const double d = mk * x - am;     // mk (x - A)
+          s5 += d * d;
+        }
+      }
+  } else if (t < nX + nT) {
+    int I, J;
+    lower_tile(t - nX, I, J);
+    const int i0 = I * TS, j0 = J * TS;
+    stage_panel(Zi, S + L.Z[0] + (size_t)n * PM, i0, m, sc);
+    stage_panel(Zj, S + L.Z[0] + (size_t)n * PM, j0, m, sc);
+    __syncthreads();
+    lowrank_tile(F, Zi, Zj, ty, tx);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = i0 + ty + 16 * r, j = j0 + tx + 16 * c;
+        if (i < m && j < m) {
+          const double tt = S[L.T + (size_t)i * m + j];
+          const double mu = rho * (S[L.V[0] + (size_t)(n + i) * N1 + n + j] - F[r][c]);
+          rp = fmax(rp, fabs(tt - F[r][c]));
+          np_ = fmax(np_, fabs(F[r][c]));
+          const double gT = -mu;
+          rd = fmax(rd, fabs(((i == j) ? a.cT : 0.0) - gT));
+          nd_ = fmax(nd_, fabs(gT));
+          if (i == j) s6 += tt;
+        }
+      }
+  } else if (t < nX + nT + nYt) {
+    int I, J;
+    lower_tile(t - nX - nT, I, J);
+    const int i0 = I * TS, j0 = J * TS;
+    for (int b = 0; b < 3; ++b) {
+      stage_panel(Zi + b * TS * ZLD, S + L.Z[b], i0, n, sc + b * PM);
+      stage_panel(Zj + b * TS * ZLD, S + L.Z[b], j0, n, sc + b * PM);
+    }
+    for (int e = threadIdx.x; e < Lc * TS; e += 256) {
+      const int l = e / TS, q = e - l * TS;
+      xi[l * TS + q] = (i0 + q < n) ? S[L.xs + (size_t)l * n + i0 + q] : 0.0;
+      xj[l * TS + q] = (j0 + q < n) ? S[L.xs + (size_t)l * n + j0 + q] : 0.0;
+    }
+    __syncthreads();
+    double F2[4][4], F3[4][4], yv[4][4];
+    lowrank_tile(F, Zi, Zj, ty, tx);
+    lowrank_tile(F2, Zi + TS * ZLD, Zj + TS * ZLD, ty, tx);
+    lowrank_tile(F3, Zi + 2 * TS * ZLD, Zj + 2 * TS * ZLD, ty, tx);
+    const double v4 = S[L.scal + S_V4];
+    const double m4 = rho * (v4 - fmax(v4, 0.0));
+    double trp = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int il = ty + 16 * r, jl = tx + 16 * c, i = i0 + il, j = j0 + jl;
+        yv[r][c] = 0.0;
+        if (i < n && j < n) {
+          const double y = S[L.Y + (size_t)i * n + j];
+          yv[r][c] = y;
+          const double V3 = S[L.V[2] + (size_t)i * n + j];
+          const double s3 = V3 + F3[r][c];
+          const double z3 = ((i == j) ? a.a : 0.0) - y;
+          rp = fmax(rp, fmax(fabs(y - F[r][c]), fmax(fabs(y - F2[r][c]), fabs(z3 - s3))));
+          np_ = fmax(np_, fmax(fabs(F[r][c]), fmax(fabs(F2[r][c]), fabs(s3))));
+          const double mu1 = rho * (S[L.V[0] + (size_t)i * N1 + j] - F[r][c]);
+          const double mu2 = rho * (S[L.V[1] + (size_t)i * N2 + j] - F2[r][c]);
+          const double mu3 = -rho * F3[r][c];
+          double g = -mu1 - mu2 + mu3 + ((i == j) ? m4 : 0.0);
+          for (int l = 0; l < Lc; ++l) g = fma(rho * mgs[l], xi[l * TS + il] * xj[l * TS + jl], g);
+          rd = fmax(rd, fabs(g));
+          nd_ = fmax(nd_, fabs(g));
+          if (i == j) { s8 += F3[r][c]; trp += y; }
+        }
+      }
+    const double wgt = (I != J) ? 2.0 : 1.0;
+    trp = warp_sum(trp);
+    if (lane == 0) wred[warp * L.rcap + 0] = trp;
+    for (int l = 0; l < Lc; ++l) {
+      double q = 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q = fma(xi[l * TS + ty + 16 * r] * xj[l * TS + tx + 16 * c], yv[r][c], q);
+      q = warp_sum(q);
+      if (lane == 0) wred[warp * L.rcap + 1 + Lc * k + l] = wgt * q;
+    }
+    __syncthreads();
+    double* rpart = S + L.rows_part + (size_t)(t - nX - nT) * L.rcap;
+    for (int q = threadIdx.x; q < 1 + Lc * (k + 1); q += 256) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += wred[w * L.rcap + q];
+      rpart[q] = s;
+    }
+  } else {
+    const int ut = t - nX - nT - nYt;
+    const int i0 = ut * TS;
+    stage_panel(Zi, S + L.Z[1], i0, n, sc + PM);
+    for (int e = threadIdx.x; e < k * PM; e += 256) {
+      const int j = e / PM, c = e - j * PM;
+      Zj[j * ZLD + c] = S[L.Z[1] + (size_t)(n + j) * PM + c] * sc[PM + c];
+    }
+    for (int e = threadIdx.x; e < Lc * TS; e += 256) {
+      const int l = e / TS, q = e - l * TS;
+      xi[l * TS + q] = (i0 + q < n) ? S[L.xs + (size_t)l * n + i0 + q] : 0.0;
+    }
+    __syncthreads();
+    const double sa = a.sa;
+    for (int e = threadIdx.x; e < TS * k; e += 256) {
+      const int il = e / k, j = e - il * k, i = i0 + il;
+      double u = 0.0;
+      if (i < n) {
+        double Fv = 0.0;
+        for (int c = 0; c < PM; ++c) Fv = fma(Zi[il * ZLD + c], Zj[j * ZLD + c], Fv);
+        u = S[L.U + (size_t)i * k + j];
+        const double v5 = S[L.v5 + (size_t)i * k + j];
+        const double lo5 = (i >= n - k + j) ? 0.0 : -sa;
+        const double s5v = clampd(v5, lo5, sa);
+        const double m5 = rho * (v5 - s5v);
+        const double mu2 = rho * (S[L.V[1] + (size_t)i * N2 + n + j] - Fv);
+        rp = fmax(rp, fmax(fabs(u - Fv), fabs(u - s5v)));
+        np_ = fmax(np_, fmax(fabs(Fv), fabs(s5v)));
+        double g = -2.0 * mu2 - m5;
+        for (int l = 0; l < Lc; ++l) {
+          const double vv = S[L.vv + (size_t)l * k + j];
+          const double mv = rho * (vv - clampd(vv, S[L.clb + (size_t)l * k + j], S[L.cub + (size_t)l * k + j]));
+          g -= xi[l * TS + il] * (mv + rho * mgs[l] * S[L.cal + (size_t)l * k + j]);
+        }
+        rd = fmax(rd, fabs(g));
+        nd_ = fmax(nd_, fabs(g));
+        s9 += (m5 < 0.0) ? m5 * lo5 : m5 * sa;
+      }
+      tb[il * (TS + 1) + j] = u;
+    }
+    __syncthreads();
+    double* rpart = S + L.rows_part + (size_t)(nYt + ut) * L.rcap;
+    for (int e = threadIdx.x; e < Lc * k; e += 256) {
+      const int l = e / k, j = e - l * k;
+      double q = 0.0;
+      for (int il = 0; il < TS; ++il) q = fma(xi[l * TS + il], tb[il * (TS + 1) + j], q);
+      rpart[1 + l * k + j] = q;
+    }
+    if (threadIdx.x == 0) rpart[0] = 0.0;
+    for (int l = threadIdx.x; l < Lc; l += 256) rpart[1 + Lc * k + l] = 0.0;
+    if (ut == 0) {
+      // identity corner of block 2: z = delta, s = F, mu = rho (V - F)
+      for (int e = threadIdx.x; e < k * k; e += 256) {
+        const int i = e / k, j = e - i * k;
+        double Fv = 0.0;
+        for (int c = 0; c < PM; ++c) Fv = fma(Zj[i * ZLD + c], Zj[j * ZLD + c], Fv);
+        rp = fmax(rp, fabs(((i == j) ? 1.0 : 0.0) - Fv));
+        np_ = fmax(np_, fabs(Fv));
+        if (i == j) s7 += S[L.V[1] + (size_t)(n + i) * N2 + n + j] - Fv;
+      }
+    }
+  }
+  rp = block_max(rp, red); rd = block_max(rd, red); np_ = block_max(np_, red); nd_ = block_max(nd_, red);
+  s4 = block_sum(s4, red); s5 = block_sum(s5, red); s6 = block_sum(s6, red); s7 = block_sum(s7, red);
+  s8 = block_sum(s8, red); s9 = block_sum(s9, red);
+  if (threadIdx.x == 0) {
+    part[0] = rp; part[1] = rd; part[2] = np_; part[3] = nd_; part[4] = s4; part[5] = s5; part[6] = s6; part[7] = s7;
+    part[8] = s8; part[9] = s9;
+  }
+}
+
+// k_decide: one warp-CTA per node: reduce, decide, adapt rho.
+__global__ void __launch_bounds__(128) k_decide(BigArgs a, int* counters /* [0] active after, [1] confirm, [2] adapted */) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double red[32];
+  const Layout& L = a.L;
+  const int slot = a.active[blockIdx.x];
+  double* S = node_ptr(a, slot);
+  int* NI = node_int(a, slot);
+  const int k = L.k, n = L.n, m = L.m, Lc = NI[I_L], tid = threadIdx.x;
+  const int was_confirm = NI[I_CONFIRM];
+  const bool scheduled = (a.it % a.o.check_every == 0) || (a.it >= a.o.max_iter);
+  if (!scheduled && !was_confirm) {            // off-schedule check forced by another node: nothing to do for this one
+    if (tid == 0) atomicAdd(&counters[0], 1);
+    return;
+  }
+  const int rq = 1 + Lc * (k + 1);
+  double* R0 = sm;
+  for (int q = tid; q < rq; q += 128) {
+    double s = 0.0;
+    for (int t = 0; t < L.tilesYU; ++t) s += S[L.rows_part + (size_t)t * L.rcap + q];
+    R0[q] = s;
+  }
+  double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0, s8 = 0.0, s9 = 0.0;
+  for (int t = tid; t < L.tilesAll; t += 128) {
+    const double* p = S + L.chk_part + (size_t)t * NCHK;
+    rp = fmax(rp, p[0]); rd = fmax(rd, p[1]); np_ = fmax(np_, p[2]); nd_ = fmax(nd_, p[3]);
+  }
+  // sums in fixed order by one thread each (deterministic)
+  if (tid < 6) {
+    double s = 0.0;
+    for (int t = 0; t < L.tilesAll; ++t) s += S[L.chk_part + (size_t)t * NCHK + 4 + tid];
+    red[tid] = s;
+  }
+  __syncthreads();
+  s4 = red[0]; s5 = red[1]; s6 = red[2]; s7 = red[3]; s8 = red[4]; s9 = red[5];
+  __syncthreads();
+  const double rho = S[L.scal + S_RHO];
+  // scalar rows
+  double dsum = 0.0, bmax = 0.0;
+  for (int e = tid; e < Lc * k; e += 128) {
+    const double vv = S[L.vv + e], lb = S[L.clb + e], ub = S[L.cub + e];
+    const double sv = clampd(vv, lb, ub), mv = rho * (vv - sv);
+    rp = fmax(rp, fabs(R0[1 + e] - sv));
+    np_ = fmax(np_, fabs(sv));
+    dsum -= (mv < 0.0) ? mv * lb : mv * ub;
+  }
+  for (int l = tid; l < Lc; l += 128) {
+    const double vg = S[L.vg + l], sg = fmax(vg, 0.0), mg = rho * (vg - sg), be = S[L.cbe + l];
+    double zg = be - R0[1 + Lc * k + l];
+    for (int j = 0; j < k; ++j) zg += S[L.cal + (size_t)l * k + j] * R0[1 + l * k + j];
+    rp = fmax(rp, fabs(zg - sg));
+    np_ = fmax(np_, fmax(fabs(sg), fabs(be)));
+    bmax = fmax(bmax, fabs(be));
+    dsum += be * mg;
+  }
+  rp = block_max(rp, red); rd = block_max(rd, red); np_ = block_max(np_, red); nd_ = block_max(nd_, red);
+  dsum = block_sum(dsum, red);
+  if (tid != 0) return;
+  const double v4 = S[L.scal + S_V4], s4r = fmax(v4, 0.0), m4 = rho * (v4 - s4r);
+  rp = fmax(rp, fabs((a.ktr - R0[0]) - s4r));
+  np_ = fmax(np_, fmax(fabs(s4r), fmax(a.a, a.ktr)));
+  nd_ = fmax(nd_, a.cT);
+  const double dual = -0.5 * s4 + a.c0 + rho * s7 - rho * a.a * s8 + a.ktr * m4 + dsum - s9;
+  const double objp = 0.5 * s5 + a.cT * s6;
+  const double ub = (a.o.cutoff < 1e299) ? a.o.cutoff : 2.0 * fmax(fabs(objp), fabs(dual)) + 1.0;
+  auto w1 = [&](double trTb) { return (double)n * a.ktr + sqrt((double)n * m * a.ktr * trTb) + (double)m * trTb + (double)n * k * a.sa; };
+  const double bound = dual - rd * w1(ub / a.cT);
+  const double bound_c0 = dual - rd * w1(a.c0 / a.cT);
+  S[L.scal + S_RP] = rp; S[L.scal + S_RD] = rd; S[L.scal + S_OBJP] = objp; S[L.scal + S_OBJD] = dual;
+  S[L.scal + S_NP] = np_; S[L.scal + S_ND] = nd_;
+  NI[I_ITERS] = a.it;
+  NI[I_CONFIRM] = 0;
+  bool guard_ok = true;
+  double resmax = 0.0;
+  for (int b = 0; b < 3; ++b) { guard_ok = guard_ok && (NI[I_R + b] < L.p[b]); resmax = fmax(resmax, S[L.scal + S_RES + b]); }
+  // mu lies in the dual cone only when the trackers hold every eigenvalue of the minority side (a guard column is left) and
+  // are converged: the certified bound is reported from such checks only (it never decreases)
+  const bool tracked_ok = (was_confirm || a.it >= a.o.max_iter) && guard_ok && resmax <= 10.0 * a.o.confirm_tol;
+  if (tracked_ok) S[L.scal + S_LB] = fmax(S[L.scal + S_LB], bound);
+  int decision = -1;
+  if (!(fabs(objp) < 1e300 && fabs(dual) < 1e300 && rp < 1e300 && rd < 1e300)) {
+    NI[I_STATUS] = OMC_STATUS_NUMERICAL; NI[I_DONE] = 1;
+    return;
+  }
+  if (rp <= a.o.eps_abs + a.o.eps_rel * np_ && rd <= a.o.eps_abs + a.o.eps_rel * nd_) decision = OMC_STATUS_OPTIMAL;
+  else if (a.o.cutoff < 1e299 && bound > a.o.cutoff) decision = OMC_STATUS_CUTOFF;
+  else if (a.o.infeasible_by_bound && Lc > 0 && bound_c0 > a.c0 * (1.0 + 1e-9) + 1e-12) decision = OMC_STATUS_INFEASIBLE;
+  if (decision >= 0) {
+    if (tracked_ok || a.it >= a.o.max_iter) {
+      NI[I_STATUS] = tracked_ok ? decision : OMC_STATUS_ITERATION_LIMIT;
+      NI[I_DONE] = 1;
+      return;
+    }
+    NI[I_CONFIRM] = 1;
+    atomicAdd(&counters[0], 1);
+    atomicAdd(&counters[1], 1);
+    return;
+  }
+  if (a.it >= a.o.max_iter) { NI[I_STATUS] = OMC_STATUS_ITERATION_LIMIT; NI[I_DONE] = 1; return; }
+  atomicAdd(&counters[0], 1);
+  if (a.o.adapt_every > 0 && (a.it % a.o.adapt_every == 0)) {
+    const double ratio = sqrt((rp / fmax(np_, 1e-12)) / fmax(rd / fmax(nd_, 1e-12), 1e-30));
+    if (ratio > a.o.adapt_thresh || ratio < 1.0 / a.o.adapt_thresh) {
+      const double rho_new = fmin(fmax(rho * ratio, 1e-6), 1e6);
+      S[L.scal + S_CFAC] = rho / rho_new;
+      S[L.scal + S_RHO] = rho_new;
+      NI[I_ADAPTED] = 1;
+      atomicAdd(&counters[2], 1);
+    }
+  }
+}
+
+// k_rescale: after a rho change, mu stays: v <- s + cfac (v - s) on every cone row; eigenvectors are unchanged and the
+// Ritz values of the mu part scale by cfac.  grid (tiles of 64 rows of V_b, node, b); b = 3: scalar rows + theta.
+__global__ void __launch_bounds__(256) k_rescale(BigArgs a) {
+  __shared__ double sc[PM];
+  __shared__ double Zr[PM];
+  const Layout& L = a.L;
+  const int slot = a.active[blockIdx.y];
+  const int* NI = node_int(a, slot);
+  if (!NI[I_ADAPTED]) return;
+  double* S = node_ptr(a, slot);
+  const double cf = S[L.scal + S_CFAC];
+  const int b = blockIdx.z, tid = threadIdx.x;
+  if (b == 3) {
+    if (blockIdx.x != 0) return;
+    const int k = L.k, n = L.n, Lc = NI[I_L];
+    const double sa = a.sa;
+    if (tid == 0) { const double v4 = S[L.scal + S_V4], s4 = fmax(v4, 0.0); S[L.scal + S_V4] = s4 + cf * (v4 - s4); }
+    for (int e = tid; e < n * k; e += 256) {
+      const int i = e / k, j = e - i * k;
+      const double v = S[L.v5 + e], lo5 = (i >= n - k + j) ? 0.0 : -sa, s = clampd(v, lo5, sa);
+      S[L.v5 + e] = s + cf * (v - s);
+    }
+    for (int e = tid; e < Lc * k; e += 256) {
+      const double v = S[L.vv + e], s = clampd(v, S[L.clb + e], S[L.cub + e]);
+      S[L.vv + e] = s + cf * (v - s);
+    }
+    for (int l = tid; l < Lc; l += 256) { const double v = S[L.vg + l], s = fmax(v, 0.0); S[L.vg + l] = s + cf * (v - s); }
+    return;
+  }
+  if ((int)blockIdx.x >= L.nt[b]) return;
+  const int N = L.N[b];
+  if (tid < PM) { const double th = S[L.th[b] + tid]; sc[tid] = (tid < L.p[b] && th > 0.0) ? th : 0.0; }
+  __syncthreads();
+  // side +: V <- F + cf (V - F) = cf V + (1 - cf) F;   side - (b = 2): s = V + Fm -> V <- V + (1 - cf) Fm ... with mu/rho = -Fm:
+  //         V = s - Fm -> s - cf Fm = V + (1 - cf) Fm
+  const double cV = (b == 2) ? 1.0 : cf, cF = 1.0 - cf;
+  const int r0 = blockIdx.x * TS;
+  for (int row = r0; row < r0 + TS && row < N; ++row) {
+    __syncthreads();
+    if (tid < PM) Zr[tid] = S[L.Z[b] + (size_t)row * PM + tid] * sc[tid];
+    __syncthreads();
+    for (int c = tid; c < N; c += 256) {
+      double F = 0.0;
+#pragma unroll
+      for (int q = 0; q < PM; ++q) F = fma(Zr[q], S[L.Z[b] + (size_t)c * PM + q], F);
+      const size_t e = L.V[b] + (size_t)row * N + c;
+      S[e] = cV * S[e] + cF * F;
+    }
+  }
+}
+// theta after a rho change (separate tiny kernel so that k_rescale reads the old values everywhere)
+__global__ void __launch_bounds__(64) k_rescale_theta(BigArgs a) {
+  const Layout& L = a.L;
+  const int slot = a.active[blockIdx.x];
+  const int* NI = node_int(a, slot);
+  if (!NI[I_ADAPTED]) return;
+  double* S = node_ptr(a, slot);
+  const double cf = S[L.scal + S_CFAC];
+  const int b = threadIdx.x / PM, c = threadIdx.x % PM;
+  if (b >= 3 || c >= L.p[b]) return;
+  const double th = S[L.th[b] + c];
+  // side +: positive Ritz values are s (unchanged), the others are mu / rho (scaled); side -: the other way round
+  if (b < 2) S[L.th[b] + c] = (th > 0.0) ? th : cf * th;
+  else S[L.th[b] + c] = (th > 0.0) ? cf * th : th;
+}
+
+// k_extract: results in the reference's layout (column-major X n x m, Y n x n, U n x k, unscaled).
+__global__ void __launch_bounds__(256) k_extract(BigArgs a, int B, double* outX, double* outY, double* outU, double* outT, int* status, int* iters,
+                                                 double* objective, double* lower_bound, double* res) {
+  const Layout& L = a.L;
+  const int slot = blockIdx.x;
+  if (slot >= B) return;
+  const double* S = node_ptr(a, slot);
+  const int* NI = node_int(a, slot);
+  const int n = L.n, m = L.m, k = L.k, tid = threadIdx.x;
+  if (outX) for (size_t e = tid; e < (size_t)n * m; e += 256) { const int j = e / n, i = e - (size_t)j * n; outX[(size_t)slot * n * m + e] = S[L.X + (size_t)i * m + j]; }
+  if (outY) for (size_t e = tid; e < (size_t)n * n; e += 256) outY[(size_t)slot * n * n + e] = S[L.Y + e] / a.a;
+  if (outU) for (size_t e = tid; e < (size_t)n * k; e += 256) { const int j = e / n, i = e - (size_t)j * n; outU[(size_t)slot * n * k + e] = S[L.U + (size_t)i * k + j] / a.sa; }
+  if (outT) for (size_t e = tid; e < (size_t)m * m; e += 256) outT[(size_t)slot * m * m + e] = S[L.T + e] * a.a;
+  if (tid == 0) {
+    const int st = NI[I_STATUS];
+    status[slot] = st;
+    iters[slot] = NI[I_ITERS];
+    lower_bound[slot] = S[L.scal + S_LB];
+    objective[slot] = (st == OMC_STATUS_CUTOFF) ? S[L.scal + S_LB] : S[L.scal + S_OBJP];
+    res[2 * slot] = S[L.scal + S_RP]; res[2 * slot + 1] = S[L.scal + S_RD];
+  }
+}
+
+}  // namespace omcbig

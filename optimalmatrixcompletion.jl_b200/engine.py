@@ -148,12 +148,14 @@ class Problem:
         return ptr, ids, dirs
 
     # ---- relaxation -----------------------------------------------------------------------
-    def frontier(self, node_cuts: List[List[Cut]], warm_ids=None, save_ids=None) -> "Frontier":
-        return Frontier(self, node_cuts, warm_ids, save_ids)
+    def frontier(self, node_cuts: List[List[Cut]], warm_ids=None, save_ids=None, engine: str = "auto") -> "Frontier":
+        return Frontier(self, node_cuts, warm_ids, save_ids, engine)
 
-    def relax_batch(self, node_cuts: List[List[Cut]], opts: Optional[RelaxOpts] = None, warm_ids=None, save_ids=None):
-        """Bodies of B calls of matrix_completion_SDP_relaxation (OMC.jl:1431-1943) in one launch."""
-        f = Frontier(self, node_cuts, warm_ids, save_ids)
+    def relax_batch(self, node_cuts: List[List[Cut]], opts: Optional[RelaxOpts] = None, warm_ids=None, save_ids=None,
+                    engine: str = "auto"):
+        """Bodies of B calls of matrix_completion_SDP_relaxation (OMC.jl:1431-1943) in one launch (engine "persistent")
+        or one lockstep run (engine "batched"); "auto" = batched when n + m > 104."""
+        f = Frontier(self, node_cuts, warm_ids, save_ids, engine)
         try:
             t0 = time.perf_counter()
             f.relax(opts)
@@ -178,7 +180,7 @@ class Problem:
 class Frontier:
     """A batch of open nodes resident in HBM (omc_frontier)."""
 
-    def __init__(self, problem: Problem, node_cuts, warm_ids=None, save_ids=None):
+    def __init__(self, problem: Problem, node_cuts, warm_ids=None, save_ids=None, engine: str = "auto"):
         self.p = problem
         self.B = len(node_cuts)
         ptr, ids, dirs = problem._flatten(node_cuts)
@@ -186,10 +188,27 @@ class Frontier:
         w = np.asarray(warm_ids, np.int32) if warm_ids is not None else None
         s = np.asarray(save_ids, np.int32) if save_ids is not None else None
         self.handle = C.c_void_p()
-        check(problem.lib.omc_frontier_create(problem.handle, self.B, _ptr(ptr, C.c_int32), _ptr(ids, C.c_int32),
-                                              _ptr(dirs, C.c_uint8), _ptr(w, C.c_int32), _ptr(s, C.c_int32),
-                                              C.byref(self.handle)))
+        check(problem.lib.omc_frontier_create_ex(problem.handle, self.B, _ptr(ptr, C.c_int32), _ptr(ids, C.c_int32),
+                                                 _ptr(dirs, C.c_uint8), _ptr(w, C.c_int32), _ptr(s, C.c_int32),
+                                                 _lib.ENGINES[engine], C.byref(self.handle)))
         self.kernel_ms = None
+
+    def stats(self) -> dict:
+        """omc_frontier_stats: engine, kernel launches, lockstep iterations, node-iterations, checks, rho changes, bytes per node."""
+        out = np.zeros(8, np.int64)
+        check(self.p.lib.omc_frontier_stats(self.handle, _ptr(out, C.c_int64)))
+        return dict(engine={1: "persistent", 2: "batched"}[int(out[0])], launches=int(out[1]), iterations=int(out[2]),
+                    node_iterations=int(out[3]), checks=int(out[4]), rho_changes=int(out[5]), node_bytes=int(out[6]))
+
+    def debug_fetch(self, node: int, which: int, cap: int) -> np.ndarray:
+        out = np.zeros(cap)
+        cnt = self.p.lib.omc_frontier_debug_fetch(self.handle, int(node), int(which), _ptr(out, C.c_double), int(cap))
+        if cnt < 0:
+            raise RuntimeError("omc_frontier_debug_fetch failed")
+        return out[:cnt]
+
+    def set_tuning(self, steps_max=0, steps_start=0, track_tol=0.0, confirm_tol=0.0):
+        check(self.p.lib.omc_frontier_set_tuning(self.handle, int(steps_max), int(steps_start), float(track_tol), float(confirm_tol)))
 
     def relax(self, opts: Optional[RelaxOpts] = None) -> float:
         ms = C.c_float()
@@ -217,7 +236,7 @@ class Frontier:
                 "status_code": int(status[b]),
                 "feasible": int(status[b]) != _lib.STATUS_INFEASIBLE,  # OMC.jl:1879, 1935
                 "objective": float(obj[b]),                           # OMC.jl:1882-1895
-                "lower_bound": float(lb[b]),
+                "lower_bound": float(lb[b]) if lb[b] > -1e299 else float("-inf"),   # no certified bound yet
                 "iters": int(iters[b]),
                 "res_p": float(res[2 * b]), "res_d": float(res[2 * b + 1]),
             }

@@ -51,8 +51,8 @@ def hash_panel(N, p, seed):
 
 def orthonormalize(Z):
     """CholQR twice (what the engine does: Gram, Cholesky, triangular solve; no Householder)."""
-    Q, _ = cholqr(Z)
-    Q, _ = cholqr(Q)
+    Q, _ = cholqr(Z, piv_rel=1e-14)
+    Q, _ = cholqr(Q, piv_rel=1e-14)
     return Q
 
 
@@ -60,23 +60,34 @@ def start_basis(N, p, seed):
     return orthonormalize(hash_panel(N, p, seed))
 
 
-def cholqr(R, piv_rel=1e-12):
-    """Cholesky-QR with a rank guard: a column whose pivot falls below piv_rel * max diag is dropped (zero column)."""
+def cholqr(R, piv_rel=1e-12, floor2=0.0, rel_small=0.0, probe=-1):
+    """Cholesky-QR with a rank guard on the column-equilibrated Gram matrix.  A column is dropped (zero column) when its
+    squared norm is <= floor2, or <= rel_small * (largest squared norm among the columns other than ``probe``), or when its
+    pivot in D^-1 R'R D^-1 falls below piv_rel (nearly dependent on earlier columns).  The ``probe`` column is exempt from
+    the rel_small rule."""
     p = R.shape[1]
     M = R.T @ R
-    dmax = max(float(np.diag(M).max()), 0.0)
+    d = np.diag(M).copy()
+    dres = d.copy()
+    if probe >= 0:
+        dres[probe] = 0.0
+    dmax = max(float(dres.max()), 0.0) if p else 0.0
+    colok = (d > floor2) & (d > 0.0) & ((d > rel_small * dmax) | (np.arange(p) == probe))
+    sc = np.where(colok, 1.0 / np.sqrt(np.where(colok, d, 1.0)), 0.0)
+    M = M * sc[:, None] * sc[None, :]
     L = np.zeros((p, p)); valid = np.ones(p, bool)
     for j in range(p):
         v = M[j, j] - L[j, :j] @ L[j, :j]
-        if not (v > piv_rel * dmax and v > 0.0):
+        if not (colok[j] and v > piv_rel):
             valid[j] = False
             L[j, j] = 1.0
             continue
         L[j, j] = np.sqrt(v)
         L[j + 1:, j] = (M[j + 1:, j] - L[j + 1:, :j] @ L[j, :j]) / L[j, j]
     L[:, ~valid] = 0.0
+    L[~valid, :] = 0.0
     L[~valid, ~valid] = 1.0
-    Rt = np.linalg.solve(L, np.where(valid, R, 0.0).T).T
+    Rt = np.linalg.solve(L, (np.where(valid, R, 0.0) * sc).T).T
     return np.where(valid, Rt, 0.0), valid
 
 
@@ -91,16 +102,33 @@ class Tracker:
         self.res = np.inf         # ||V Z - Z diag(theta)||_F of the last step (relative to ||theta||)
         self.nprod = 0
 
-    def step(self, V):
-        """One block-LOBPCG step on side * V.  Returns the relative Ritz residual before the step."""
+    def step(self, V, tag=0):
+        """One block-LOBPCG step on side * V.  Returns the relative Ritz residual before the step.  ``tag`` seeds the
+        pseudo-random probe that replaces the last residual column (it * 64 + step * 4 + block in the engine)."""
         Z, sd = self.Z, self.side
         W = sd * (V @ Z)
         H = Z.T @ W
         R = W - Z @ H
-        # Ritz residual of the columns that enter the projection (theta > 0); guard columns sit in the clustered part of
-        # the spectrum, converge slowly and do not matter
-        resid = float(np.linalg.norm(R[:, self.th > 0]))
-        Rt, valid = cholqr(R)                 # one Gram-Schmidt pass only; Z is re-orthonormalised at every residual check
+        pc = self.p - 1
+        if pc > 0:
+            # the trial space [Z, R] stays generic: an eigenvector exactly orthogonal to Z and to every residual (the identity
+            # corner of [Y U; U' I] at a node without cuts) would otherwise never be found again once it left the panel
+            amp = 1e-3 * np.sqrt(float((H * H).sum()) / self.N)
+            with np.errstate(over="ignore"):
+                R[:, pc] = amp * hash_unit(np.arange(self.N, dtype=np.uint64), np.uint64(tag), 12345)
+        # two explicit projections against Z ("twice is enough"): R = W - Z H carries a component (I - Z'Z) H along Z that
+        # can dwarf a converged residual column; one projection leaves (I - Z'Z) times it, which CholQR's normalisation then
+        # amplifies by ||H|| / ||R_col|| -- measured: orthonormality of Z lost within 20 iterations
+        R = R - Z @ (Z.T @ R)
+        R = R - Z @ (Z.T @ R)
+        cols = self.th > 0
+        if pc > 0:
+            cols = cols & (np.arange(self.p) != pc)       # (column p - 1 holds the probe)
+        resid = float(np.linalg.norm(R[:, cols]))
+        # dropped: residual columns below 1e-10 ||H|| (rounding noise), below 1e-5 of the largest residual column, or nearly
+        # dependent on earlier columns (equilibrated pivot below 1e-10)
+        hs2 = float((H * H).sum(axis=0).max())
+        Rt, valid = cholqr(R, piv_rel=1e-10, floor2=1e-20 * hs2, rel_small=1e-10, probe=pc if pc > 0 else -1)
         W2 = sd * (V @ Rt)
         self.nprod += 2
         p = self.p
@@ -110,7 +138,7 @@ class Tracker:
         C = Rt.T @ W2
         G[:p, p:] = Xc; G[p:, :p] = Xc.T
         G[p:, p:] = 0.5 * (C + C.T)
-        big = 1e3 * (np.abs(G).max() + 1.0)
+        big = 64.0 * (np.abs(G).max() + 1.0)
         for j in np.nonzero(~valid)[0]:         # dropped directions sink to the bottom of the spectrum
             G[p + j, :] = 0.0; G[:, p + j] = 0.0; G[p + j, p + j] = -big
         lam, Q = np.linalg.eigh(G)
@@ -218,14 +246,15 @@ def solve_relaxation_big(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, s
         st.X = al * Xt + (1 - al) * st.X; st.Y = al * Yt + (1 - al) * st.Y
         st.T = al * Tt + (1 - al) * st.T; st.U = al * Ut + (1 - al) * st.U
         # ---- tracker steps on the new arguments
-        for tr, V in ((t1, st.V1), (t2, st.V2), (t3, st.V3)):
+        for bidx, (tr, V) in enumerate(((t1, st.V1), (t2, st.V2), (t3, st.V3))):
             ns = o.steps_start if it == 1 else 1
-            tol = o.confirm_tol if confirm else o.track_tol
+            conf = confirm or it >= o.max_iter
+            tol = o.confirm_tol if conf else o.track_tol
             q = 0
             while True:
-                res = tr.step(V); q += 1
+                res = tr.step(V, it * 64 + q * 4 + bidx); q += 1
                 # res is the residual BEFORE the step: one more step measures the new basis only if asked for
-                if q >= ns and (res <= tol or q >= (o.steps_start if confirm else o.steps_max)):
+                if q >= ns and (res <= tol or q >= (o.steps_start if conf else o.steps_max)):
                     break
             nsteps_total += q
         if log is not None:
@@ -235,7 +264,7 @@ def solve_relaxation_big(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, s
             was_confirm = confirm
             confirm = False
             for t in st.tr:               # keep the tracked bases orthonormal over thousands of updates
-                t.Z, _ = cholqr(t.Z)
+                t.Z, _ = cholqr(t.Z, piv_rel=1e-14)
             s1 = t1.lowrank(); s2 = t2.lowrank(); s3 = st.V3 - t3.lowrank()
             s4 = max(st.v4, 0.0); s5 = np.clip(st.v5, c.lo, c.hi)
             sv = np.clip(st.vv, c.lb, c.ub); sg = np.maximum(st.vg, 0.0)
@@ -257,16 +286,18 @@ def solve_relaxation_big(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, s
             obj_p = 0.5 * float(np.sum(Mk * (st.X - A) ** 2)) + c.cT * float(np.trace(st.T))
             ub = o.cutoff if o.cutoff < 1e299 else 2.0 * max(abs(obj_p), abs(dual)) + 1.0
             w1 = lambda trTb: n * c.ktr + np.sqrt(n * m * c.ktr * trTb) + m * trTb + n * c.k * c.sa
-            bound = dual - rd * w1(ub / c.cT)
+            bound_now = dual - rd * w1(ub / c.cT)
             bound_c0 = dual - rd * w1(c.c0 / c.cT)
             guard_ok = all(t.r() < t.p for t in st.tr)
-            tracked_ok = was_confirm and guard_ok and max(t.res for t in st.tr) <= 10 * o.confirm_tol
+            tracked_ok = (was_confirm or it >= o.max_iter) and guard_ok and max(t.res for t in st.tr) <= 10 * o.confirm_tol
+            if tracked_ok:            # mu is in the dual cone only then: the certified bound comes from such checks only
+                bound = max(bound, bound_now)
             if o.verbose:
                 print(f"it {it:6d} rp {rp:.3e} rd {rd:.3e} rho {rho:.3e} r {[t.r() for t in st.tr]} res {[f'{t.res:.1e}' for t in st.tr]}")
             decision = None
             if rp <= o.eps_abs + o.eps_rel * n_p and rd <= o.eps_abs + o.eps_rel * n_d:
                 decision = STATUS_OPTIMAL
-            elif o.cutoff < 1e299 and bound > o.cutoff:
+            elif o.cutoff < 1e299 and bound_now > o.cutoff:
                 decision = STATUS_CUTOFF
             elif o.infeasible_by_bound and L > 0 and bound_c0 > c.c0 * (1.0 + 1e-9) + 1e-12:
                 decision = STATUS_INFEASIBLE
