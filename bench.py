@@ -1,26 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- nodes relaxed / second of the B200 bounding engine on BASELINE.json config 2.
+"""bench.py -- nodes relaxed / second of the B200 bounding engine.
 
-Workload ("config.workload"): k = 1, 50 x 50 noisy Gaussian low-rank data, 1250 observed entries, gamma = 80,
-linear cuts, smallest_1_eigvec breakpoints (README quick-start shape).  A *step* is one pass of the hot path --
-the fused per-node relaxation kernel (replaces matrix_completion_SDP_relaxation, OMC.jl:1431-1943) -- over one
-frontier batch of open branch-and-bound nodes, every node relaxed from a cold start to eps = 1e-8.
-The frontier is built once, untimed, by best-first disjunctive expansion from the root with the incumbent
-withheld (the config-2 instances certify optimality within 3 nodes, so a real run never holds a wide frontier).
+Workload ("config.workload", default BASELINE.json config 4 = the largest configuration whose 1184-node frontier fits one
+GPU; OMC_BENCH_CFG=C5 runs config 5's shape with a smaller per-GPU batch, OMC_BENCH_CFG=C2 the round-1 line):
+k = 3, 100 x 100 noisy Gaussian low-rank data, 3000 observed entries, gamma = 80, linear3 cuts, smallest_2_eigvec
+breakpoints.  A *step* is one pass of the hot path -- the relaxation of every node of one frontier batch of open
+branch-and-bound nodes (replaces matrix_completion_SDP_relaxation, OMC.jl:1431-1943), each from a cold start to
+eps = 1e-8 -- through the batched large-block engine (csrc/omc_big.cuh): the frontier advances in lockstep, one short
+kernel sequence per ADMM iteration.  The frontier is built once, untimed, by best-first disjunctive expansion from the
+root with the incumbent withheld.
 
-  value     nodes/s with the batch resident in HBM (CUDA events on the library's launch stream)
-  e2e       same through omc_relax_batch with pinned HOST buffers (descriptor H2D + result D2H inside the timing)
-  roofline  FP64: algorithmic flops of the PSD projections / kernel time against the measured DMMA peak
-  cpu_baseline / --impl reference: the CPU oracle (NumPy restatement of the same program; Mosek/Julia are not
-            installable here) on a bounded sample of the same kind of frontier.
+  value     nodes/s with the batch descriptors resident in HBM (CUDA events on the library's launch stream around the
+            whole lockstep run); only nodes that END the pass with a terminal status count (OPTIMAL / INFEASIBLE /
+            CUTOFF); nodes stopped by max_iter are reported in config.status_counts and do not count
+  e2e       same through omc_relax_batch with pinned HOST buffers (descriptor H2D + result D2H inside the timing), every step
+  roofline  HBM: algorithmic bytes of one lockstep iteration (every array of a node record that the iteration must read or
+            write once) x node-iterations / run time, against MEASURED_PEAKS.json's hbm_gbs
+  cpu_baseline / --impl reference: the CPU oracle (NumPy restatement of the same program, exact eigh projections; Mosek and
+            Julia are not installable here) on a bounded sample of the SAME frontier nodes.
 
-N > 1 (torchrun): the frontier of N*B nodes is sharded block-cyclically, one process per GPU, no data-path
-collective; the tiny [incumbent, min lower bound] all-reduce-min after each step goes over NCCL.
+N > 1 (torchrun): the frontier of N*B nodes is sharded block-cyclically, one process per GPU, no data-path collective; the
+tiny [incumbent, min lower bound] all-reduce-min after each step goes over NCCL.
 """
 import argparse
 import os as _os, sys as _sys
 if "reference" in _sys.argv:   # the oracle runs one node per process: keep BLAS single-threaded inside each
-    _os.environ.setdefault("OMP_NUM_THREADS", "1"); _os.environ.setdefault("OPENBLAS_NUM_THREADS", "1"); _os.environ.setdefault("MKL_NUM_THREADS", "1")  # OMC_REF_THREADS
+    _os.environ.setdefault("OMP_NUM_THREADS", "1"); _os.environ.setdefault("OPENBLAS_NUM_THREADS", "1"); _os.environ.setdefault("MKL_NUM_THREADS", "1")
 import ctypes as C
 import json
 import os
@@ -34,22 +39,43 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "C2: k=1, 50x50 noisy, 1250 observed, gamma=80, linear cuts, smallest_1_eigvec; frontier batch of open B&B nodes"
+CFG = os.environ.get("OMC_BENCH_CFG", "C4")
+CONFIGS = {   # (k, n, m, n_indices, cut type, nev, default nodes per GPU, max_iter)
+    "C2": dict(k=1, n=50, m=50, nidx=1250, ct="linear", nev=1, nodes=1184, max_iter=5000,
+               name="C2: k=1, 50x50 noisy, 1250 observed, gamma=80, linear cuts, smallest_1_eigvec"),
+    "C4": dict(k=3, n=100, m=100, nidx=3000, ct="linear3", nev=2, nodes=1184, max_iter=4000,
+               name="C4: k=3, 100x100 noisy, 3000 observed, gamma=80, linear3 cuts, smallest_2_eigvec"),
+    "C5": dict(k=5, n=1000, m=1000, nidx=200000, ct="linear", nev=1, nodes=32, max_iter=3000,
+               name="C5: k=5, 1000x1000, 20% observed, gamma=80, linear cuts, smallest_1_eigvec"),
+}
+W = CONFIGS[CFG]
+WORKLOAD = W["name"] + "; frontier batch of open B&B nodes"
 EPS = 1e-8
-MAX_ITER = int(os.environ.get("OMC_BENCH_MAX_ITER", "5000"))
-
-
-def f_proj(N):
-    return 16.0 / 3.0 * N ** 3          # tridiagonalise + back-transform + reconstruct
-
-
-def node_iter_flops(n, m, k, L):
-    return f_proj(n + m) + f_proj(n + k) + f_proj(n) + 2.0 * L * (n * n + n * k)
+MAX_ITER = int(os.environ.get("OMC_BENCH_MAX_ITER", str(W["max_iter"])))
+GAMMA = 80.0
+FIXTURE = os.path.join(ROOT, "tests", "golden", f"{CFG.lower()}_frontier_pool.json")
 
 
 def c2_instance(seed=0):
-    from omc_b200.synthetic import generate_matrix_completion_data  # host-side data generator of the package (not the oracle)
+    from omc_b200.synthetic import generate_matrix_completion_data
     return generate_matrix_completion_data(1, 50, 50, 1250, seed)
+
+
+def instance(seed=0):
+    from omc_b200.synthetic import generate_matrix_completion_data  # host-side data generator of the package (not the oracle)
+    return generate_matrix_completion_data(W["k"], W["n"], W["m"], W["nidx"], seed)
+
+
+def node_iteration_bytes(n, m, k, L):
+    """Algorithmic HBM bytes of ONE lockstep iteration of ONE node: every dense array of the node
+    record that the iteration has to read or write, counted once per read and once per write, FP64; the symmetric arrays
+    in the full storage the engine keeps.  X/Theta pass: X, Theta, V1[X], V1[X'], V1[Theta] read+write, mask*A read.
+    Y/U passes: Y, V1[Y], V2, V3 read+write, Y~ write+read.  Tracker (one step): V1, V2, V3 read twice (two panel products)."""
+    N1, N2 = n + m, n + k
+    xt = 2 * (n * m) + 2 * (m * m) + 3 * (n * m) + 2 * (m * m) + n * m          # X rw, T rw, V1 X-part r + 2w, V1 T-part rw, AM r
+    yu = 2 * (n * n) + 2 * (n * n) + 2 * (N2 * N2) + 2 * (n * n) + 2 * (n * n)  # Y rw, V1 Y-part rw, V2 rw, V3 rw, Y~ w+r
+    tr = 2 * (N1 * N1 + N2 * N2 + n * n)                                       # two panel products per tracker step
+    return 8.0 * (xt + yu + tr) + 8.0 * L * n * 4
 
 
 # -------------------------------------------------------------------------------------------------
@@ -83,24 +109,28 @@ class ClockSampler(threading.Thread):
 
 
 # -------------------------------------------------------------------------------------------------
-# frontier construction (untimed setup)
+# frontier construction (untimed setup) -- built ONCE for the whole job (rank 0 builds, every rank takes its shard)
 # -------------------------------------------------------------------------------------------------
-def build_frontier_gpu(problem, target, omc):
-    """Best-first expansion with the incumbent withheld: pop the 148 open nodes with the smallest bound, relax them
-    in one launch, branch on the separation oracle's eigenvector (master-feasible nodes are leaves)."""
+def build_frontier_gpu(problem, target, omc, cutoff=float("inf"), cfg=None):
+    """Best-first expansion: pop the open nodes with the smallest bound, relax them in one batch (with the incumbent as
+    cut-off, like the branch-and-bound loop), branch on the separation oracle's breakpoint vector (master-feasible nodes are
+    leaves, pruned nodes are dropped).  Returns the open BBNodes, best bound first."""
     from omc_b200.host import BBNode, JuliaPriorityQueue, create_matrix_cut_child_nodes
-    opts = omc.default_opts(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER)
+    from omc_b200.engine import LABELS
+    cfg = cfg or W
+    opts = omc.default_opts(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER, cutoff=cutoff)
     nodes = {1: BBNode(node_id=1, parent_id=0, LB=-np.inf, depth=0)}
     pq = JuliaPriorityQueue([(1, -np.inf)])
     counter = 1
+    per_split = len(LABELS[cfg["ct"]]) ** cfg["k"]
     while len(nodes) < target and len(pq):
-        room = max(1, (target - len(nodes)))           # every split adds (children - 1) open nodes
+        room = max(1, (target - len(nodes) + per_split - 2) // (per_split - 1))     # every split adds (children - 1) open nodes
         batch = [nodes.pop(pq.dequeue_pair()[0]) for _ in range(min(148, len(pq), room))]
         res = problem.relax_batch([nd.disjunctive_cuts for nd in batch], opts)
-        ok = [i for i, r in enumerate(res) if r["status_code"] == 0]
+        ok = [i for i, r in enumerate(res) if r["status_code"] == 0 and r["objective"] <= cutoff]
         if not ok:
             continue
-        lam, vec, bp, feas = omc.smallest_eigvecs_batch(np.stack([res[i]["Y"] for i in ok]), np.stack([res[i]["U"] for i in ok]), 1)
+        lam, vec, bp, feas = omc.smallest_eigvecs_batch(np.stack([res[i]["Y"] for i in ok]), np.stack([res[i]["U"] for i in ok]), cfg["nev"])
         for q, i in enumerate(ok):
             if feas[q] or batch[i].depth >= 60:
                 continue
@@ -109,17 +139,29 @@ def build_frontier_gpu(problem, target, omc):
             for kd in kids:
                 nodes[kd.node_id] = kd
                 pq.enqueue(kd.node_id, kd.LB)
-    out = sorted(nodes.values(), key=lambda nd: (nd.LB, nd.node_id))
-    return out[:target]
+    return sorted(nodes.values(), key=lambda nd: (nd.LB, nd.node_id))[:target]
 
 
 def load_frontier_fixture(limit=None):
-    """Cut descriptors of the first frontier nodes (tests/golden/c2_frontier.json, dumped by
-    scripts/dump_frontier_fixture.py): a list of oracle-style cut lists [(x, vhat, dirs), ...] per node."""
+    """Cut descriptors of the first config-2 frontier nodes (tests/golden/c2_frontier.json, round-1 format): a list of
+    oracle-style cut lists [(x, vhat, dirs), ...] per node."""
     with open(os.path.join(ROOT, "tests", "golden", "c2_frontier.json")) as f:
         fx = json.load(f)
     nodes = fx["nodes"][:limit] if limit else fx["nodes"]
     return [[(np.array(c["x"]), np.array(c["vhat"]), list(c["dirs"])) for c in nd["cuts"]] for nd in nodes]
+
+
+def load_frontier_pool(path=None, limit=None):
+    """The committed frontier of a configuration in pool form (scripts/dump_frontier_pool.py): the cuts of a tree are shared
+    (a split adds ONE cut to all its children), so the fixture stores every cut once and each node as (pool id, direction
+    codes) pairs.  Returns (list of oracle-style cut lists per node, incumbent objective)."""
+    from omc_b200.engine import LABELS
+    with open(path or FIXTURE) as f:
+        fx = json.load(f)
+    lab = LABELS[fx["cut_type"]]
+    pool = [(np.array(c[0]), np.array(c[1])) for c in fx["pool"]]
+    nodes = fx["nodes"][:limit] if limit else fx["nodes"]
+    return [[(pool[e[0]][0], pool[e[0]][1], [lab[d] for d in e[1:]]) for e in nd] for nd in nodes], float(fx["incumbent"])
 
 
 def _oracle_warm(_):
@@ -133,43 +175,50 @@ def _oracle_warm(_):
 
 def _oracle_worker(args):
     os.environ["OMP_NUM_THREADS"] = "1"
-    A, mask, gamma, k, cuts = args
-    from oracle import relaxation as R
-    r = R.solve_relaxation(A, mask, gamma, k, "linear", cuts, opts=R.Options(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER))
+    A, mask, gamma, k, ct, cuts, max_iter, cutoff = args
+    from oracle import bigblock as Bg
+    # exact-projection oracle has no cut-off rule; the restatement of the batched engine has the same rules as the GPU arm
+    r = Bg.solve_relaxation_big(A, mask, gamma, k, ct, cuts, opts=Bg.BigOptions(eps_abs=EPS, eps_rel=EPS, max_iter=max_iter,
+                                                                                infeasible_by_bound=True, cutoff=cutoff))
     return r["iters"], r["status"]
 
 
 # -------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the CPU restatement of the path (oracle port) on all host cores, bounded sample."""
+    """--impl reference: the CPU restatement of the path (oracle port, exact eigh projections) on all host cores, on a bounded
+    sample of the committed frontier fixture (the first nodes of the frontier the GPU arm relaxes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    A, mask = c2_instance(0)
+    A, mask = instance(0)
     sample = max(2, min(cores, 64))
-    t0 = time.time()
-    cuts = load_frontier_fixture(sample)
-    setup = time.time() - t0
-    jobs = [(A, mask, 80.0, 1, c) for c in cuts]
+    cuts, incumbent = load_frontier_pool(limit=sample * 4)
+    cuts = cuts[:: max(1, len(cuts) // sample)][:sample]            # spread over the first nodes of the frontier
+    jobs = [(A, mask, GAMMA, W["k"], W["ct"], c, MAX_ITER, incumbent) for c in cuts]
     ctx = mp.get_context("fork")
     with ctx.Pool(processes=min(cores, len(jobs))) as pool:
         pool.map(_oracle_warm, range(min(cores, len(jobs))))       # warm-up: import + LAPACK init in every worker
         t0 = time.perf_counter()
-        iters = 0
+        iters = 0; done = 0; steps_done = 0
         for _ in range(args.steps):
             res = pool.map(_oracle_worker, jobs)
-            iters += sum(r[0] for r in res)
+            iters += sum(r[0] for r in res); done += sum(1 for r in res if r[1] != 1); steps_done += 1
+            if time.perf_counter() - t0 > 240.0:                   # bounded: the whole run ends within a few minutes
+                break
         dt = time.perf_counter() - t0
-    value = len(jobs) * args.steps / dt
+    value = done / dt
     line = {"impl": "reference", "metric": "nodes relaxed/sec", "value": value, "unit": "nodes/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "steps": steps_done, "warmup": args.warmup, "ms_per_step": dt / steps_done * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "nodes_per_step": len(jobs), "eps": EPS, "max_iter": MAX_ITER,
-                       "note": "CPU restatement of the relaxation (NumPy/LAPACK ADMM), not Mosek: Julia and Mosek are absent"},
+                       "nodes_terminal_per_step": done / steps_done,
+                       "cutoff": incumbent,
+                       "note": "CPU restatement of the relaxation (NumPy/LAPACK, oracle/bigblock.py: same ADMM, same cut-off and infeasibility rules as the "
+                               "GPU arm), not Mosek: Julia and Mosek are absent; only nodes ending with a terminal status count, as in the GPU arm"},
             "cpu_baseline": {"value": value, "unit": "nodes/s", "cores": min(cores, len(jobs)), "kind": "port",
-                             "sample": f"first {len(jobs)} nodes of the config-2 frontier fixture x {args.steps} steps, {iters} ADMM iterations, one node per core"},
+                             "sample": f"first {len(jobs)} nodes of the {CFG} frontier fixture x {steps_done} steps, {iters} ADMM iterations, one node per core"},
             "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -188,18 +237,25 @@ def run_b200(args):
     omc = omc_b200
     omc.init(local)
     lib = omc._lib.load()
-    peaks = omc.measure_fp64_peak()
-    A, mask = c2_instance(0)
-    n, m, k = 50, 50, 1
-    problem = omc.Problem(k, A, mask, 80.0, "linear")
-    B = args.nodes
+    A, mask = instance(0)
+    n, m, k = W["n"], W["m"], W["k"]
+    problem = omc.Problem(k, A, mask, GAMMA, W["ct"])
+    B = args.nodes or W["nodes"]
+    # ---- the frontier: taken from the committed fixture when it holds enough nodes, else built ONCE on rank 0 and broadcast
     t0 = time.time()
-    frontier_nodes = build_frontier_gpu(problem, B * world, omc)
-    mine = omc.shard_block_cyclic(frontier_nodes, rank, world)
+    all_cuts, incumbent = load_frontier_pool()
+    if len(all_cuts) < B * world:
+        raise SystemExit(f"the committed frontier holds {len(all_cuts)} nodes, {B * world} asked (scripts/dump_frontier_pool.py builds a larger one)")
+    src = os.path.relpath(FIXTURE, ROOT)
+    if args.scaling == "strong":
+        all_cuts = all_cuts[: B]                                   # ONE fixed frontier of B nodes shared by all ranks
+    else:
+        all_cuts = all_cuts[: B * world]
+    mine = all_cuts[rank::world]                                   # block-cyclic shard of the one frontier
+    node_cuts = [[omc.Cut(problem.add_cut(x, vh), x, vh, d) for x, vh, d in cs] for cs in mine]
     setup_s = time.time() - t0
-    node_cuts = [nd.disjunctive_cuts for nd in mine]
     Bl = len(node_cuts)
-    opts = omc.default_opts(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER)
+    opts = omc.default_opts(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER, cutoff=incumbent)   # the incumbent prunes, as in the B&B loop
     fr = omc.Frontier(problem, node_cuts)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
     red = torch.zeros(2, dtype=torch.float64, device="cuda")
@@ -211,9 +267,9 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def step():
-        flush.fill_(1.0)                       # L2 flush between iterations
+        flush.fill_(1.0)                       # L2 flush between steps (the frontier state, 1.1 MB per node, also exceeds L2)
         torch.cuda.synchronize()
-        ms = fr.relax(opts)                    # CUDA events on the library stream bracket the fused kernel
+        ms = fr.relax(opts)                    # CUDA events on the library stream bracket the whole lockstep run
         if world > 1:                          # the path's only exchange: all-reduce-min of [incumbent, min LB]
             red[0] = 1e300; red[1] = 1e300
             dist.all_reduce(red, op=dist.ReduceOp.MIN)
@@ -229,12 +285,15 @@ def run_b200(args):
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
     out = fr.fetch(matrices=False)
-    iters = np.array([o["iters"] for o in out]); status = np.bincount([o["status_code"] for o in out], minlength=5)
+    stats = fr.stats()
+    iters = np.array([o["iters"] for o in out]); codes = np.array([o["status_code"] for o in out])
+    status = np.bincount(codes, minlength=6)
+    terminal = int(np.sum((codes == 0) | (codes == 2) | (codes == 4)))
     Ls = np.array([len(c) for c in node_cuts])
-    flops_step = float(sum(it * node_iter_flops(n, m, k, L) for it, L in zip(iters, Ls)))
+    bytes_step = float(sum(it * node_iteration_bytes(n, m, k, L) for it, L in zip(iters, Ls)))
     dev_ms = float(np.sum(kernel_ms)) / args.steps
 
-    # ---- e2e: host buffers through omc_relax_batch (pinned), H2D of descriptors + D2H of results inside the timing
+    # ---- e2e: host buffers through omc_relax_batch (pinned), H2D of descriptors + D2H of results inside the timing, every step
     ptr, ids, dirs = problem._flatten(node_cuts)
     pin = lambda t: t.pin_memory()
     h_ptr, h_ids, h_dirs = pin(torch.from_numpy(ptr.copy())), pin(torch.from_numpy(ids.copy())), pin(torch.from_numpy(dirs.copy()))
@@ -257,84 +316,76 @@ def run_b200(args):
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
+    for _ in range(args.steps):
         e2e_step()
     barrier()
-    e2e_wall = (time.perf_counter() - t0) / e2e_steps
-    print(f"[bench rank {rank}] kernel ms per step {[round(v) for v in kernel_ms]}, e2e wall ms per step {e2e_wall * 1e3:.0f}, e2e kernel iters {int(h_iters.sum())} vs {int(iters.sum())}", file=sys.stderr, flush=True)
+    e2e_wall = (time.perf_counter() - t0) / args.steps
+    print(f"[bench rank {rank}] device ms per step {[round(v) for v in kernel_ms]}, e2e wall ms per step {e2e_wall * 1e3:.0f}, "
+          f"terminal {terminal}/{Bl}, mean cuts/node {Ls.mean():.2f}, node-iterations {int(iters.sum())}, launches/step {stats['launches']}", file=sys.stderr, flush=True)
 
     # ---- max over ranks
     tmax = torch.tensor([dev_ms, wall / args.steps * 1e3, e2e_wall * 1e3], dtype=torch.float64, device="cuda")
-    tsum = torch.tensor([float(Bl), flops_step, float(iters.sum())], dtype=torch.float64, device="cuda")
+    tsum = torch.tensor([float(Bl), bytes_step, float(iters.sum()), float(terminal), float(Ls.sum())] + [float(v) for v in status[:6]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
     dev_ms_max, wall_ms_max, e2e_ms_max = [float(v) for v in tmax.tolist()]
-    total_nodes, total_flops, total_iters = [float(v) for v in tsum.tolist()]
+    ts = [float(v) for v in tsum.tolist()]
+    total_nodes, total_bytes, total_iters, total_terminal, total_cuts = ts[:5]
+    status_all = [int(v) for v in ts[5:11]]
 
     if rank == 0:
         # cpu_baseline: the oracle on one core, bounded sample of the same frontier (N = 1 only)
         cpu = None
         if world == 1 and not args.no_cpu:
-            from oracle import relaxation as R
-            t0 = time.perf_counter(); done = 0; cit = 0
-            sample_nodes = mine[:: max(1, len(mine) // 8)]
-            for nd in sample_nodes:
-                cuts = [(c.x, c.Uhat, c.directions) for c in nd.disjunctive_cuts]
-                r = R.solve_relaxation(A, mask, 80.0, k, "linear", cuts, opts=R.Options(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER))
-                done += 1; cit += r["iters"]
-                if time.perf_counter() - t0 > 20.0:
+            from oracle import bigblock as Bg
+            t0 = time.perf_counter(); done = 0; cit = 0; term = 0
+            stride = max(1, len(mine) // 6)
+            for cs in mine[::stride]:
+                r = Bg.solve_relaxation_big(A, mask, GAMMA, k, W["ct"], cs, opts=Bg.BigOptions(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER,
+                                                                                                infeasible_by_bound=True, cutoff=incumbent))
+                done += 1; cit += r["iters"]; term += int(r["status"] != 1)
+                if time.perf_counter() - t0 > 25.0:
                     break
             dt = time.perf_counter() - t0
-            cpu = {"value": done / dt, "unit": "nodes/s", "cores": 1, "kind": "port",
-                   "sample": f"{done} nodes of the same frontier (every {max(1, len(mine) // 8)}th), {cit} ADMM iterations, {dt:.1f} s; NumPy/LAPACK restatement, not Mosek"}
+            cpu = {"value": term / dt, "unit": "nodes/s", "cores": 1, "kind": "port",
+                   "sample": f"{done} nodes of the same frontier (every {stride}th), {term} reached a terminal status, {cit} ADMM iterations, {dt:.1f} s; "
+                             "NumPy/LAPACK restatement of the same ADMM (oracle/bigblock.py), not Mosek"}
         secondary = None
-        if world == 1:
-            # the other two parts of BASELINE.json's metric, measured outside the timed region:
-            # wall time of the whole branch-and-bound to gap <= 1e-4 on config 2, and alt-min sweeps/s on config 5's shape
-            t0 = time.perf_counter()
-            sol, _, inst = omc.matrix_completion_branchandbound(k, A, mask, 80.0, node_selection="bestfirst", disjunctive_cuts_type="linear",
-                                                                 disjunctive_cuts_breakpoints="smallest_1_eigvec", time_limit=120, verbosity=0)
-            t_gap = time.perf_counter() - t0
-            from omc_b200.synthetic import generate_matrix_completion_data
-            A5, m5 = generate_matrix_completion_data(5, 1000, 1000, 200000, 0)
-            p5 = omc.Problem(5, A5, m5, 80.0, "linear")
-            U5 = np.linalg.svd(np.where(m5, A5, 0.0))[0][:, :5]
-            am = omc.alternating_minimization(p5, U5)
-            # alt-min over a batch of restarts (OMC.jl:529-538: U_initial + max|U_initial| randn), one CTA per instance
-            rng5 = np.random.default_rng(0)
-            starts5 = [U5] + [U5 + np.abs(U5).max() * rng5.standard_normal(U5.shape) for _ in range(147)]
-            amb = omc.alternating_minimization_batch(p5, starts5, max_iters=20)
-            secondary = {"time_to_1e-4_gap_s": t_gap, "bnb_gap": inst["tree"].now_gap, "bnb_nodes_explored": inst["run_details"]["nodes_explored"],
-                         "bnb_objective": sol["objective"], "altmin_sweeps_per_s_c5": am["n_iters"] / max(am["solve_time"], 1e-9),
-                         "altmin_sweeps_per_s_c5_batch148": sum(r["n_iters"] for r in amb) / max(amb[0]["solve_time"], 1e-9),
-                         "altmin_c5": {"n_iters": am["n_iters"], "converged": am["converged"], "objective": am["objectives"][-1], "solve_time_s": am["solve_time"]}}
-            p5.close()
-        peak_tf = peaks["dmma_tflops"]
+        if world == 1 and not args.no_secondary:
+            secondary = secondary_metrics(omc)
+        peak = 6541.8
+        peak_src = "fallback of B200_PROFILING.md"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak = float(json.load(f)["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
         traffic = None
-        try:   # DRAM bytes per ADMM iteration from the committed ncu --set full capture of this kernel
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_relax_summary.json")) as f:
-                traffic = float(json.load(f)["dram_bytes_per_admm_iteration"]) * total_iters / max(1, world)
+        try:   # DRAM bytes per node-iteration from the committed ncu capture of the same workload (profiles/)
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_big_summary.json")) as f:
+                traffic = float(json.load(f)["dram_bytes_per_node_iteration"]) * total_iters / max(1, world)
         except Exception:
             traffic = None
-        achieved_tf = (flops_step / (dev_ms * 1e-3)) * 1e-12          # this rank's kernel
+        achieved = bytes_step / (dev_ms * 1e-3) * 1e-9            # this rank
         line = {
-            "metric": "nodes relaxed/sec", "value": total_nodes / (dev_ms_max * 1e-3), "unit": "nodes/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak",
+            "metric": "nodes relaxed/sec", "value": total_terminal / (dev_ms_max * 1e-3), "unit": "nodes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "nodes_per_gpu": Bl, "nodes_total": int(total_nodes), "eps": EPS, "max_iter": MAX_ITER,
-                       "start": "cold", "l2": "flushed between steps (256 MiB fill)", "parallelism": f"frontier sharded block-cyclically over {world} GPU(s)",
-                       "iters_per_node_mean": total_iters / total_nodes, "status_counts[opt,iterlim,infeas,time,cutoff]": status.tolist(),
-                       "frontier_setup_s": setup_s, "wall_ms_per_step": wall_ms_max},
-            "e2e": {"value": total_nodes / (e2e_ms_max * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": args.steps,
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
-                         "note": "FP64: algorithmic flops = iterations x 16/3 (N1^3+N2^3+N3^3) (+ cut rows) of the fused relaxation kernel (SURVEY 8d); the tracked "
-                                 "low-rank projection executes ~10x fewer flops than that and the kernel is bound by dependent-latency chains, not by the FP64 pipe "
-                                 "(DESIGN.md 4-5); peak = DMMA m8n8k4 FP64 "
-                                 f"measured in this run (DFMA {peaks['dfma_tflops']:.1f} TF); MEASURED_PEAKS.json carries no FP64 figure; traffic = DRAM bytes per launch "
-                                 "estimated as iterations x the per-iteration DRAM bytes of the committed ncu capture (profiles/r01_ncu_relax_summary.json)"},
+            "config": {"workload": WORKLOAD, "engine": stats["engine"], "nodes_per_gpu": Bl, "nodes_total": int(total_nodes),
+                       "nodes_terminal": int(total_terminal), "eps": EPS, "max_iter": MAX_ITER, "cutoff": incumbent,
+                       "start": "cold", "l2": "flushed between steps (256 MiB fill); frontier state exceeds L2", "frontier": src,
+                       "parallelism": f"one frontier of {int(total_nodes)} nodes sharded block-cyclically over {world} GPU(s)",
+                       "iters_per_node_mean": total_iters / total_nodes, "cuts_per_node_mean": total_cuts / total_nodes,
+                       "status_counts[opt,iterlim,infeas,time,cutoff,numerical]": status_all,
+                       "frontier_setup_s": setup_s, "wall_ms_per_step": wall_ms_max, "lockstep_iterations": stats["iterations"],
+                       "node_bytes": stats["node_bytes"]},
+            "e2e": {"value": total_terminal / (e2e_ms_max * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(stats["launches"]) * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "note": "batched engine, whole lockstep run (its kernels stream every node record once per pass): algorithmic bytes = node-iterations x "
+                                 f"{node_iteration_bytes(n, m, k, 0):.0f} B (+ cut vectors), DESIGN.md section 4b; peak = {peak_src}; traffic = DRAM bytes measured by ncu "
+                                 "per node-iteration (profiles/r02_ncu_big_summary.json) x node-iterations of this run"},
             "clocks": sampler.summary(),
         }
         if cpu is not None:
@@ -347,14 +398,44 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def secondary_metrics(omc):
+    """The other two parts of BASELINE.json's metric, measured outside the timed region: wall time of the whole branch-and-bound
+    to gap <= 1e-4 on config 2, and alt-min sweeps/s on config 5's shape."""
+    from omc_b200.synthetic import generate_matrix_completion_data
+    out = {}
+    try:
+        A2, m2 = generate_matrix_completion_data(1, 50, 50, 1250, 0)
+        t0 = time.perf_counter()
+        sol, _, inst = omc.matrix_completion_branchandbound(1, A2, m2, 80.0, node_selection="bestfirst", disjunctive_cuts_type="linear",
+                                                             disjunctive_cuts_breakpoints="smallest_1_eigvec", time_limit=120, verbosity=0)
+        out.update({"time_to_1e-4_gap_s_c2": time.perf_counter() - t0, "bnb_gap_c2": inst["tree"].now_gap,
+                    "bnb_nodes_explored_c2": inst["run_details"]["nodes_explored"], "bnb_objective_c2": sol["objective"]})
+        A5, m5 = generate_matrix_completion_data(5, 1000, 1000, 200000, 0)
+        p5 = omc.Problem(5, A5, m5, 80.0, "linear")
+        U5 = np.linalg.svd(np.where(m5, A5, 0.0))[0][:, :5]
+        am = omc.alternating_minimization(p5, U5)
+        rng5 = np.random.default_rng(0)
+        starts5 = [U5] + [U5 + np.abs(U5).max() * rng5.standard_normal(U5.shape) for _ in range(147)]
+        amb = omc.alternating_minimization_batch(p5, starts5, max_iters=20)
+        out.update({"altmin_sweeps_per_s_c5": am["n_iters"] / max(am["solve_time"], 1e-9),
+                    "altmin_sweeps_per_s_c5_batch148": sum(r["n_iters"] for r in amb) / max(amb[0]["solve_time"], 1e-9),
+                    "altmin_c5": {"n_iters": am["n_iters"], "converged": am["converged"], "objective": am["objectives"][-1], "solve_time_s": am["solve_time"]}})
+        p5.close()
+    except Exception as e:     # secondary numbers never take the headline down
+        out["error"] = repr(e)[:200]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nodes", type=int, default=1184, help="frontier nodes per GPU (8 x 148 SMs)")
+    ap.add_argument("--nodes", type=int, default=0, help="frontier nodes per GPU (default: 1184 = 8 x 148 SMs at config 4)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: one fixed frontier of --nodes nodes shared by all GPUs")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

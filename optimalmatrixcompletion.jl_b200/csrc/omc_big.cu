@@ -147,6 +147,7 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
   a.o.cutoff = ro->cutoff; a.o.max_iter = ro->max_iter; a.o.check_every = ro->check_every; a.o.adapt_every = ro->adapt_every;
   a.o.fix_linear3_right = ro->fix_linear3_right; a.o.cut_type = pv.cut_type;
   a.o.track_tol = tune->track_tol; a.o.confirm_tol = tune->confirm_tol; a.o.adapt_thresh = 5.0;
+  a.o.jacobi_sweeps = tune->jacobi_sweeps;
   a.o.steps_max = tune->steps_max; a.o.steps_start = tune->steps_start; a.o.infeasible_by_bound = tune->infeasible_by_bound;
   const auto t_start = std::chrono::steady_clock::now();
   BCU(cudaEventRecord(f->ev0, st));
@@ -284,6 +285,7 @@ int big_prepare_problem(int n, int m, const double* A, const double* Mk, double*
 }
 
 void big_default_tuning(BigTuning* t) {
+  t->jacobi_sweeps = 3;
   t->steps_max = 3; t->steps_start = 6; t->track_tol = 1e-3; t->confirm_tol = 1e-9; t->seed = 1; t->infeasible_by_bound = 1;
 }
 

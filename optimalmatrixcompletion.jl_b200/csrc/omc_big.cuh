@@ -90,7 +90,7 @@ inline Layout make_layout(int n, int m, int k, int Lcap) {
   L.n = n; L.m = m; L.k = k; L.Lcap = Lcap; L.rcap = 1 + Lcap * (k + 1);
   L.N[0] = n + m; L.N[1] = n + k; L.N[2] = n;
   for (int b = 0; b < 3; ++b) {
-    L.p[b] = L.N[b] / 2 < PM ? (L.N[b] / 2 > 0 ? L.N[b] / 2 : 1) : PM;
+    L.p[b] = L.N[b] < PM ? L.N[b] : PM;     // N <= PM: the panel is a complete eigenbasis and the projection is exact
     L.nt[b] = (L.N[b] + TS - 1) / TS;
   }
   L.tn = (n + TS - 1) / TS; L.tm = (m + TS - 1) / TS;
@@ -120,7 +120,7 @@ inline Layout make_layout(int n, int m, int k, int Lcap) {
 
 struct Opts {
   double eps_abs, eps_rel, sigma, alpha, rho0, cutoff, track_tol, confirm_tol, adapt_thresh;
-  int max_iter, check_every, adapt_every, steps_max, steps_start, fix_linear3_right, cut_type, infeasible_by_bound;
+  int max_iter, check_every, adapt_every, steps_max, steps_start, fix_linear3_right, cut_type, infeasible_by_bound, jacobi_sweeps;
 };
 
 struct BigArgs {
@@ -820,17 +820,24 @@ __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int JN = 2 * PM, JLD = JN + 1;
 
-__device__ __forceinline__ void jacobi_warp(double* A, double* Q, int lane, double* cs) {
-  // A: JN x JN symmetric (ld JLD), Q: eigenvector accumulator (identity on entry).  Round-robin ordering over JN players.
-  for (int sweep = 0; sweep < 12; ++sweep) {
-    double off = 0.0, dg = 0.0;
+// Cyclic Jacobi on the JN x JN symmetric matrix A (shared memory, ld JLD) by one warp; Q accumulates the rotations (identity
+// on entry).  Round-robin ordering: each round rotates PM disjoint pairs.  Per round the lanes < PM compute the rotation
+// of their pair; then every lane updates one column (rows phase) and one row (columns phase, also of Q) with all loads of
+// the phase issued before the first store, so that the shared-memory latency overlaps.  The rotations keep Q orthogonal
+// whatever the number of sweeps; the projected matrix is nearly diagonal once the tracker has locked on (off-diagonal =
+// Ritz residual), so `max_sweeps` = 3 resolves it to rounding there, and an unconverged start-phase Rayleigh-Ritz is
+// finished by the following tracker steps.
+__device__ __forceinline__ void jacobi_warp(double* A, double* Q, int lane, double* cs, int* pq, int max_sweeps, double dg_scale) {
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    double off = 0.0;
     for (int c = 0; c < JN; ++c) {
       const double v = A[lane * JLD + c];
-      if (c == lane) dg = fmax(dg, fabs(v)); else off = fmax(off, fabs(v));
+      if (c != lane) off = fmax(off, fabs(v));
     }
-    off = warp_max(off); dg = warp_max(dg);
-    if (off <= 1e-15 * dg || off < 1e-300) break;
+    off = warp_max(off);
+    if (off <= 1e-14 * dg_scale || off < 1e-300) break;
     for (int rnd = 0; rnd < JN - 1; ++rnd) {
+      int rot = 0;
       if (lane < PM) {
         int p_, q_;
         if (lane == 0) { p_ = JN - 1; q_ = rnd; }
@@ -838,35 +845,46 @@ __device__ __forceinline__ void jacobi_warp(double* A, double* Q, int lane, doub
         if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
         const double apq = A[p_ * JLD + q_], app = A[p_ * JLD + p_], aqq = A[q_ * JLD + q_];
         double c_ = 1.0, s_ = 0.0;
-        if (fabs(apq) > 1e-300 && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq)) + 1e-300) {
+        if (fabs(apq) > 1e-16 * dg_scale && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
           const double tau = (aqq - app) / (2.0 * apq);
           const double t_ = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c_ = 1.0 / sqrt(1.0 + t_ * t_);
+          c_ = rsqrt(1.0 + t_ * t_);
           s_ = t_ * c_;
+          rot = 1;
         }
-        cs[lane * 4 + 0] = c_; cs[lane * 4 + 1] = s_;
-        cs[lane * 4 + 2] = (double)p_; cs[lane * 4 + 3] = (double)q_;
+        cs[lane * 2 + 0] = c_; cs[lane * 2 + 1] = s_;
+        pq[lane * 2 + 0] = p_; pq[lane * 2 + 1] = q_;
       }
+      rot = __any_sync(0xffffffffu, rot);
       __syncwarp();
+      if (!rot) continue;
+      double ap[PM], aq[PM];
       // rows: A <- J' A   (lane = column)
+#pragma unroll
+      for (int i = 0; i < PM; ++i) { ap[i] = A[pq[2 * i] * JLD + lane]; aq[i] = A[pq[2 * i + 1] * JLD + lane]; }
+#pragma unroll
       for (int i = 0; i < PM; ++i) {
-        const double c_ = cs[i * 4], s_ = cs[i * 4 + 1];
-        const int p_ = (int)cs[i * 4 + 2], q_ = (int)cs[i * 4 + 3];
-        const double ap = A[p_ * JLD + lane], aq = A[q_ * JLD + lane];
-        A[p_ * JLD + lane] = c_ * ap - s_ * aq;
-        A[q_ * JLD + lane] = s_ * ap + c_ * aq;
+        const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
+        A[pq[2 * i] * JLD + lane] = c_ * ap[i] - s_ * aq[i];
+        A[pq[2 * i + 1] * JLD + lane] = s_ * ap[i] + c_ * aq[i];
       }
       __syncwarp();
       // columns: A <- A J, Q <- Q J   (lane = row)
+#pragma unroll
+      for (int i = 0; i < PM; ++i) { ap[i] = A[lane * JLD + pq[2 * i]]; aq[i] = A[lane * JLD + pq[2 * i + 1]]; }
+#pragma unroll
       for (int i = 0; i < PM; ++i) {
-        const double c_ = cs[i * 4], s_ = cs[i * 4 + 1];
-        const int p_ = (int)cs[i * 4 + 2], q_ = (int)cs[i * 4 + 3];
-        const double ap = A[lane * JLD + p_], aq = A[lane * JLD + q_];
-        A[lane * JLD + p_] = c_ * ap - s_ * aq;
-        A[lane * JLD + q_] = s_ * ap + c_ * aq;
-        const double qp = Q[lane * JLD + p_], qq = Q[lane * JLD + q_];
-        Q[lane * JLD + p_] = c_ * qp - s_ * qq;
-        Q[lane * JLD + q_] = s_ * qp + c_ * qq;
+        const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
+        A[lane * JLD + pq[2 * i]] = c_ * ap[i] - s_ * aq[i];
+        A[lane * JLD + pq[2 * i + 1]] = s_ * ap[i] + c_ * aq[i];
+      }
+#pragma unroll
+      for (int i = 0; i < PM; ++i) { ap[i] = Q[lane * JLD + pq[2 * i]]; aq[i] = Q[lane * JLD + pq[2 * i + 1]]; }
+#pragma unroll
+      for (int i = 0; i < PM; ++i) {
+        const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
+        Q[lane * JLD + pq[2 * i]] = c_ * ap[i] - s_ * aq[i];
+        Q[lane * JLD + pq[2 * i + 1]] = s_ * ap[i] + c_ * aq[i];
       }
       __syncwarp();
     }
@@ -940,7 +958,8 @@ __global__ void __launch_bounds__(32) k_rr(BigArgs a) {
   __shared__ double A[JN * JLD];
   __shared__ double Q[JN * JLD];
   __shared__ double M[PM * ZLD], Lm[PM * ZLD], Tm[PM * ZLD], X0[PM * ZLD], C0[PM * ZLD], Hh[PM * ZLD];
-  __shared__ double cs[PM * 4];
+  __shared__ double cs[PM * 2];
+  __shared__ int pq[PM * 2];
   __shared__ double lam[JN];
   __shared__ int valid[PM], sel[PM];
   const Layout& L = a.L;
@@ -1029,7 +1048,7 @@ __global__ void __launch_bounds__(32) k_rr(BigArgs a) {
   }
   Q[lane * JLD + lane] = 1.0;
   __syncwarp();
-  jacobi_warp(A, Q, lane, cs);
+  jacobi_warp(A, Q, lane, cs, pq, a.o.jacobi_sweeps, amax);
   lam[lane] = A[lane * JLD + lane];
   __syncwarp();
   // rank by value (descending, ties by index)
@@ -1643,7 +1662,7 @@ __global__ void __launch_bounds__(128) k_decide(BigArgs a, int* counters /* [0] 
   NI[I_CONFIRM] = 0;
   bool guard_ok = true;
   double resmax = 0.0;
-  for (int b = 0; b < 3; ++b) { guard_ok = guard_ok && (NI[I_R + b] < L.p[b]); resmax = fmax(resmax, S[L.scal + S_RES + b]); }
+  for (int b = 0; b < 3; ++b) { guard_ok = guard_ok && (NI[I_R + b] < L.p[b] || L.p[b] == L.N[b]); resmax = fmax(resmax, S[L.scal + S_RES + b]); }
   // mu lies in the dual cone only when the trackers hold every eigenvalue of the minority side (a guard column is left) and
   // are converged: the certified bound is reported from such checks only (it never decreases)
   const bool tracked_ok = (was_confirm || a.it >= a.o.max_iter) && guard_ok && resmax <= 10.0 * a.o.confirm_tol;

@@ -20,7 +20,7 @@ struct BigProblemView {
 };
 
 struct BigTuning {
-  int steps_max, steps_start, seed, infeasible_by_bound;
+  int steps_max, steps_start, seed, infeasible_by_bound, jacobi_sweeps;
   double track_tol, confirm_tol;
 };
 

@@ -96,7 +96,7 @@ class Tracker:
 
     def __init__(self, N, pm, side, seed, Z0=None, th0=None):
         self.N, self.side = N, side
-        self.p = p = min(pm, N // 2) if N >= 2 else 1
+        self.p = p = min(pm, N)          # N <= pm: the panel is a complete eigenbasis and the projection is exact
         self.Z = start_basis(N, p, seed) if Z0 is None else Z0.copy()
         self.th = np.zeros(p) if th0 is None else th0.copy()
         self.res = np.inf         # ||V Z - Z diag(theta)||_F of the last step (relative to ||theta||)
@@ -288,7 +288,7 @@ def solve_relaxation_big(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, s
             w1 = lambda trTb: n * c.ktr + np.sqrt(n * m * c.ktr * trTb) + m * trTb + n * c.k * c.sa
             bound_now = dual - rd * w1(ub / c.cT)
             bound_c0 = dual - rd * w1(c.c0 / c.cT)
-            guard_ok = all(t.r() < t.p for t in st.tr)
+            guard_ok = all(t.r() < t.p or t.p == t.N for t in st.tr)
             tracked_ok = (was_confirm or it >= o.max_iter) and guard_ok and max(t.res for t in st.tr) <= 10 * o.confirm_tol
             if tracked_ok:            # mu is in the dual cone only then: the certified bound comes from such checks only
                 bound = max(bound, bound_now)
