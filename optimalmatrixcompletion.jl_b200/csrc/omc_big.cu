@@ -69,8 +69,9 @@ int big_create(const BigProblemView& pv, int B, const int* node_cut_ptr, const i
   f->L = make_layout(pv.n, pv.m, pv.k, Lmax);
   const Layout& L = f->L;
   if (pv.k > PM) { g_berr = "large-block engine: k > 16 unsupported"; delete f; return -4; }
-  f->smem_y = ((size_t)6 * TS * ZLD + 3 * PM + TS * (TS + 1) + 2 * (size_t)L.Lcap * TS + L.Lcap + 1 + 8 * (size_t)L.rcap + 32) * sizeof(double);
-  f->smem_xt = ((size_t)2 * TS * ZLD + PM + TS * (TS + 1)) * sizeof(double);
+  f->smem_y = ((size_t)YOFF_X + 2 * (size_t)L.Lcap * TS + L.Lcap + 1 + 8 * (size_t)L.rcap + 32) * sizeof(double);
+  f->smem_xt = ((size_t)2 * TS * ZLD + PM + 8) * sizeof(double);
+  static_assert(2 * TS * ZLD >= TS * (TS + 1) && YOFF_SC >= TS * (TS + 1), "the transposition buffer aliases the panels");
   f->smem_small = (size_t)4 * L.rcap * sizeof(double);
   f->smem_init = (size_t)(Lmax * Lmax + 1) * sizeof(double);
   if (f->smem_y > 227 * 1024 || f->smem_init > 227 * 1024) {
@@ -116,6 +117,8 @@ int big_create(const BigProblemView& pv, int B, const int* node_cut_ptr, const i
   BCU(cudaFuncSetAttribute(k_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_y));
   BCU(cudaFuncSetAttribute(k_xt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_xt));
   BCU(cudaFuncSetAttribute(k_node_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_init));
+  BCU(cudaFuncSetAttribute(k_rr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM));
+  BCU(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM));
   BCU(cudaStreamSynchronize(st));
   f->h_int.resize((size_t)B * ISTR);
   *out = f;
@@ -177,7 +180,9 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
     k_y1<<<dim3(L.tilesYU, nact), 256, f->smem_y, st>>>(a);
     k_small<<<nact, 128, f->smem_small, st>>>(a);
     k_y2<<<dim3(L.tilesYU, nact), 256, f->smem_y, st>>>(a);
-    const int rounds = (it == 1 || force || it >= a.o.max_iter) ? a.o.steps_start : a.o.steps_max;
+    const bool check = (it % a.o.check_every == 0) || it >= a.o.max_iter;
+    // steps_start rounds at the first iteration and, when some node has a termination decision pending, in check iterations
+    const int rounds = (it == 1 || (check && force) || it >= a.o.max_iter) ? a.o.steps_start : a.o.steps_max;
     for (int s = 0; s < rounds; ++s) {
       a.step = s;
       if (s == 0) k_prod<<<dim3(ntmax, nact, 3), 128, 0, st>>>(a, 0);
@@ -186,13 +191,12 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
       k_resid<<<dim3(ntmax, nact, 3), 256, 0, st>>>(a, 2);
       k_gram<<<dim3(nact, 3), 256, 0, st>>>(a);
       k_prod<<<dim3(ntmax, nact, 3), 128, 0, st>>>(a, 1);
-      k_rr<<<dim3(nact, 3), 32, 0, st>>>(a);
-      k_update<<<dim3(ntmax, nact, 3), 256, 0, st>>>(a);
+      k_rr<<<dim3(nact, 3), 256, RR_SMEM, st>>>(a);
+      k_update<<<dim3(ntmax, nact, 3), 256, UPD_SMEM, st>>>(a);
       stt.launches += (s == 0) ? 8 : 7;
     }
     stt.launches += 4;
     stt.node_iterations += nact;
-    const bool check = (it % a.o.check_every == 0) || it >= a.o.max_iter || force;
     if (!check) continue;
     k_reorth<<<dim3(nact, 3), 256, 0, st>>>(a);
     BCU(cudaMemsetAsync(f->counters, 0, 8 * sizeof(int), st));
@@ -204,7 +208,7 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
     BCU(cudaGetLastError());
     if (h_cnt[2] > 0) {
       k_rescale<<<dim3(ntmax, nact, 4), 256, 0, st>>>(a);
-      k_rescale_theta<<<nact, 64, 0, st>>>(a);
+      k_rescale_theta<<<nact, 3 * PM, 0, st>>>(a);
       k_minv<<<nact, 256, 0, st>>>(a, 1);
       stt.launches += 3; stt.rho_changes += h_cnt[2];
     }

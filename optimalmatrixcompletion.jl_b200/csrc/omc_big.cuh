@@ -8,8 +8,8 @@
 //   v-form ADMM (COSMO/OSQP splitting of oracle/relaxation.py):  v <- v + alpha (z~ - P_K(v)),  mu = rho (v - P_K(v)).
 //   The projection of a PSD-block argument V_b is never formed: the minority spectral side of V_b (positive side of
 //   [Y X; X' Theta] and [Y U; U' I], negative side of aI - Y) is tracked as Z_b diag(theta_b) Z_b' with a panel of
-//   PM = 16 columns refined by block-LOBPCG steps on [Z, R] (R = residual of V Z, explicitly re-projected against Z),
-//   Rayleigh-Ritz on the 32 x 32 projected matrix by a warp-level cyclic Jacobi; every pass over V_b uses V_b and the factor.
+//   PM = 32 columns (16 for aI - Y) refined by block-LOBPCG steps on [Z, R] (R = residual of V Z, explicitly re-projected against Z),
+//   Rayleigh-Ritz on the 64 x 64 projected matrix by a CTA-parallel cyclic Jacobi; every pass over V_b uses V_b and the factor.
 //
 // Kernels (grid.y = active node, grid.z = PSD block where it applies):
 //   k_xt      X and Theta regions: w-update, v-update and w relaxation fused in one pass (these entries meet no dense row)
@@ -64,7 +64,8 @@ __device__ __forceinline__ double block_max(double v, double* scratch) {
   return warp_max(r);
 }
 
-constexpr int PM = 16;        // tracker panel width
+constexpr int PM = 32;        // tracker panel width (blocks 1 and 2)
+constexpr int P3 = 16;        // panel width of block 3 (negative side of aI - Y: a handful of eigenvalues)
 constexpr int TS = 64;        // region tile
 constexpr int NCHK = 16;      // per-tile partials of the residual check
 constexpr int ISTR = 32;      // ints per node
@@ -90,7 +91,8 @@ inline Layout make_layout(int n, int m, int k, int Lcap) {
   L.n = n; L.m = m; L.k = k; L.Lcap = Lcap; L.rcap = 1 + Lcap * (k + 1);
   L.N[0] = n + m; L.N[1] = n + k; L.N[2] = n;
   for (int b = 0; b < 3; ++b) {
-    L.p[b] = L.N[b] < PM ? L.N[b] : PM;     // N <= PM: the panel is a complete eigenbasis and the projection is exact
+    const int cap = (b == 2) ? P3 : PM;
+    L.p[b] = L.N[b] < cap ? L.N[b] : cap;   // N <= cap: the panel is a complete eigenbasis and the projection is exact
     L.nt[b] = (L.N[b] + TS - 1) / TS;
   }
   L.tn = (n + TS - 1) / TS; L.tm = (m + TS - 1) / TS;
@@ -154,37 +156,47 @@ __device__ __forceinline__ double hash_unit(unsigned long long i, unsigned long 
   return (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
 }
 
-// stage rows [row0, row0 + 64) of a panel (ld PM) into shared memory, column a scaled by sc[a] (sqrt(theta+) -> the low-rank
-// term becomes a plain inner product, bitwise symmetric in (i, j))
-__device__ __forceinline__ void stage_panel(double* dst, const double* __restrict__ P, int row0, int nrows, const double* sc) {
-  for (int e = threadIdx.x; e < TS * PM; e += blockDim.x) {
-    const int r = e / PM, c = e - r * PM;
+// stage the first nc columns of rows [row0, row0 + 64) of a panel (global ld PM) into shared memory (ld), column a scaled
+// by sc[a] (sqrt(theta+) -> the low-rank term becomes a plain inner product, bitwise symmetric in (i, j))
+__device__ __forceinline__ void stage_panel(double* dst, int ld, const double* __restrict__ P, int row0, int nrows, const double* sc, int nc) {
+  for (int e = threadIdx.x; e < TS * nc; e += blockDim.x) {
+    const int r = e / nc, c = e - r * nc;
     const int gr = row0 + r;
-    dst[r * ZLD + c] = (gr < nrows) ? P[(size_t)gr * PM + c] * sc[c] : 0.0;
+    dst[r * ld + c] = (gr < nrows) ? P[(size_t)gr * PM + c] * sc[c] : 0.0;
   }
 }
-__device__ __forceinline__ void lowrank_tile(double (&F)[4][4], const double* Zi, const double* Zj, int ty, int tx) {
+__device__ __forceinline__ void lowrank_tile(double (&F)[4][4], const double* Zi, const double* Zj, int ld, int nc, int ty, int tx) {
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) F[r][c] = 0.0;
 #pragma unroll 4
-  for (int a = 0; a < PM; ++a) {
+  for (int a = 0; a < nc; ++a) {
     double zi[4], zj[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) zi[r] = Zi[(ty + 16 * r) * ZLD + a];
+    for (int r = 0; r < 4; ++r) zi[r] = Zi[(ty + 16 * r) * ld + a];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) zj[c] = Zj[(tx + 16 * c) * ZLD + a];
+    for (int c = 0; c < 4; ++c) zj[c] = Zj[(tx + 16 * c) * ld + a];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) F[r][c] = fma(zi[r], zj[c], F[r][c]);
   }
 }
-// sqrt(max(theta, 0)) of a block's Ritz values into shared memory
-__device__ __forceinline__ void stage_scale(double* sc, const double* th, int p) {
+// sqrt(max(theta, 0)) of a block's Ritz values into shared memory; returns the number of leading columns that hold every
+// positive Ritz value (they are sorted in descending order by k_rr, so this is their count)
+__device__ __forceinline__ int stage_scale(double* sc, const double* th, int p) {
+  int nc = 0;
+  for (int a = 0; a < p; ++a) if (th[a] > 0.0) nc = a + 1;
   if (threadIdx.x < PM) sc[threadIdx.x] = (threadIdx.x < p && th[threadIdx.x] > 0.0) ? sqrt(th[threadIdx.x]) : 0.0;
+  return nc;
 }
+// shared-memory layout of the Y / U region kernels (doubles): panels of the three blocks (rows i and rows j), the scales,
+// a 64 x 17 tile for U; the transposition buffer of store_mirror aliases the panels (they are dead by then)
+constexpr int YLD2 = P3 + 1;
+constexpr int YOFF_I0 = 0, YOFF_J0 = TS * ZLD, YOFF_I1 = 2 * TS * ZLD, YOFF_J1 = 3 * TS * ZLD, YOFF_I2 = 4 * TS * ZLD,
+              YOFF_J2 = 4 * TS * ZLD + TS * YLD2, YOFF_SC = 4 * TS * ZLD + 2 * TS * YLD2, YOFF_UB = YOFF_SC + 3 * PM,
+              YOFF_X = YOFF_UB + TS * 17;
 // write the transpose of a register tile through shared memory: dst[(col0 + c) * ld + row0 + r] = v[r][c]
 __device__ __forceinline__ void store_mirror(double* __restrict__ dst, size_t ld, int row0, int col0, int nrows, int ncols,
                                              const double (&v)[4][4], double* tb, int ty, int tx) {
@@ -218,9 +230,9 @@ __global__ void __launch_bounds__(256) k_xt(BigArgs a) {
   double* S = node_ptr(a, slot);
   const int n = L.n, m = L.m, N1 = L.N[0];
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  double* Zi = sm; double* Zj = Zi + TS * ZLD; double* sc = Zj + TS * ZLD; double* tb = sc + PM;
+  double* Zi = sm; double* Zj = Zi + TS * ZLD; double* sc = Zj + TS * ZLD; double* tb = sm;   // (tb aliases the dead panels)
   const double rho = S[L.scal + S_RHO], sig = a.o.sigma, al = a.o.alpha;
-  stage_scale(sc, S + L.th[0], L.p[0]);
+  const int nc = stage_scale(sc, S + L.th[0], L.p[0]);
   __syncthreads();
   double* V1 = S + L.V[0];
   const int t = blockIdx.x;
@@ -228,10 +240,10 @@ __global__ void __launch_bounds__(256) k_xt(BigArgs a) {
   if (t < L.tn * L.tm) {
     const int I = t / L.tm, J = t - I * L.tm;
     const int i0 = I * TS, j0 = J * TS;
-    stage_panel(Zi, S + L.Z[0], i0, n, sc);
-    stage_panel(Zj, S + L.Z[0] + (size_t)n * PM, j0, m, sc);
+    stage_panel(Zi, ZLD, S + L.Z[0], i0, n, sc, nc);
+    stage_panel(Zj, ZLD, S + L.Z[0] + (size_t)n * PM, j0, m, sc, nc);
     __syncthreads();
-    lowrank_tile(F, Zi, Zj, ty, tx);
+    lowrank_tile(F, Zi, Zj, ZLD, nc, ty, tx);
     double vnew[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -255,10 +267,10 @@ __global__ void __launch_bounds__(256) k_xt(BigArgs a) {
     int I, J;
     lower_tile(t - L.tn * L.tm, I, J);
     const int i0 = I * TS, j0 = J * TS;
-    stage_panel(Zi, S + L.Z[0] + (size_t)n * PM, i0, m, sc);
-    stage_panel(Zj, S + L.Z[0] + (size_t)n * PM, j0, m, sc);
+    stage_panel(Zi, ZLD, S + L.Z[0] + (size_t)n * PM, i0, m, sc, nc);
+    stage_panel(Zj, ZLD, S + L.Z[0] + (size_t)n * PM, j0, m, sc, nc);
     __syncthreads();
-    lowrank_tile(F, Zi, Zj, ty, tx);
+    lowrank_tile(F, Zi, Zj, ZLD, nc, ty, tx);
     double vnew[4][4], tnew[4][4];
     double* T = S + L.T;
     double* V1T = V1 + (size_t)n * N1 + n;
@@ -302,11 +314,14 @@ __global__ void __launch_bounds__(256) k_y1(BigArgs a) {
   const int n = L.n, k = L.k, N1 = L.N[0], N2 = L.N[1];
   const int Lc = NI[I_L];
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* Zi = sm;                      // [3][TS*ZLD]
-  double* Zj = Zi + 3 * TS * ZLD;       // [3][TS*ZLD]
-  double* sc = Zj + 3 * TS * ZLD;       // [3][PM]
-  double* tb = sc + 3 * PM;             // [TS*(TS+1)]
-  double* xi = tb + TS * (TS + 1);      // [Lc][TS]
+  double* Zi_[3] = {sm + YOFF_I0, sm + YOFF_I1, sm + YOFF_I2};
+  double* Zj_[3] = {sm + YOFF_J0, sm + YOFF_J1, sm + YOFF_J2};
+  const int ld_[3] = {ZLD, ZLD, YLD2};
+  int nc_[3];
+  double* sc = sm + YOFF_SC;            // [3][PM]
+  double* ub = sm + YOFF_UB;            // [TS][17] U tile
+  double* tb = sm;                      // [TS*(TS+1)] aliases the panels
+  double* xi = sm + YOFF_X;             // [Lc][TS]
   double* xj = xi + (size_t)L.Lcap * TS;
   double* tgs = xj + (size_t)L.Lcap * TS;   // [Lc] tg/rho of the aggregated rows
   double* wred = tgs + L.Lcap + 1;      // [8][rcap]
@@ -316,12 +331,7 @@ __global__ void __launch_bounds__(256) k_y1(BigArgs a) {
   const int t = blockIdx.x;
   const int rq = 1 + Lc * (k + 1);
   for (int e = threadIdx.x; e < 8 * L.rcap; e += 256) wred[e] = 0.0;
-  for (int b = 0; b < 3; ++b) {
-    if (threadIdx.x < PM) {
-      const double th = S[L.th[b] + threadIdx.x];
-      sc[b * PM + threadIdx.x] = (threadIdx.x < L.p[b] && th > 0.0) ? sqrt(th) : 0.0;
-    }
-  }
+  for (int b = 0; b < 3; ++b) nc_[b] = stage_scale(sc + b * PM, S + L.th[b], L.p[b]);
   for (int l = threadIdx.x; l < Lc; l += 256) tgs[l] = S[L.vg + l] - 2.0 * fmax(S[L.vg + l], 0.0) + S[L.cbe + l];
   __syncthreads();
   double* part = S + L.rows_part + (size_t)t * L.rcap;
@@ -330,8 +340,8 @@ __global__ void __launch_bounds__(256) k_y1(BigArgs a) {
     lower_tile(t, I, J);
     const int i0 = I * TS, j0 = J * TS;
     for (int b = 0; b < 3; ++b) {
-      stage_panel(Zi + b * TS * ZLD, S + L.Z[b], i0, n, sc + b * PM);
-      stage_panel(Zj + b * TS * ZLD, S + L.Z[b], j0, n, sc + b * PM);
+      stage_panel(Zi_[b], ld_[b], S + L.Z[b], i0, n, sc + b * PM, nc_[b]);
+      stage_panel(Zj_[b], ld_[b], S + L.Z[b], j0, n, sc + b * PM, nc_[b]);
     }
     for (int e = threadIdx.x; e < Lc * TS; e += 256) {
       const int l = e / TS, q = e - l * TS;
@@ -340,9 +350,9 @@ __global__ void __launch_bounds__(256) k_y1(BigArgs a) {
     }
     __syncthreads();
     double F1[4][4], F2[4][4], F3[4][4], yt[4][4];
-    lowrank_tile(F1, Zi, Zj, ty, tx);
-    lowrank_tile(F2, Zi + TS * ZLD, Zj + TS * ZLD, ty, tx);
-    lowrank_tile(F3, Zi + 2 * TS * ZLD, Zj + 2 * TS * ZLD, ty, tx);
+    lowrank_tile(F1, Zi_[0], Zj_[0], ld_[0], nc_[0], ty, tx);
+    lowrank_tile(F2, Zi_[1], Zj_[1], ld_[1], nc_[1], ty, tx);
+    lowrank_tile(F3, Zi_[2], Zj_[2], ld_[2], nc_[2], ty, tx);
     const double v4 = S[L.scal + S_V4];
     const double t4 = v4 - 2.0 * fmax(v4, 0.0) + a.ktr;
     double trp = 0.0;
@@ -382,7 +392,9 @@ __global__ void __launch_bounds__(256) k_y1(BigArgs a) {
     // U tile: rows i0 .. i0+63, columns 0..k-1.  U~pre = (sig U + rho gU) / dYU,
     // gU/rho = -2 (D2u - 2 F2u) - (v5 - 2 s5) - sum_l x_li (tv_lj + tg_l alpha_lj)
     const int i0 = (t - nYt) * TS;
-    stage_panel(Zi, S + L.Z[1], i0, n, sc + PM);
+    double* Zi = Zi_[1]; double* Zj = Zj_[1];
+    const int nc1 = nc_[1];
+    stage_panel(Zi, ZLD, S + L.Z[1], i0, n, sc + PM, nc1);
     // the k rows n .. n+k-1 of Z2 (scaled)
     for (int e = threadIdx.x; e < k * PM; e += 256) {
       const int j = e / PM, c = e - j * PM;
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(256) k_y1(BigArgs a) {
       double ut = 0.0;
       if (i < n) {
         double F = 0.0;
-        for (int c = 0; c < PM; ++c) F = fma(Zi[il * ZLD + c], Zj[j * ZLD + c], F);
+        for (int c = 0; c < nc1; ++c) F = fma(Zi[il * ZLD + c], Zj[j * ZLD + c], F);
         const double D = S[L.V[1] + (size_t)i * N2 + n + j];
         const double v5 = S[L.v5 + (size_t)i * k + j];
         const double lo5 = (i >= n - k + j) ? 0.0 : -sa;
@@ -414,14 +426,14 @@ __global__ void __launch_bounds__(256) k_y1(BigArgs a) {
         ut = (sig * S[L.U + (size_t)i * k + j] + rho * g) / dYU;
         S[L.Ut + (size_t)i * k + j] = ut;
       }
-      tb[il * (TS + 1) + j] = ut;     // keep the tile for the row sums below
+      ub[il * 17 + j] = ut;           // keep the tile for the row sums below
     }
     __syncthreads();
     // x_l'U~_j over the 64 rows of this tile: one (l, j) per thread
     for (int e = threadIdx.x; e < Lc * k; e += 256) {
       const int l = e / k, j = e - l * k;
       double q = 0.0;
-      for (int il = 0; il < TS; ++il) q = fma(xi[l * TS + il], tb[il * (TS + 1) + j], q);
+      for (int il = 0; il < TS; ++il) q = fma(xi[l * TS + il], ub[il * 17 + j], q);
       part[1 + l * k + j] = q;
     }
     if (threadIdx.x == 0) part[0] = 0.0;
@@ -511,22 +523,19 @@ __global__ void __launch_bounds__(256) k_y2(BigArgs a) {
   const int n = L.n, k = L.k, N1 = L.N[0], N2 = L.N[1];
   const int Lc = NI[I_L];
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  double* Zi = sm;
-  double* Zj = Zi + 3 * TS * ZLD;
-  double* sc = Zj + 3 * TS * ZLD;
-  double* tb = sc + 3 * PM;
-  double* xi = tb + TS * (TS + 1);
+  double* Zi_[3] = {sm + YOFF_I0, sm + YOFF_I1, sm + YOFF_I2};
+  double* Zj_[3] = {sm + YOFF_J0, sm + YOFF_J1, sm + YOFF_J2};
+  const int ld_[3] = {ZLD, ZLD, YLD2};
+  int nc_[3];
+  double* sc = sm + YOFF_SC;
+  double* tb = sm;                          // aliases the panels
+  double* xi = sm + YOFF_X;
   double* xj = xi + (size_t)L.Lcap * TS;
   double* cg = xj + (size_t)L.Lcap * TS;    // [Lc] cw of the aggregated rows
   const double al = a.o.alpha;
   const int nYt = L.tn * (L.tn + 1) / 2;
   const int t = blockIdx.x;
-  for (int b = 0; b < 3; ++b) {
-    if (threadIdx.x < PM) {
-      const double th = S[L.th[b] + threadIdx.x];
-      sc[b * PM + threadIdx.x] = (threadIdx.x < L.p[b] && th > 0.0) ? sqrt(th) : 0.0;
-    }
-  }
+  for (int b = 0; b < 3; ++b) nc_[b] = stage_scale(sc + b * PM, S + L.th[b], L.p[b]);
   for (int l = threadIdx.x; l < Lc; l += 256) cg[l] = S[L.cw + 1 + Lc * k + l];
   __syncthreads();
   const double cw0 = S[L.cw + 0];
@@ -535,8 +544,8 @@ __global__ void __launch_bounds__(256) k_y2(BigArgs a) {
     lower_tile(t, I, J);
     const int i0 = I * TS, j0 = J * TS;
     for (int b = 0; b < 3; ++b) {
-      stage_panel(Zi + b * TS * ZLD, S + L.Z[b], i0, n, sc + b * PM);
-      stage_panel(Zj + b * TS * ZLD, S + L.Z[b], j0, n, sc + b * PM);
+      stage_panel(Zi_[b], ld_[b], S + L.Z[b], i0, n, sc + b * PM, nc_[b]);
+      stage_panel(Zj_[b], ld_[b], S + L.Z[b], j0, n, sc + b * PM, nc_[b]);
     }
     for (int e = threadIdx.x; e < Lc * TS; e += 256) {
       const int l = e / TS, q = e - l * TS;
@@ -545,9 +554,9 @@ __global__ void __launch_bounds__(256) k_y2(BigArgs a) {
     }
     __syncthreads();
     double F1[4][4], F2[4][4], F3[4][4], o1[4][4], o2[4][4], o3[4][4], oy[4][4];
-    lowrank_tile(F1, Zi, Zj, ty, tx);
-    lowrank_tile(F2, Zi + TS * ZLD, Zj + TS * ZLD, ty, tx);
-    lowrank_tile(F3, Zi + 2 * TS * ZLD, Zj + 2 * TS * ZLD, ty, tx);
+    lowrank_tile(F1, Zi_[0], Zj_[0], ld_[0], nc_[0], ty, tx);
+    lowrank_tile(F2, Zi_[1], Zj_[1], ld_[1], nc_[1], ty, tx);
+    lowrank_tile(F3, Zi_[2], Zj_[2], ld_[2], nc_[2], ty, tx);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -578,7 +587,9 @@ __global__ void __launch_bounds__(256) k_y2(BigArgs a) {
     }
   } else {
     const int i0 = (t - nYt) * TS;
-    stage_panel(Zi, S + L.Z[1], i0, n, sc + PM);
+    double* Zi = Zi_[1]; double* Zj = Zj_[1];
+    const int nc1 = nc_[1];
+    stage_panel(Zi, ZLD, S + L.Z[1], i0, n, sc + PM, nc1);
     for (int e = threadIdx.x; e < k * PM; e += 256) {
       const int j = e / PM, c = e - j * PM;
       Zj[j * ZLD + c] = S[L.Z[1] + (size_t)(n + j) * PM + c] * sc[PM + c];
@@ -594,7 +605,7 @@ __global__ void __launch_bounds__(256) k_y2(BigArgs a) {
       const int i = i0 + il;
       if (i >= n) continue;
       double F = 0.0;
-      for (int c = 0; c < PM; ++c) F = fma(Zi[il * ZLD + c], Zj[j * ZLD + c], F);
+      for (int c = 0; c < nc1; ++c) F = fma(Zi[il * ZLD + c], Zj[j * ZLD + c], F);
       // cU_ij = - sum_l x_li (cv_lj + cg_l alpha_lj);  U~ = U~pre - cU
       double cu = 0.0;
       for (int l = 0; l < Lc; ++l) cu -= xi[l * TS + il] * (S[L.cw + 1 + l * k + j] + cg[l] * S[L.cal + (size_t)l * k + j]);
@@ -613,7 +624,7 @@ __global__ void __launch_bounds__(256) k_y2(BigArgs a) {
       for (int e = threadIdx.x; e < k * k; e += 256) {
         const int i = e / k, j = e - i * k;
         double F = 0.0;
-        for (int c = 0; c < PM; ++c) F = fma(Zj[i * ZLD + c], Zj[j * ZLD + c], F);
+        for (int c = 0; c < nc1; ++c) F = fma(Zj[i * ZLD + c], Zj[j * ZLD + c], F);
         const size_t ev = L.V[1] + (size_t)(n + i) * N2 + n + j;
         S[ev] = S[ev] + al * (((i == j) ? 1.0 : 0.0) - F);
       }
@@ -622,16 +633,16 @@ __global__ void __launch_bounds__(256) k_y2(BigArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_prod: Wout = side * V_b P, P a 16-column panel (Z for which = 0, R for which = 1), FP64 DMMA m8n8k4.  One CTA = 64 rows
+// k_prod: Wout = side * V_b P, P a PM-column panel (Z for which = 0, R for which = 1), FP64 DMMA m8n8k4.  One CTA = 64 rows
 // of one (node, block): V streams through shared memory in 64 x 32 chunks (register-prefetched).  Epilogue: partial Gram
 // matrices of this row tile, partA = Z_tile' Wout_tile and (which = 1) partB = R_tile' Wout_tile.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int KC = 32, VLD = 36, PLD = 24;
+constexpr int KC = 32, VLD = 36, PLD = PM + 8;
+constexpr int NTL = PM / 8;     // DMMA n-tiles per warp
 
 __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
-  __shared__ __align__(16) double Vs[TS * VLD];
+  __shared__ __align__(16) double Vs[TS * VLD];      // V chunk; the W tile (ld ZLD) aliases it in the epilogue
   __shared__ __align__(16) double Ps[KC * PLD];
-  __shared__ double Ws[TS * ZLD];
   __shared__ double Ls[TS * ZLD];
   const Layout& L = a.L;
   const int b = blockIdx.z;
@@ -647,12 +658,12 @@ __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
   double* Wout = S + (which ? L.W2[b] : L.W[b]);
   const int r0 = blockIdx.x * TS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
-  double c[2][2][2];
+  double c[2][NTL][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
-  double pv[16], pp[4];
+    for (int j = 0; j < NTL; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  double pv[16], pp[KC * PM / 128];
   auto fetch = [&](int kc) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -661,8 +672,8 @@ __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
       pv[q] = (gr < N && gc < N) ? V[(size_t)gr * N + gc] : 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = q * 128 + tid, row = idx >> 4, col = idx & 15;
+    for (int q = 0; q < KC * PM / 128; ++q) {
+      const int idx = q * 128 + tid, row = idx / PM, col = idx % PM;
       pp[q] = (kc + row < N) ? P[(size_t)(kc + row) * PM + col] : 0.0;
     }
   };
@@ -675,8 +686,8 @@ __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
       Vs[row * VLD + col] = pv[q];
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = q * 128 + tid, row = idx >> 4, col = idx & 15;
+    for (int q = 0; q < KC * PM / 128; ++q) {
+      const int idx = q * 128 + tid, row = idx / PM, col = idx % PM;
       Ps[row * PLD + col] = pp[q];
     }
     __syncthreads();
@@ -685,25 +696,27 @@ __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
 #pragma unroll
     for (int kk = 0; kk < KC / 4; ++kk) {
       const double a0 = Vs[(rb + g) * VLD + kk * 4 + t4], a1 = Vs[(rb + 8 + g) * VLD + kk * 4 + t4];
-      const double b0 = Ps[(kk * 4 + t4) * PLD + g], b1 = Ps[(kk * 4 + t4) * PLD + 8 + g];
-      dmma884(c[0][0][0], c[0][0][1], a0, b0, c[0][0][0], c[0][0][1]);
-      dmma884(c[0][1][0], c[0][1][1], a0, b1, c[0][1][0], c[0][1][1]);
-      dmma884(c[1][0][0], c[1][0][1], a1, b0, c[1][0][0], c[1][0][1]);
-      dmma884(c[1][1][0], c[1][1][1], a1, b1, c[1][1][0], c[1][1][1]);
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        const double bb = Ps[(kk * 4 + t4) * PLD + nt * 8 + g];
+        dmma884(c[0][nt][0], c[0][nt][1], a0, bb, c[0][nt][0], c[0][nt][1]);
+        dmma884(c[1][nt][0], c[1][nt][1], a1, bb, c[1][nt][0], c[1][nt][1]);
+      }
     }
   }
-  // epilogue: W tile to shared + global
+  __syncthreads();
+  double* Ws = Vs;                 // 64 x ZLD <= 64 x VLD
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
+    for (int nt = 0; nt < NTL; ++nt) {
       const int row = warp * 16 + mt * 8 + g, col = nt * 8 + 2 * t4;
       Ws[row * ZLD + col] = sd * c[mt][nt][0];
       Ws[row * ZLD + col + 1] = sd * c[mt][nt][1];
     }
   __syncthreads();
   for (int e = tid; e < TS * PM; e += 128) {
-    const int row = e >> 4, col = e & 15;
+    const int row = e / PM, col = e % PM;
     if (r0 + row < N) Wout[(size_t)(r0 + row) * PM + col] = Ws[row * ZLD + col];
     else Ws[row * ZLD + col] = 0.0;
   }
@@ -711,13 +724,13 @@ __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
     const double* Lp = S + (pass ? L.R[b] : L.Z[b]);
     __syncthreads();
     for (int e = tid; e < TS * PM; e += 128) {
-      const int row = e >> 4, col = e & 15;
+      const int row = e / PM, col = e % PM;
       Ls[row * ZLD + col] = (r0 + row < N) ? Lp[(size_t)(r0 + row) * PM + col] : 0.0;
     }
     __syncthreads();
     double* part = S + (pass ? L.partB[b] : L.partA[b]) + (size_t)blockIdx.x * PM * PM;
     for (int e = tid; e < PM * PM; e += 128) {
-      const int ai = e >> 4, bi = e & 15;
+      const int ai = e / PM, bi = e % PM;
       double s = 0.0;
 #pragma unroll 8
       for (int r = 0; r < TS; ++r) s = fma(Ls[r * ZLD + ai], Ws[r * ZLD + bi], s);
@@ -746,21 +759,23 @@ __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
   double* S = node_ptr(a, slot);
   const int N = L.N[b], tid = threadIdx.x;
   const int r0 = blockIdx.x * TS;
-  {
-    const int ai = tid >> 4, bi = tid & 15;
+  double h2 = 0.0;
+  for (int e = tid; e < PM * PM; e += 256) {
+    const int ai = e / PM, bi = e % PM;
     double s = 0.0;
     if (pass == 0 && a.step > 0) {
       s = (ai == bi && ai < L.p[b]) ? S[L.th[b] + ai] : 0.0;   // (dead columns carry a -1e300 sentinel)
     } else {
       const double* part = S + ((pass & 1) ? L.partB[b] : L.partA[b]);
-      for (int t = 0; t < L.nt[b]; ++t) s += part[(size_t)t * PM * PM + tid];
+      for (int t = 0; t < L.nt[b]; ++t) s += part[(size_t)t * PM * PM + e];
     }
     Hs[ai * ZLD + bi] = s;
-    if (pass == 0 && blockIdx.x == 0) S[L.H[b] + tid] = s;
+    h2 += s * s;
+    if (pass == 0 && blockIdx.x == 0) S[L.H[b] + e] = s;
   }
   const double* src = S + (pass ? L.R[b] : L.W[b]);
   for (int e = tid; e < TS * PM; e += 256) {
-    const int row = e >> 4, col = e & 15;
+    const int row = e / PM, col = e % PM;
     const bool ok = r0 + row < N;
     Zs[row * ZLD + col] = ok ? S[L.Z[b] + (size_t)(r0 + row) * PM + col] : 0.0;
     Rs[row * ZLD + col] = ok ? src[(size_t)(r0 + row) * PM + col] : 0.0;
@@ -771,136 +786,62 @@ __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
   // [Y U; U' I] at a node without cuts, where U = 0) would otherwise never be found again once it has left the panel
   double amp = 0.0;
   if (pass == 0) {
-    double h2 = 0.0;
-    { const int ai = tid >> 4, bi = tid & 15; const double h = Hs[ai * ZLD + bi]; h2 = h * h; }
     h2 = block_sum(h2, red);
     amp = 1e-3 * sqrt(h2 / (double)N);
   }
   {
-    const int row = tid >> 2, cb = (tid & 3) * 4;
-    double acc[4];
+    constexpr int CPT = TS * PM / 256;      // outputs per thread (8): one row, CPT consecutive columns
+    const int row = tid / (PM / CPT), cb = (tid % (PM / CPT)) * CPT;
+    double acc[CPT];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = Rs[row * ZLD + cb + q];
-#pragma unroll
+    for (int q = 0; q < CPT; ++q) acc[q] = Rs[row * ZLD + cb + q];
+#pragma unroll 4
     for (int c = 0; c < PM; ++c) {
       const double z = Zs[row * ZLD + c];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fma(-z, Hs[c * ZLD + cb + q], acc[q]);
+      for (int q = 0; q < CPT; ++q) acc[q] = fma(-z, Hs[c * ZLD + cb + q], acc[q]);
     }
     if (pass == 0) {
       const int pc = L.p[b] - 1;
-      if (pc >= cb && pc < cb + 4 && pc > 0)
-        acc[pc - cb] = amp * hash_unit((unsigned long long)(r0 + row), (unsigned long long)(a.it * 64 + a.step * 4 + b), 12345ull);
+      if (pc > 0) {
+#pragma unroll
+        for (int q = 0; q < CPT; ++q)
+          if (cb + q == pc)
+            acc[q] = amp * hash_unit((unsigned long long)(r0 + row), (unsigned long long)(a.it * 64 + a.step * 4 + b), 12345ull);
+      }
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < CPT; ++q) {
       Rs[row * ZLD + cb + q] = acc[q];
       if (r0 + row < N) S[L.R[b] + (size_t)(r0 + row) * PM + cb + q] = acc[q];
     }
   }
   __syncthreads();
   {
-    const int ai = tid >> 4, bi = tid & 15;
     const double* Lm = (pass == 2) ? Rs : Zs;
-    double s = 0.0;
-#pragma unroll 8
-    for (int r = 0; r < TS; ++r) s = fma(Lm[r * ZLD + ai], Rs[r * ZLD + bi], s);
     double* part = S + ((pass & 1) ? L.partA[b] : L.partB[b]) + (size_t)blockIdx.x * PM * PM;
-    part[tid] = s;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// k_rr: one warp per (node, block).  M = sum partA (after k_resid2) -> guarded Cholesky -> T = L^-T; the second product
-// gave partA = Z'(V R), partB = R'(V R): Xc = (Z'VR) T, C = T'(R'VR) T; Rayleigh-Ritz on [[H, Xc], [Xc', C]] by cyclic
-// Jacobi (round-robin pairs, lanes = pairs / columns); keeps the p largest Ritz pairs; writes Q (2 PM x PM, the
-// bottom half already multiplied by T so that Znew = Z Qtop + R Qbot), theta, and the step control flags.
-// This kernel is launched AFTER the second product; the Cholesky input M was saved by k_chol (below) into H's neighbour.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int JN = 2 * PM, JLD = JN + 1;
-
-// Cyclic Jacobi on the JN x JN symmetric matrix A (shared memory, ld JLD) by one warp; Q accumulates the rotations (identity
-// on entry).  Round-robin ordering: each round rotates PM disjoint pairs.  Per round the lanes < PM compute the rotation
-// of their pair; then every lane updates one column (rows phase) and one row (columns phase, also of Q) with all loads of
-// the phase issued before the first store, so that the shared-memory latency overlaps.  The rotations keep Q orthogonal
-// whatever the number of sweeps; the projected matrix is nearly diagonal once the tracker has locked on (off-diagonal =
-// Ritz residual), so `max_sweeps` = 3 resolves it to rounding there, and an unconverged start-phase Rayleigh-Ritz is
-// finished by the following tracker steps.
-__device__ __forceinline__ void jacobi_warp(double* A, double* Q, int lane, double* cs, int* pq, int max_sweeps, double dg_scale) {
-  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    double off = 0.0;
-    for (int c = 0; c < JN; ++c) {
-      const double v = A[lane * JLD + c];
-      if (c != lane) off = fmax(off, fabs(v));
-    }
-    off = warp_max(off);
-    if (off <= 1e-14 * dg_scale || off < 1e-300) break;
-    for (int rnd = 0; rnd < JN - 1; ++rnd) {
-      int rot = 0;
-      if (lane < PM) {
-        int p_, q_;
-        if (lane == 0) { p_ = JN - 1; q_ = rnd; }
-        else { p_ = (rnd + lane) % (JN - 1); q_ = (rnd + JN - 1 - lane) % (JN - 1); }
-        if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
-        const double apq = A[p_ * JLD + q_], app = A[p_ * JLD + p_], aqq = A[q_ * JLD + q_];
-        double c_ = 1.0, s_ = 0.0;
-        if (fabs(apq) > 1e-16 * dg_scale && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double t_ = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c_ = rsqrt(1.0 + t_ * t_);
-          s_ = t_ * c_;
-          rot = 1;
-        }
-        cs[lane * 2 + 0] = c_; cs[lane * 2 + 1] = s_;
-        pq[lane * 2 + 0] = p_; pq[lane * 2 + 1] = q_;
-      }
-      rot = __any_sync(0xffffffffu, rot);
-      __syncwarp();
-      if (!rot) continue;
-      double ap[PM], aq[PM];
-      // rows: A <- J' A   (lane = column)
-#pragma unroll
-      for (int i = 0; i < PM; ++i) { ap[i] = A[pq[2 * i] * JLD + lane]; aq[i] = A[pq[2 * i + 1] * JLD + lane]; }
-#pragma unroll
-      for (int i = 0; i < PM; ++i) {
-        const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
-        A[pq[2 * i] * JLD + lane] = c_ * ap[i] - s_ * aq[i];
-        A[pq[2 * i + 1] * JLD + lane] = s_ * ap[i] + c_ * aq[i];
-      }
-      __syncwarp();
-      // columns: A <- A J, Q <- Q J   (lane = row)
-#pragma unroll
-      for (int i = 0; i < PM; ++i) { ap[i] = A[lane * JLD + pq[2 * i]]; aq[i] = A[lane * JLD + pq[2 * i + 1]]; }
-#pragma unroll
-      for (int i = 0; i < PM; ++i) {
-        const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
-        A[lane * JLD + pq[2 * i]] = c_ * ap[i] - s_ * aq[i];
-        A[lane * JLD + pq[2 * i + 1]] = s_ * ap[i] + c_ * aq[i];
-      }
-#pragma unroll
-      for (int i = 0; i < PM; ++i) { ap[i] = Q[lane * JLD + pq[2 * i]]; aq[i] = Q[lane * JLD + pq[2 * i + 1]]; }
-#pragma unroll
-      for (int i = 0; i < PM; ++i) {
-        const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
-        Q[lane * JLD + pq[2 * i]] = c_ * ap[i] - s_ * aq[i];
-        Q[lane * JLD + pq[2 * i + 1]] = s_ * ap[i] + c_ * aq[i];
-      }
-      __syncwarp();
+    for (int e = tid; e < PM * PM; e += 256) {
+      const int ai = e / PM, bi = e % PM;
+      double s = 0.0;
+#pragma unroll 8
+      for (int r = 0; r < TS; ++r) s = fma(Lm[r * ZLD + ai], Rs[r * ZLD + bi], s);
+      part[e] = s;
     }
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
 // guarded Cholesky-QR factor of the PM x PM Gram matrix M (ld ZLD) by one warp.  Columns are equilibrated first
 // (M~ = D^-1 M D^-1, D = sqrt(diag M)) so that the guards do not depend on the relative scale of the columns: a column is
-// dropped when its squared norm is <= floor2 or when its pivot in M~ is <= piv_rel (nearly dependent on earlier columns).
+// dropped when its squared norm is <= floor2, or <= rel_small * the largest one (the probe column is exempt and does not
+// count for the largest), or when its pivot in M~ is <= piv_rel (nearly dependent on earlier columns).
 // Tm = D^-1 L~^-T with zero columns for dropped ones: P Tm is orthonormal on the kept columns.
+// ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void chol_guard_warp(double* M, double* Lm, double* Tm, int* valid, int lane, double piv_rel, double floor2,
                                                 int pcols, double rel_small = 0.0, int probe = -1) {
   __shared__ double dscale[PM];
   {
-    // a column is also dropped when its squared norm is <= rel_small * the largest one (the probe column is exempt and
-    // does not count for the largest)
     const double d = (lane < PM) ? M[lane * ZLD + lane] : 0.0;
     const double dmax = fmax(warp_max((lane < pcols && lane != probe) ? d : 0.0), 0.0);
     if (lane < PM) {
@@ -911,7 +852,7 @@ __device__ __forceinline__ void chol_guard_warp(double* M, double* Lm, double* T
   for (int e = lane; e < PM * ZLD; e += 32) { Lm[e] = 0.0; Tm[e] = 0.0; }
   __syncwarp();
   for (int e = lane; e < PM * PM; e += 32) {
-    const int i = e >> 4, j = e & 15;
+    const int i = e / PM, j = e % PM;
     M[i * ZLD + j] *= dscale[i] * dscale[j];
   }
   __syncwarp();
@@ -937,167 +878,17 @@ __device__ __forceinline__ void chol_guard_warp(double* M, double* Lm, double* T
     if (!valid[j]) for (int c = lane; c < j; c += 32) Lm[j * ZLD + c] = 0.0;
   }
   __syncwarp();
-  // L~inv by forward substitution, one column per lane; Tm[c][i] = dscale[c] * L~inv[i][c]
+  // L~inv by forward substitution, one column per lane, built in place in Tm: Tm[c][i] = L~inv[i][c] (then scaled)
   if (lane < PM) {
     const int cidx = lane;
-    double x[PM];
-#pragma unroll
-    for (int i = 0; i < PM; ++i) {
+    for (int i = cidx; i < PM; ++i) {
       double sacc = (i == cidx) ? 1.0 : 0.0;
-#pragma unroll
-      for (int c = 0; c < PM; ++c) if (c < i) sacc -= Lm[i * ZLD + c] * x[c];
-      x[i] = (i >= cidx) ? sacc / Lm[i * ZLD + i] : 0.0;
+      for (int c = cidx; c < i; ++c) sacc -= Lm[i * ZLD + c] * Tm[cidx * ZLD + c];
+      Tm[cidx * ZLD + i] = sacc / Lm[i * ZLD + i];
     }
-#pragma unroll
-    for (int i = 0; i < PM; ++i) Tm[cidx * ZLD + i] = (valid[i] && valid[cidx]) ? dscale[cidx] * x[i] : 0.0;
+    for (int i = 0; i < PM; ++i) Tm[cidx * ZLD + i] = (i >= cidx && valid[i] && valid[cidx]) ? dscale[cidx] * Tm[cidx * ZLD + i] : 0.0;
   }
   __syncwarp();
-}
-
-__global__ void __launch_bounds__(32) k_rr(BigArgs a) {
-  __shared__ double A[JN * JLD];
-  __shared__ double Q[JN * JLD];
-  __shared__ double M[PM * ZLD], Lm[PM * ZLD], Tm[PM * ZLD], X0[PM * ZLD], C0[PM * ZLD], Hh[PM * ZLD];
-  __shared__ double cs[PM * 2];
-  __shared__ int pq[PM * 2];
-  __shared__ double lam[JN];
-  __shared__ int valid[PM], sel[PM];
-  const Layout& L = a.L;
-  const int b = blockIdx.y;
-  const int slot = a.active[blockIdx.x];
-  int* NI = node_int(a, slot);
-  if (a.step > 0 && !NI[I_MORE + b]) return;
-  double* S = node_ptr(a, slot);
-  const int lane = threadIdx.x, p = L.p[b];
-  // Gram matrices: M was reduced and stored in Q-area slot by k_chol? (no: reduce here) -- partials layout:
-  //   after k_resid(pass 1): partA = R'R per tile;   after k_prod(which 1): partA = Z'W2, partB = R'W2.
-  // k_prod overwrites partA, so M is reduced by k_resid2's successor kernel k_gram (below) into L.Q[b] before k_prod runs.
-  for (int e = lane; e < PM * PM; e += 32) {
-    const int i = e >> 4, j = e & 15;
-    M[i * ZLD + j] = S[L.Q[b] + e];           // M saved by k_gram
-    double sx = 0.0, sc_ = 0.0;
-    for (int t = 0; t < L.nt[b]; ++t) {
-      sx += S[L.partA[b] + (size_t)t * PM * PM + e];
-      sc_ += S[L.partB[b] + (size_t)t * PM * PM + e];
-    }
-    X0[i * ZLD + j] = sx; C0[i * ZLD + j] = sc_;
-    Hh[i * ZLD + j] = S[L.H[b] + e];
-  }
-  __syncwarp();
-  // residual of the minority columns (before this step) and the scale of H
-  double res2 = 0.0, hs2 = 0.0;
-  if (lane < PM) {
-    if (lane < p - 1 && S[L.th[b] + lane] > 0.0) res2 = M[lane * ZLD + lane];   // (column p - 1 holds the probe)
-    double h = 0.0;
-    for (int i = 0; i < PM; ++i) h += Hh[i * ZLD + lane] * Hh[i * ZLD + lane];
-    hs2 = h;
-  }
-  res2 = warp_sum(res2); hs2 = warp_max(hs2);
-  chol_guard_warp(M, Lm, Tm, valid, lane, 1e-10, 1e-20 * hs2, p, 1e-10, (p > 1) ? p - 1 : -1);
-  // A = [[sym(H), X0 T], [., T' C0 T]]
-  for (int e = lane; e < JN * JLD; e += 32) { A[e] = 0.0; Q[e] = 0.0; }
-  __syncwarp();
-  for (int e = lane; e < PM * PM; e += 32) {
-    const int i = e >> 4, j = e & 15;
-    A[i * JLD + j] = 0.5 * (Hh[i * ZLD + j] + Hh[j * ZLD + i]);
-    double s = 0.0;
-    for (int c = 0; c < PM; ++c) s = fma(X0[i * ZLD + c], Tm[c * ZLD + j], s);     // (X0 T)[i][j], T[c][j] = Tm[c][j]
-    A[i * JLD + PM + j] = s; A[(PM + j) * JLD + i] = s;
-  }
-  __syncwarp();
-  // C = T' C0 T: first Y = C0 T into M (reuse), then T' Y
-  for (int e = lane; e < PM * PM; e += 32) {
-    const int i = e >> 4, j = e & 15;
-    double s = 0.0;
-    for (int c = 0; c < PM; ++c) s = fma(C0[i * ZLD + c], Tm[c * ZLD + j], s);
-    M[i * ZLD + j] = s;
-  }
-  __syncwarp();
-  for (int e = lane; e < PM * PM; e += 32) {
-    const int i = e >> 4, j = e & 15;
-    double s = 0.0;
-    for (int c = 0; c < PM; ++c) s = fma(Tm[c * ZLD + i], M[c * ZLD + j], s);
-    X0[i * ZLD + j] = s;
-  }
-  __syncwarp();
-  double amax = 0.0;
-  for (int e = lane; e < PM * PM; e += 32) {
-    const int i = e >> 4, j = e & 15;
-    A[(PM + i) * JLD + PM + j] = 0.5 * (X0[i * ZLD + j] + X0[j * ZLD + i]);
-  }
-  __syncwarp();
-  for (int e = lane; e < JN * JN; e += 32) amax = fmax(amax, fabs(A[(e / JN) * JLD + (e % JN)]));
-  amax = warp_max(amax);
-  const double big = 64.0 * (amax + 1.0);
-  // dead columns of Z (index >= p) and dropped residual columns sink to the bottom of the spectrum
-  if (lane < PM) {
-    if (lane >= p) {
-      for (int c = 0; c < JN; ++c) { A[lane * JLD + c] = 0.0; A[c * JLD + lane] = 0.0; }
-    }
-  }
-  __syncwarp();
-  if (lane < PM) {
-    if (!valid[lane]) {
-      for (int c = 0; c < JN; ++c) { A[(PM + lane) * JLD + c] = 0.0; A[c * JLD + PM + lane] = 0.0; }
-    }
-  }
-  __syncwarp();
-  if (lane < PM) {
-    if (lane >= p) A[lane * JLD + lane] = -big;
-    if (!valid[lane]) A[(PM + lane) * JLD + PM + lane] = -big;
-  }
-  Q[lane * JLD + lane] = 1.0;
-  __syncwarp();
-  jacobi_warp(A, Q, lane, cs, pq, a.o.jacobi_sweeps, amax);
-  lam[lane] = A[lane * JLD + lane];
-  __syncwarp();
-  // rank by value (descending, ties by index)
-  {
-    const double li = lam[lane];
-    int rank = 0;
-    for (int j = 0; j < JN; ++j) rank += (lam[j] > li || (lam[j] == li && j < lane)) ? 1 : 0;
-    if (rank < PM) sel[rank] = lane;
-  }
-  __syncwarp();
-  // Q' (2 PM x PM): column c = eigenvector sel[c], sign: largest-|.| component positive; bottom half multiplied by T
-  double thn = -1e300;
-  if (lane < PM) {
-    const int c = lane, src = sel[c];
-    if (c < p) {
-      double best = 0.0, sg = 1.0;
-      for (int i = 0; i < JN; ++i) {
-        const double v = Q[i * JLD + src];
-        if (fabs(v) > best) { best = fabs(v); sg = (v < 0.0) ? -1.0 : 1.0; }
-      }
-      for (int i = 0; i < PM; ++i) S[L.Q[b] + (size_t)i * PM + c] = sg * Q[i * JLD + src];
-      for (int i = 0; i < PM; ++i) {
-        double s = 0.0;
-        for (int j = 0; j < PM; ++j) s = fma(Tm[i * ZLD + j], Q[(PM + j) * JLD + src], s);
-        S[L.Q[b] + (size_t)(PM + i) * PM + c] = sg * s;
-      }
-      thn = lam[src];
-    } else {
-      for (int i = 0; i < JN; ++i) S[L.Q[b] + (size_t)i * PM + c] = 0.0;
-    }
-  }
-  double tn2 = (lane < p) ? thn * thn : 0.0;
-  tn2 = warp_sum(tn2);
-  int rpos = (lane < p && thn > 0.0) ? 1 : 0;
-  rpos = __reduce_add_sync(0xffffffffu, rpos);
-  if (lane < PM) S[L.th[b] + lane] = (lane < p) ? thn : -1e300;
-  if (lane == 0) {
-    const double res = sqrt(fmax(res2, 0.0)) / fmax(sqrt(tn2), 1e-300);
-    S[L.scal + S_RES + b] = res;
-    const int q = (a.step == 0) ? 1 : NI[I_Q + b] + 1;
-    NI[I_Q + b] = q;
-    NI[I_R + b] = rpos;
-    const int confirm = NI[I_CONFIRM] || (a.it >= a.o.max_iter);
-    const int ns = (a.it == 1) ? a.o.steps_start : 1;
-    const double tol = confirm ? a.o.confirm_tol : a.o.track_tol;
-    const int qmax = confirm ? a.o.steps_start : a.o.steps_max;
-    const bool stop = (q >= ns) && (res <= tol || q >= qmax);
-    NI[I_MORE + b] = stop ? 0 : 1;
-  }
 }
 
 // k_gram: M = sum over tiles of partB (R'R, written by k_resid pass 2) saved to L.Q[b] before k_prod(which = 1) reuses it.
@@ -1108,89 +899,340 @@ __global__ void __launch_bounds__(256) k_gram(BigArgs a) {
   const int* NI = node_int(a, slot);
   if (a.step > 0 && !NI[I_MORE + b]) return;
   double* S = node_ptr(a, slot);
-  double s = 0.0;
-  for (int t = 0; t < L.nt[b]; ++t) s += S[L.partB[b] + (size_t)t * PM * PM + threadIdx.x];
-  S[L.Q[b] + threadIdx.x] = s;
+  for (int e = threadIdx.x; e < PM * PM; e += 256) {
+    double s = 0.0;
+    for (int t = 0; t < L.nt[b]; ++t) s += S[L.partB[b] + (size_t)t * PM * PM + e];
+    S[L.Q[b] + e] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_rr: one CTA (256 threads) per (node, block).  M = R'R (saved by k_gram) -> guarded Cholesky -> T = D^-1 L~^-T; the second
+// product gave partA = Z'(V R), partB = R'(V R): Xc = (Z'VR) T, C = T'(R'VR) T; Rayleigh-Ritz on [[H, Xc], [Xc', C]]
+// (2 PM x 2 PM) by a CTA-parallel cyclic Jacobi (round-robin pairs; per round: PM rotations, then all row updates, then all
+// column updates of A and of the eigenvector accumulator Q); keeps the p largest Ritz pairs; writes Q' (2 PM x PM, the bottom
+// half already multiplied by T so that Znew = Z Qtop + R Qbot), theta, and the step control flags.
+// The rotations keep Q orthogonal whatever the number of sweeps; the projected matrix is nearly diagonal once the tracker has
+// locked on (off-diagonal = Ritz residual), so `jacobi_sweeps` = 3 resolves it to rounding there, and an unconverged
+// start-phase Rayleigh-Ritz is finished by the following tracker steps.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int JN = 2 * PM, JLD = JN + 1;
+constexpr size_t RR_SMEM = ((size_t)2 * JN * JLD + 3 * PM * ZLD + 2 * PM + JN + 64) * sizeof(double) + (3 * PM + 2 * JN + 8) * sizeof(int);
+
+__global__ void __launch_bounds__(256) k_rr(BigArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  double* A = sm;                       // [JN][JLD]
+  double* Q = A + JN * JLD;             // [JN][JLD]   (scratch for X0 / C0 before the Jacobi)
+  double* Mm = Q + JN * JLD;            // [PM][ZLD]
+  double* Lm = Mm + PM * ZLD;
+  double* Tm = Lm + PM * ZLD;
+  double* cs = Tm + PM * ZLD;           // [PM][2]
+  double* lam = cs + 2 * PM;            // [JN]
+  double* red = lam + JN;               // [64]
+  int* valid = reinterpret_cast<int*>(red + 64);   // [PM]
+  int* pq = valid + PM;                 // [PM][2]
+  int* sel = pq + 2 * PM;               // [JN]
+  int* live = sel + JN;                 // [JN]
+  int* flag = live + JN;                // [8]
+  const Layout& L = a.L;
+  const int b = blockIdx.y;
+  const int slot = a.active[blockIdx.x];
+  int* NI = node_int(a, slot);
+  if (a.step > 0 && !NI[I_MORE + b]) return;
+  double* S = node_ptr(a, slot);
+  const int tid = threadIdx.x, lane = tid & 31, p = L.p[b];
+  double* X0 = Q; double* C0 = Q + PM * ZLD;
+  for (int e = tid; e < PM * PM; e += 256) {
+    const int i = e / PM, j = e % PM;
+    Mm[i * ZLD + j] = S[L.Q[b] + e];
+    double sx = 0.0, sc_ = 0.0;
+    for (int t = 0; t < L.nt[b]; ++t) {
+      sx += S[L.partA[b] + (size_t)t * PM * PM + e];
+      sc_ += S[L.partB[b] + (size_t)t * PM * PM + e];
+    }
+    X0[i * ZLD + j] = sx; C0[i * ZLD + j] = sc_;
+  }
+  __syncthreads();
+  // residual of the minority columns (before this step; column p - 1 holds the probe) and the scale of H
+  double res2 = 0.0, hs2 = 0.0;
+  if (tid < PM) {
+    if (tid < p - 1 && S[L.th[b] + tid] > 0.0) res2 = Mm[tid * ZLD + tid];
+    double h = 0.0;
+    for (int i = 0; i < PM; ++i) { const double v = S[L.H[b] + i * PM + tid]; h += v * v; }
+    hs2 = h;
+  }
+  res2 = block_sum(res2, red);
+  hs2 = block_max(hs2, red);
+  if (tid < 32) chol_guard_warp(Mm, Lm, Tm, valid, lane, 1e-10, 1e-20 * hs2, p, 1e-10, (p > 1) ? p - 1 : -1);
+  __syncthreads();
+  // A = [[sym(H), X0 T], [., T' C0 T]];  Y = C0 T goes to Mm (M is dead)
+  for (int e = tid; e < JN * JLD; e += 256) A[e] = 0.0;
+  __syncthreads();
+  for (int e = tid; e < PM * PM; e += 256) {
+    const int i = e / PM, j = e % PM;
+    A[i * JLD + j] = 0.5 * (S[L.H[b] + i * PM + j] + S[L.H[b] + j * PM + i]);
+    double s = 0.0, y = 0.0;
+    for (int c = 0; c < PM; ++c) {
+      const double t = Tm[c * ZLD + j];
+      s = fma(X0[i * ZLD + c], t, s);
+      y = fma(C0[i * ZLD + c], t, y);
+    }
+    A[i * JLD + PM + j] = s; A[(PM + j) * JLD + i] = s;
+    Mm[i * ZLD + j] = y;
+  }
+  __syncthreads();
+  for (int e = tid; e < PM * PM; e += 256) {
+    const int i = e / PM, j = e % PM;
+    double s = 0.0;
+    for (int c = 0; c < PM; ++c) s = fma(Tm[c * ZLD + i], Mm[c * ZLD + j], s);
+    Lm[i * ZLD + j] = s;                         // T' C0 T (L is dead)
+  }
+  __syncthreads();
+  for (int e = tid; e < PM * PM; e += 256) {
+    const int i = e / PM, j = e % PM;
+    A[(PM + i) * JLD + PM + j] = 0.5 * (Lm[i * ZLD + j] + Lm[j * ZLD + i]);
+  }
+  __syncthreads();
+  double amax = 0.0;
+  for (int e = tid; e < JN * JN; e += 256) amax = fmax(amax, fabs(A[(e / JN) * JLD + (e % JN)]));
+  amax = block_max(amax, red);
+  const double big = 64.0 * (amax + 1.0);
+  // ---- compaction: dead columns of Z (index >= p) and dropped residual columns are decoupled from the rest; the Jacobi
+  // runs on the live indices only (n2 = their number rounded up to even; a padding index sits at -big).  In steady state
+  // most residual columns are converged and dropped, so n2 is close to p instead of 2 PM.
+  if (tid == 0) {
+    int nl = 0;
+    for (int i = 0; i < p; ++i) sel[nl++] = i;
+    for (int j = 0; j < PM; ++j) if (valid[j]) sel[nl++] = PM + j;
+    flag[1] = nl;
+    if (nl & 1) sel[nl++] = -1;
+    flag[2] = nl;
+  }
+  __syncthreads();
+  const int nl = flag[1], n2 = flag[2];
+  double* Ac = Q;                       // compact matrix (ld JLD)
+  for (int e = tid; e < n2 * n2; e += 256) {
+    const int i = e / n2, j = e % n2;
+    const int li = sel[i], lj = sel[j];
+    Ac[i * JLD + j] = (li < 0 || lj < 0) ? ((i == j) ? -big : 0.0) : A[li * JLD + lj];
+  }
+  __syncthreads();
+  if (tid < JN) live[tid] = sel[tid];               // live map (sel is reused for the ranking)
+  double* Qc = A;                       // eigenvector accumulator
+  for (int e = tid; e < n2 * JLD; e += 256) Qc[e] = 0.0;
+  __syncthreads();
+  if (tid < n2) Qc[tid * JLD + tid] = 1.0;
+  __syncthreads();
+  const int npair = n2 >> 1;
+  // ---- cyclic Jacobi on Ac (n2 x n2)
+  const double off_tol = ((NI[I_CONFIRM] || a.it >= a.o.max_iter) ? 1e-14 : 1e-12) * amax;
+  for (int sweep = 0; sweep < a.o.jacobi_sweeps; ++sweep) {
+    double off = 0.0;
+    {
+      const int cj = tid & (JN - 1);
+      if (cj < n2)
+        for (int i = tid >> 6; i < n2; i += 4)
+          if (i != cj) off = fmax(off, fabs(Ac[i * JLD + cj]));
+    }
+    off = block_max(off, red);
+    if (off <= off_tol || off < 1e-300) break;
+    for (int rnd = 0; rnd < n2 - 1; ++rnd) {
+      if (tid == 0) flag[0] = 0;
+      __syncthreads();
+      if (tid < npair) {
+        int p_, q_;
+        if (tid == 0) { p_ = n2 - 1; q_ = rnd; }
+        else { p_ = (rnd + tid) % (n2 - 1); q_ = (rnd + n2 - 1 - tid) % (n2 - 1); }
+        if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
+        const double apq = Ac[p_ * JLD + q_], app = Ac[p_ * JLD + p_], aqq = Ac[q_ * JLD + q_];
+        double c_ = 1.0, s_ = 0.0;
+        if (fabs(apq) > 1e-16 * amax && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t_ = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c_ = rsqrt(1.0 + t_ * t_);
+          s_ = t_ * c_;
+          flag[0] = 1;
+        }
+        cs[tid * 2 + 0] = c_; cs[tid * 2 + 1] = s_;
+        pq[tid * 2 + 0] = p_; pq[tid * 2 + 1] = q_;
+      }
+      __syncthreads();
+      if (!flag[0]) continue;
+      // rows: Ac <- J' Ac.  item = (pair i, column c); division-free map: column = tid & 63, pairs strided by 4
+      const int cc = tid & (JN - 1), g0 = tid >> 6;
+      if (cc < n2) {
+        for (int i = g0; i < npair; i += 4) {
+          const double s_ = cs[2 * i + 1];
+          if (s_ == 0.0) continue;
+          const double c_ = cs[2 * i];
+          const int p_ = pq[2 * i], q_ = pq[2 * i + 1];
+          const double ap = Ac[p_ * JLD + cc], aq = Ac[q_ * JLD + cc];
+          Ac[p_ * JLD + cc] = c_ * ap - s_ * aq;
+          Ac[q_ * JLD + cc] = s_ * ap + c_ * aq;
+        }
+      }
+      __syncthreads();
+      // columns: Ac <- Ac J, Qc <- Qc J.  item = (pair i, row r)
+      for (int i = g0; i < npair; i += 4) {
+        const int r = cc;
+        if (r >= n2) break;
+        const double s_ = cs[2 * i + 1];
+        if (s_ == 0.0) continue;
+        const double c_ = cs[2 * i];
+        const int p_ = pq[2 * i], q_ = pq[2 * i + 1];
+        const double ap = Ac[r * JLD + p_], aq = Ac[r * JLD + q_];
+        Ac[r * JLD + p_] = c_ * ap - s_ * aq;
+        Ac[r * JLD + q_] = s_ * ap + c_ * aq;
+        const double qp = Qc[r * JLD + p_], qq = Qc[r * JLD + q_];
+        Qc[r * JLD + p_] = c_ * qp - s_ * qq;
+        Qc[r * JLD + q_] = s_ * qp + c_ * qq;
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < n2) lam[tid] = Ac[tid * JLD + tid];
+  __syncthreads();
+  // rank by value (descending, ties by index); the padding index sits at the bottom
+  if (tid < n2) {
+    const double li = lam[tid];
+    int rank = 0;
+    for (int j = 0; j < n2; ++j) rank += (lam[j] > li || (lam[j] == li && j < tid)) ? 1 : 0;
+    sel[rank] = tid;
+  }
+  __syncthreads();
+  // sign convention per kept column: largest-|.| component positive (kept in cs[c])
+  if (tid < p) {
+    const int src = sel[tid];
+    double best = 0.0, sg = 1.0;
+    for (int i = 0; i < nl; ++i) {
+      const double v = Qc[i * JLD + src];
+      if (fabs(v) > best) { best = fabs(v); sg = (v < 0.0) ? -1.0 : 1.0; }
+    }
+    cs[tid] = sg;
+  }
+  __syncthreads();
+  // Q' (2 PM x PM): column c = eigenvector sel[c] scattered back to the original indices; bottom half multiplied by T.
+  // Mm receives the bottom halves first (compact -> original residual index), then T is applied.
+  for (int e = tid; e < PM * PM; e += 256) Mm[(e / PM) * ZLD + (e % PM)] = 0.0;
+  for (int e = tid; e < JN * PM; e += 256) if (e < PM * PM) S[L.Q[b] + e] = 0.0;
+  __syncthreads();
+  for (int e = tid; e < nl * p; e += 256) {
+    const int i = e / p, c = e % p;
+    const int li = live[i];
+    const double v = cs[c] * Qc[i * JLD + sel[c]];
+    if (li < PM) S[L.Q[b] + (size_t)li * PM + c] = v;
+    else Mm[(li - PM) * ZLD + c] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < PM * PM; e += 256) {
+    const int ii = e / PM, c = e % PM;
+    double v = 0.0;
+    if (c < p) for (int j = 0; j < PM; ++j) v = fma(Tm[ii * ZLD + j], Mm[j * ZLD + c], v);
+    S[L.Q[b] + (size_t)(PM + ii) * PM + c] = v;
+  }
+  double thn = -1e300;
+  if (tid < p) thn = lam[sel[tid]];
+  double tn2 = (tid < p) ? thn * thn : 0.0;
+  tn2 = block_sum(tn2, red);
+  double rposd = (tid < p && thn > 0.0) ? 1.0 : 0.0;
+  rposd = block_sum(rposd, red);
+  if (tid < PM) S[L.th[b] + tid] = thn;
+  if (tid == 0) {
+    const double res = sqrt(fmax(res2, 0.0)) / fmax(sqrt(tn2), 1e-300);
+    S[L.scal + S_RES + b] = res;
+    const int q = (a.step == 0) ? 1 : NI[I_Q + b] + 1;
+    NI[I_Q + b] = q;
+    NI[I_R + b] = (int)(rposd + 0.5);
+    // a node whose termination decision is pending (confirm) tracks at the tight tolerance until the next scheduled check
+    // and may use steps_start steps in the iteration of that check (the host launches that many rounds there)
+    const bool last = a.it >= a.o.max_iter;
+    const bool confirm = NI[I_CONFIRM] || last;
+    const bool check_it = (a.it % a.o.check_every == 0) || last;
+    const int ns = (a.it == 1) ? a.o.steps_start : 1;
+    const double tol = confirm ? a.o.confirm_tol : a.o.track_tol;
+    const int qmax = (confirm && check_it) ? a.o.steps_start : a.o.steps_max;
+    const bool stop = (q >= ns) && (res <= tol || q >= qmax);
+    NI[I_MORE + b] = stop ? 0 : 1;
+  }
 }
 
 // k_update: Z <- Z Qtop + R Qbot, W <- W Qtop + W2 Qbot (rows of one tile, in place).
+constexpr size_t UPD_SMEM = ((size_t)JN * ZLD + 2 * TS * ZLD) * sizeof(double);
 __global__ void __launch_bounds__(256) k_update(BigArgs a) {
-  __shared__ double Qs[JN * ZLD];
-  __shared__ double Zs[TS * ZLD], Rs[TS * ZLD];
+  extern __shared__ __align__(16) double sm[];
+  double* Qs = sm;                   // [JN][ZLD]
+  double* Zs = Qs + JN * ZLD;        // [TS][ZLD]
+  double* Rs = Zs + TS * ZLD;
   const Layout& L = a.L;
   const int b = blockIdx.z;
   if ((int)blockIdx.x >= L.nt[b]) return;
   const int slot = a.active[blockIdx.y];
   const int* NI = node_int(a, slot);
-  // NOTE: I_MORE was rewritten by k_rr for THIS step; the update must run for every (node, block) that ran the step,
-  // i.e. those with q advanced in this step: k_rr stores q; a block that did not run keeps MORE = 0 and q unchanged.
+  // the update runs for every (node, block) that ran this step: k_rr advanced its step counter to step + 1
   if (a.step > 0 && NI[I_Q + b] != a.step + 1) return;
   double* S = node_ptr(a, slot);
   const int N = L.N[b], tid = threadIdx.x, r0 = blockIdx.x * TS;
-  for (int e = tid; e < JN * PM; e += 256) Qs[(e >> 4) * ZLD + (e & 15)] = S[L.Q[b] + e];
+  for (int e = tid; e < JN * PM; e += 256) Qs[(e / PM) * ZLD + (e % PM)] = S[L.Q[b] + e];
   for (int pass = 0; pass < 2; ++pass) {
     double* A0 = S + (pass ? L.W[b] : L.Z[b]);
     const double* A1 = S + (pass ? L.W2[b] : L.R[b]);
     __syncthreads();
     for (int e = tid; e < TS * PM; e += 256) {
-      const int row = e >> 4, col = e & 15;
+      const int row = e / PM, col = e % PM;
       const bool ok = r0 + row < N;
       Zs[row * ZLD + col] = ok ? A0[(size_t)(r0 + row) * PM + col] : 0.0;
       Rs[row * ZLD + col] = ok ? A1[(size_t)(r0 + row) * PM + col] : 0.0;
     }
     __syncthreads();
-    const int row = tid >> 2, cb = (tid & 3) * 4;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    constexpr int CPT = TS * PM / 256;
+    const int row = tid / (PM / CPT), cb = (tid % (PM / CPT)) * CPT;
+    double acc[CPT];
 #pragma unroll
+    for (int q = 0; q < CPT; ++q) acc[q] = 0.0;
+#pragma unroll 4
     for (int c = 0; c < PM; ++c) {
       const double z = Zs[row * ZLD + c], r = Rs[row * ZLD + c];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fma(z, Qs[c * ZLD + cb + q], fma(r, Qs[(PM + c) * ZLD + cb + q], acc[q]));
+      for (int q = 0; q < CPT; ++q) acc[q] = fma(z, Qs[c * ZLD + cb + q], fma(r, Qs[(PM + c) * ZLD + cb + q], acc[q]));
     }
     if (r0 + row < N) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) A0[(size_t)(r0 + row) * PM + cb + q] = acc[q];
+      for (int q = 0; q < CPT; ++q) A0[(size_t)(r0 + row) * PM + cb + q] = acc[q];
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// CholQR of a panel by one CTA (start bases, periodic re-orthonormalisation of Z): P <- P L^-T, twice if asked.
+// CholQR of a panel by one CTA (start bases, periodic re-orthonormalisation of Z): P <- P T.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ void cholqr_cta(double* P, int N, int pcols, double* sm /* >= 4*PM*ZLD + 32 doubles */, int* ism /* PM ints */) {
-  double* M = sm; double* Lm = M + PM * ZLD; double* Tm = Lm + PM * ZLD; double* red = Tm + PM * ZLD;
+__device__ void cholqr_cta(double* P, int N, int pcols, double* sm /* >= 3*PM*ZLD doubles */, int* ism /* PM ints */) {
+  double* M = sm; double* Lm = M + PM * ZLD; double* Tm = Lm + PM * ZLD;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  // Gram: thread (a, b) pairs strided over rows by row-groups
-  const int ai = (tid & 255) >> 4, bi = tid & 15;
-  double s = 0.0;
-  if (tid < 256) for (int i = 0; i < N; ++i) s = fma(P[(size_t)i * PM + ai], P[(size_t)i * PM + bi], s);
-  if (tid < 256) M[ai * ZLD + bi] = s;
+  for (int e = tid; e < PM * PM; e += nthr) {
+    const int ai = e / PM, bi = e % PM;
+    double s = 0.0;
+    for (int i = 0; i < N; ++i) s = fma(P[(size_t)i * PM + ai], P[(size_t)i * PM + bi], s);
+    M[ai * ZLD + bi] = s;
+  }
   __syncthreads();
   if (tid < 32) chol_guard_warp(M, Lm, Tm, ism, tid, 1e-14, 0.0, pcols);
   __syncthreads();
-  (void)red;
+  // one row per thread, in place: out[j] = sum_{c <= j} row[c] T[c][j] (T upper triangular) -> go from the last column down
   for (int i = tid; i < N; i += nthr) {
-    double row[PM], out[PM];
-#pragma unroll
-    for (int c = 0; c < PM; ++c) row[c] = P[(size_t)i * PM + c];
-#pragma unroll
-    for (int j = 0; j < PM; ++j) {
+    double* row = P + (size_t)i * PM;
+    for (int j = PM - 1; j >= 0; --j) {
       double v = 0.0;
-#pragma unroll
-      for (int c = 0; c < PM; ++c) v = fma(row[c], Tm[c * ZLD + j], v);
-      out[j] = v;
+      for (int c = 0; c <= j; ++c) v = fma(row[c], Tm[c * ZLD + j], v);
+      row[j] = v;
     }
-#pragma unroll
-    for (int c = 0; c < PM; ++c) P[(size_t)i * PM + c] = out[c];
   }
   __syncthreads();
 }
-
 
 // start bases of the three blocks (same for every node): base[b] = CholQR2(hash panel); block 2 carries the k unit vectors
 // of the identity corner first.  grid = 3.
 __global__ void __launch_bounds__(256) k_start_basis(Layout L, double* base0, double* base1, double* base2, int seed) {
-  __shared__ double sm[4 * PM * ZLD + 32];
+  __shared__ double sm[3 * PM * ZLD];
   __shared__ int ism[PM];
   const int b = blockIdx.x;
   double* P = (b == 0) ? base0 : ((b == 1) ? base1 : base2);
@@ -1211,14 +1253,12 @@ __global__ void __launch_bounds__(256) k_start_basis(Layout L, double* base0, do
 }
 
 __global__ void __launch_bounds__(256) k_reorth(BigArgs a) {
-  __shared__ double sm[4 * PM * ZLD + 32];
+  __shared__ double sm[3 * PM * ZLD];
   __shared__ int ism[PM];
   const Layout& L = a.L;
   const int b = blockIdx.y;
   const int slot = a.active[blockIdx.x];
   const int* NI = node_int(a, slot);
-  const bool scheduled = (a.it % a.o.check_every == 0) || (a.it >= a.o.max_iter);
-  if (!scheduled && !NI[I_CONFIRM]) return;    // this node takes no part in an off-schedule check
   double* S = node_ptr(a, slot);
   cholqr_cta(S + L.Z[b], L.N[b], L.p[b], sm, ism);
 }
@@ -1380,11 +1420,13 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
   const int n = L.n, m = L.m, k = L.k, N1 = L.N[0], N2 = L.N[1];
   const int Lc = NI[I_L];
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* Zi = sm;
-  double* Zj = Zi + 3 * TS * ZLD;
-  double* sc = Zj + 3 * TS * ZLD;
-  double* tb = sc + 3 * PM;
-  double* xi = tb + TS * (TS + 1);
+  double* Zi_[3] = {sm + YOFF_I0, sm + YOFF_I1, sm + YOFF_I2};
+  double* Zj_[3] = {sm + YOFF_J0, sm + YOFF_J1, sm + YOFF_J2};
+  const int ld_[3] = {ZLD, ZLD, YLD2};
+  int nc_[3];
+  double* sc = sm + YOFF_SC;
+  double* ub = sm + YOFF_UB;
+  double* xi = sm + YOFF_X;
   double* xj = xi + (size_t)L.Lcap * TS;
   double* mgs = xj + (size_t)L.Lcap * TS;   // [Lc] mg / rho
   double* wred = mgs + L.Lcap + 1;          // [8][rcap]
@@ -1393,12 +1435,7 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
   const int t = blockIdx.x;
   const int nX = L.tn * L.tm, nT = L.tm * (L.tm + 1) / 2, nYt = L.tn * (L.tn + 1) / 2;
   for (int e = threadIdx.x; e < 8 * L.rcap; e += 256) wred[e] = 0.0;
-  for (int b = 0; b < 3; ++b) {
-    if (threadIdx.x < PM) {
-      const double th = S[L.th[b] + threadIdx.x];
-      sc[b * PM + threadIdx.x] = (threadIdx.x < L.p[b] && th > 0.0) ? sqrt(th) : 0.0;
-    }
-  }
+  for (int b = 0; b < 3; ++b) nc_[b] = stage_scale(sc + b * PM, S + L.th[b], L.p[b]);
   for (int l = threadIdx.x; l < Lc; l += 256) mgs[l] = S[L.vg + l] - fmax(S[L.vg + l], 0.0);
   __syncthreads();
   double rp = 0.0, rd = 0.0, np_ = 0.0, nd_ = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0, s8 = 0.0, s9 = 0.0;
@@ -1406,10 +1443,10 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
   double* part = S + L.chk_part + (size_t)t * NCHK;
   if (t < nX) {
     const int I = t / L.tm, J = t - I * L.tm, i0 = I * TS, j0 = J * TS;
-    stage_panel(Zi, S + L.Z[0], i0, n, sc);
-    stage_panel(Zj, S + L.Z[0] + (size_t)n * PM, j0, m, sc);
+    stage_panel(Zi_[0], ZLD, S + L.Z[0], i0, n, sc, nc_[0]);
+    stage_panel(Zj_[0], ZLD, S + L.Z[0] + (size_t)n * PM, j0, m, sc, nc_[0]);
     __syncthreads();
-    lowrank_tile(F, Zi, Zj, ty, tx);
+    lowrank_tile(F, Zi_[0], Zj_[0], ZLD, nc_[0], ty, tx);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -1433,10 +1470,10 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
     int I, J;
     lower_tile(t - nX, I, J);
     const int i0 = I * TS, j0 = J * TS;
-    stage_panel(Zi, S + L.Z[0] + (size_t)n * PM, i0, m, sc);
-    stage_panel(Zj, S + L.Z[0] + (size_t)n * PM, j0, m, sc);
+    stage_panel(Zi_[0], ZLD, S + L.Z[0] + (size_t)n * PM, i0, m, sc, nc_[0]);
+    stage_panel(Zj_[0], ZLD, S + L.Z[0] + (size_t)n * PM, j0, m, sc, nc_[0]);
     __syncthreads();
-    lowrank_tile(F, Zi, Zj, ty, tx);
+    lowrank_tile(F, Zi_[0], Zj_[0], ZLD, nc_[0], ty, tx);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -1458,8 +1495,8 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
     lower_tile(t - nX - nT, I, J);
     const int i0 = I * TS, j0 = J * TS;
     for (int b = 0; b < 3; ++b) {
-      stage_panel(Zi + b * TS * ZLD, S + L.Z[b], i0, n, sc + b * PM);
-      stage_panel(Zj + b * TS * ZLD, S + L.Z[b], j0, n, sc + b * PM);
+      stage_panel(Zi_[b], ld_[b], S + L.Z[b], i0, n, sc + b * PM, nc_[b]);
+      stage_panel(Zj_[b], ld_[b], S + L.Z[b], j0, n, sc + b * PM, nc_[b]);
     }
     for (int e = threadIdx.x; e < Lc * TS; e += 256) {
       const int l = e / TS, q = e - l * TS;
@@ -1468,9 +1505,9 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
     }
     __syncthreads();
     double F2[4][4], F3[4][4], yv[4][4];
-    lowrank_tile(F, Zi, Zj, ty, tx);
-    lowrank_tile(F2, Zi + TS * ZLD, Zj + TS * ZLD, ty, tx);
-    lowrank_tile(F3, Zi + 2 * TS * ZLD, Zj + 2 * TS * ZLD, ty, tx);
+    lowrank_tile(F, Zi_[0], Zj_[0], ld_[0], nc_[0], ty, tx);
+    lowrank_tile(F2, Zi_[1], Zj_[1], ld_[1], nc_[1], ty, tx);
+    lowrank_tile(F3, Zi_[2], Zj_[2], ld_[2], nc_[2], ty, tx);
     const double v4 = S[L.scal + S_V4];
     const double m4 = rho * (v4 - fmax(v4, 0.0));
     double trp = 0.0;
@@ -1520,7 +1557,9 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
   } else {
     const int ut = t - nX - nT - nYt;
     const int i0 = ut * TS;
-    stage_panel(Zi, S + L.Z[1], i0, n, sc + PM);
+    double* Zi = Zi_[1]; double* Zj = Zj_[1];
+    const int nc1 = nc_[1];
+    stage_panel(Zi, ZLD, S + L.Z[1], i0, n, sc + PM, nc1);
     for (int e = threadIdx.x; e < k * PM; e += 256) {
       const int j = e / PM, c = e - j * PM;
       Zj[j * ZLD + c] = S[L.Z[1] + (size_t)(n + j) * PM + c] * sc[PM + c];
@@ -1536,7 +1575,7 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
       double u = 0.0;
       if (i < n) {
         double Fv = 0.0;
-        for (int c = 0; c < PM; ++c) Fv = fma(Zi[il * ZLD + c], Zj[j * ZLD + c], Fv);
+        for (int c = 0; c < nc1; ++c) Fv = fma(Zi[il * ZLD + c], Zj[j * ZLD + c], Fv);
         u = S[L.U + (size_t)i * k + j];
         const double v5 = S[L.v5 + (size_t)i * k + j];
         const double lo5 = (i >= n - k + j) ? 0.0 : -sa;
@@ -1555,14 +1594,14 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
         nd_ = fmax(nd_, fabs(g));
         s9 += (m5 < 0.0) ? m5 * lo5 : m5 * sa;
       }
-      tb[il * (TS + 1) + j] = u;
+      ub[il * 17 + j] = u;
     }
     __syncthreads();
     double* rpart = S + L.rows_part + (size_t)(nYt + ut) * L.rcap;
     for (int e = threadIdx.x; e < Lc * k; e += 256) {
       const int l = e / k, j = e - l * k;
       double q = 0.0;
-      for (int il = 0; il < TS; ++il) q = fma(xi[l * TS + il], tb[il * (TS + 1) + j], q);
+      for (int il = 0; il < TS; ++il) q = fma(xi[l * TS + il], ub[il * 17 + j], q);
       rpart[1 + l * k + j] = q;
     }
     if (threadIdx.x == 0) rpart[0] = 0.0;
@@ -1572,7 +1611,7 @@ __global__ void __launch_bounds__(256) k_check(BigArgs a) {
       for (int e = threadIdx.x; e < k * k; e += 256) {
         const int i = e / k, j = e - i * k;
         double Fv = 0.0;
-        for (int c = 0; c < PM; ++c) Fv = fma(Zj[i * ZLD + c], Zj[j * ZLD + c], Fv);
+        for (int c = 0; c < nc1; ++c) Fv = fma(Zj[i * ZLD + c], Zj[j * ZLD + c], Fv);
         rp = fmax(rp, fabs(((i == j) ? 1.0 : 0.0) - Fv));
         np_ = fmax(np_, fabs(Fv));
         if (i == j) s7 += S[L.V[1] + (size_t)(n + i) * N2 + n + j] - Fv;
@@ -1598,11 +1637,6 @@ __global__ void __launch_bounds__(128) k_decide(BigArgs a, int* counters /* [0] 
   int* NI = node_int(a, slot);
   const int k = L.k, n = L.n, m = L.m, Lc = NI[I_L], tid = threadIdx.x;
   const int was_confirm = NI[I_CONFIRM];
-  const bool scheduled = (a.it % a.o.check_every == 0) || (a.it >= a.o.max_iter);
-  if (!scheduled && !was_confirm) {            // off-schedule check forced by another node: nothing to do for this one
-    if (tid == 0) atomicAdd(&counters[0], 1);
-    return;
-  }
   const int rq = 1 + Lc * (k + 1);
   double* R0 = sm;
   for (int q = tid; q < rq; q += 128) {
@@ -1751,7 +1785,7 @@ __global__ void __launch_bounds__(256) k_rescale(BigArgs a) {
   }
 }
 // theta after a rho change (separate tiny kernel so that k_rescale reads the old values everywhere)
-__global__ void __launch_bounds__(64) k_rescale_theta(BigArgs a) {
+__global__ void __launch_bounds__(3 * PM) k_rescale_theta(BigArgs a) {
   const Layout& L = a.L;
   const int slot = a.active[blockIdx.x];
   const int* NI = node_int(a, slot);

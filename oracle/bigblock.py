@@ -27,9 +27,9 @@ STATUS_CUTOFF = 4
 
 
 class BigOptions(Options):
-    def __init__(self, pm=16, steps_max=3, steps_start=6, track_tol=1e-3, confirm_tol=1e-9, cutoff=np.inf, seed=1, **kw):
+    def __init__(self, pm=32, pm3=16, steps_max=3, steps_start=6, track_tol=1e-3, confirm_tol=1e-9, cutoff=np.inf, seed=1, **kw):
         super().__init__(**kw)
-        self.pm, self.steps_max, self.steps_start = pm, steps_max, steps_start
+        self.pm, self.pm3, self.steps_max, self.steps_start = pm, pm3, steps_max, steps_start
         self.track_tol, self.confirm_tol, self.cutoff, self.seed = track_tol, confirm_tol, cutoff, seed
 
 
@@ -179,7 +179,9 @@ class BigState:
         self.V1 = np.zeros((n + m, n + m)); self.V2 = c.E2.copy(); self.V3 = c.I3.copy()
         self.v4 = c.ktr; self.v5 = np.zeros((n, k))
         self.vv = np.zeros((0, k)); self.vg = np.zeros(0)
-        self.tr = [Tracker(n + m, o.pm, +1, o.seed), Tracker(n + k, o.pm, +1, o.seed + 1), Tracker(n, o.pm, -1, o.seed + 2)]
+        # panel widths: 32 columns for [Y X; X' Theta] and [Y U; U' I] (deep nodes of config 4 hold up to ~28 positive
+        # eigenvalues), 16 for the negative side of aI - Y (a handful)
+        self.tr = [Tracker(n + m, o.pm, +1, o.seed), Tracker(n + k, o.pm, +1, o.seed + 1), Tracker(n, min(o.pm, o.pm3), -1, o.seed + 2)]
         # block 2 starts at E2 = diag(0, I_k): its positive side is spanned by the last k unit vectors
         t2 = self.tr[1]
         q = min(k, t2.p)
@@ -248,19 +250,22 @@ def solve_relaxation_big(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, s
         # ---- tracker steps on the new arguments
         for bidx, (tr, V) in enumerate(((t1, st.V1), (t2, st.V2), (t3, st.V3))):
             ns = o.steps_start if it == 1 else 1
-            conf = confirm or it >= o.max_iter
+            last = it >= o.max_iter
+            conf = confirm or last                  # decision pending: tight tolerance until the next scheduled check,
+            check_it = it % o.check_every == 0 or last   # steps_start steps allowed in the iteration of that check
             tol = o.confirm_tol if conf else o.track_tol
+            qmax = o.steps_start if (conf and check_it) else o.steps_max
             q = 0
             while True:
                 res = tr.step(V, it * 64 + q * 4 + bidx); q += 1
                 # res is the residual BEFORE the step: one more step measures the new basis only if asked for
-                if q >= ns and (res <= tol or q >= (o.steps_start if conf else o.steps_max)):
+                if q >= ns and (res <= tol or q >= qmax):
                     break
             nsteps_total += q
         if log is not None:
             log.append((it, t1.r(), t2.r(), t3.r(), t1.res, t2.res, t3.res))
 
-        if it % o.check_every == 0 or it == o.max_iter or confirm:
+        if it % o.check_every == 0 or it == o.max_iter:
             was_confirm = confirm
             confirm = False
             for t in st.tr:               # keep the tracked bases orthonormal over thousands of updates
@@ -305,7 +310,7 @@ def solve_relaxation_big(A, mask, gamma, k, cut_type=None, cuts=(), opts=None, s
                 if tracked_ok or it >= o.max_iter:
                     status = decision if tracked_ok else STATUS_ITERATION_LIMIT
                     break
-                confirm = True        # next iteration refines the trackers to confirm_tol and re-checks
+                confirm = True        # the trackers run at confirm_tol until the next scheduled check, which re-decides
                 continue
             if o.adaptive_rho and it % o.adapt_every == 0:
                 ratio = np.sqrt((rp / max(n_p, 1e-12)) / max(rd / max(n_d, 1e-12), 1e-30))
