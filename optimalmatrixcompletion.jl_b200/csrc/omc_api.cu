@@ -897,18 +897,22 @@ int32_t omc_smallest_eigvecs_batch(int32_t n, int32_t k, int32_t B, const double
   if (nev != 1 && nev != 2) return fail(OMC_ERR_ARG, "nev must be 1 or 2 (OMC.jl:2467,2470)");
   if (nev > n) return fail(OMC_ERR_ARG, "nev > n");
   const omc::Geo g = omc::make_geo(n);
-  if (g.NP > 104) return fail(OMC_ERR_UNSUPPORTED, "n = %d > 104: in-SM eigensolver only in this build", n);
   DevBuf<double> dY, dU, dL, dV, dB;
   DevBuf<int> dF;
   CU(dY.alloc((size_t)B * n * n)); CU(dU.alloc((size_t)B * n * k)); CU(dL.alloc((size_t)B * nev));
   CU(dV.alloc((size_t)B * n * nev)); CU(dB.alloc((size_t)B * n)); CU(dF.alloc(B));
   CU(cudaMemcpyAsync(dY.p, Y, (size_t)B * n * n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
   CU(cudaMemcpyAsync(dU.p, U, (size_t)B * n * k * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-  const size_t smem = omc::eigsep_smem_bytes(n);
-  auto kern = omc::eigsep_kernel<256>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = B < g_sm_count * 2 ? B : g_sm_count * 2;
-  kern<<<grid, 256, smem, g_stream>>>(n, k, B, dY.p, dU.p, nev, dL.p, dV.p, dB.p, dF.p);
+  if (g.NP > 104) {   // beyond the in-SM eigensolver: restarted Lanczos, one CTA per node (omc_big.cuh: k_lanczos)
+    const int rc = omcbig::big_smallest_eigvecs(n, k, B, dY.p, dU.p, nev, dL.p, dV.p, dB.p, dF.p, g_stream);
+    if (rc != 0) return fail(rc == -4 ? OMC_ERR_UNSUPPORTED : OMC_ERR_CUDA, "%s", omcbig::big_last_error());
+  } else {
+    const size_t smem = omc::eigsep_smem_bytes(n);
+    auto kern = omc::eigsep_kernel<256>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = B < g_sm_count * 2 ? B : g_sm_count * 2;
+    kern<<<grid, 256, smem, g_stream>>>(n, k, B, dY.p, dU.p, nev, dL.p, dV.p, dB.p, dF.p);
+  }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(lam, dL.p, (size_t)B * nev * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CU(cudaMemcpyAsync(vec, dV.p, (size_t)B * n * nev * sizeof(double), cudaMemcpyDeviceToHost, g_stream));

@@ -151,6 +151,7 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
   a.o.fix_linear3_right = ro->fix_linear3_right; a.o.cut_type = pv.cut_type;
   a.o.track_tol = tune->track_tol; a.o.confirm_tol = tune->confirm_tol; a.o.adapt_thresh = 5.0;
   a.o.jacobi_sweeps = tune->jacobi_sweeps;
+  a.o.window = tune->window;
   a.o.steps_max = tune->steps_max; a.o.steps_start = tune->steps_start; a.o.infeasible_by_bound = tune->infeasible_by_bound;
   const auto t_start = std::chrono::steady_clock::now();
   BCU(cudaEventRecord(f->ev0, st));
@@ -288,8 +289,24 @@ int big_prepare_problem(int n, int m, const double* A, const double* Mk, double*
   return 0;
 }
 
+int big_smallest_eigvecs(int n, int k, int B, const double* dY, const double* dU, int nev, double* dlam, double* dvec, double* dbp,
+                         int* dfeas, cudaStream_t st) {
+  if (k > 16) { g_berr = "separation oracle: k > 16 unsupported"; return -4; }
+  double* ws = nullptr;
+  BCU(cudaMalloc(&ws, (size_t)B * (LM + 3) * n * sizeof(double)));
+  const size_t smem = LANCZOS_SMEM_FIXED + (size_t)n * sizeof(double);
+  if (smem > 227 * 1024) { cudaFree(ws); g_berr = "separation oracle: n too large for the shared-memory vector"; return -4; }
+  BCU(cudaFuncSetAttribute(k_lanczos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_lanczos<<<B, 256, smem, st>>>(n, k, B, dY, dU, nev, ws, dlam, dvec, dbp, dfeas, 1e-10, 40);
+  BCU(cudaGetLastError());
+  BCU(cudaStreamSynchronize(st));
+  cudaFree(ws);
+  return 0;
+}
+
 void big_default_tuning(BigTuning* t) {
   t->jacobi_sweeps = 3;
+  t->window = 2;
   t->steps_max = 3; t->steps_start = 6; t->track_tol = 1e-3; t->confirm_tol = 1e-9; t->seed = 1; t->infeasible_by_bound = 1;
 }
 

@@ -122,7 +122,7 @@ inline Layout make_layout(int n, int m, int k, int Lcap) {
 
 struct Opts {
   double eps_abs, eps_rel, sigma, alpha, rho0, cutoff, track_tol, confirm_tol, adapt_thresh;
-  int max_iter, check_every, adapt_every, steps_max, steps_start, fix_linear3_right, cut_type, infeasible_by_bound, jacobi_sweeps;
+  int max_iter, check_every, adapt_every, steps_max, steps_start, fix_linear3_right, cut_type, infeasible_by_bound, jacobi_sweeps, window;
 };
 
 struct BigArgs {
@@ -729,13 +729,26 @@ __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
     }
     __syncthreads();
     double* part = S + (pass ? L.partB[b] : L.partA[b]) + (size_t)blockIdx.x * PM * PM;
-    for (int e = tid; e < PM * PM; e += 128) {
-      const int ai = e / PM, bi = e % PM;
-      double s = 0.0;
-#pragma unroll 8
-      for (int r = 0; r < TS; ++r) s = fma(Ls[r * ZLD + ai], Ws[r * ZLD + bi], s);
-      part[e] = s;
+    // 2 x 4 outputs per thread (16 x 8 threads cover 32 x 32)
+    const int ai = (tid >> 3) * 2, bi = (tid & 7) * 4;
+    double sacc[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) sacc[u][v] = 0.0;
+#pragma unroll 4
+    for (int r = 0; r < TS; ++r) {
+      const double l0 = Ls[r * ZLD + ai], l1 = Ls[r * ZLD + ai + 1];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const double w = Ws[r * ZLD + bi + v];
+        sacc[0][v] = fma(l0, w, sacc[0][v]); sacc[1][v] = fma(l1, w, sacc[1][v]);
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) part[(ai + u) * PM + bi + v] = sacc[u][v];
   }
 }
 
@@ -809,6 +822,17 @@ __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
           if (cb + q == pc)
             acc[q] = amp * hash_unit((unsigned long long)(r0 + row), (unsigned long long)(a.it * 64 + a.step * 4 + b), 12345ull);
       }
+      // residual window: only the residuals of the positive Ritz pairs and of the first `window` guard columns (and the
+      // probe) enter the trial space; the Rayleigh-Ritz still runs over ALL of Z, so no Ritz value ever gets worse.  The
+      // zero columns are dropped by the Cholesky guard and k_rr's Jacobi runs on p + (r + window + 1) indices instead of 2 p.
+      if (a.o.window > 0 && a.it >= 2) {
+        int rprev = 0;
+        for (int c = 0; c < L.p[b]; ++c) rprev += (S[L.th[b] + c] > 0.0) ? 1 : 0;
+        const int na = rprev + a.o.window;
+#pragma unroll
+        for (int q = 0; q < CPT; ++q)
+          if (cb + q >= na && cb + q != pc) acc[q] = 0.0;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -821,13 +845,16 @@ __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
   {
     const double* Lm = (pass == 2) ? Rs : Zs;
     double* part = S + ((pass & 1) ? L.partA[b] : L.partB[b]) + (size_t)blockIdx.x * PM * PM;
-    for (int e = tid; e < PM * PM; e += 256) {
-      const int ai = e / PM, bi = e % PM;
-      double s = 0.0;
+    // 2 x 2 outputs per thread (16 x 16 threads cover PM x PM = 32 x 32): one shared-memory load per FMA instead of two
+    static_assert(PM == 32, "Gram tiling assumes PM = 32");
+    const int ai = (tid >> 4) * 2, bi = (tid & 15) * 2;
+    double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
 #pragma unroll 8
-      for (int r = 0; r < TS; ++r) s = fma(Lm[r * ZLD + ai], Rs[r * ZLD + bi], s);
-      part[e] = s;
+    for (int r = 0; r < TS; ++r) {
+      const double l0 = Lm[r * ZLD + ai], l1 = Lm[r * ZLD + ai + 1], r0v = Rs[r * ZLD + bi], r1v = Rs[r * ZLD + bi + 1];
+      s00 = fma(l0, r0v, s00); s01 = fma(l0, r1v, s01); s10 = fma(l1, r0v, s10); s11 = fma(l1, r1v, s11);
     }
+    part[ai * PM + bi] = s00; part[ai * PM + bi + 1] = s01; part[(ai + 1) * PM + bi] = s10; part[(ai + 1) * PM + bi + 1] = s11;
   }
 }
 
@@ -907,6 +934,97 @@ __global__ void __launch_bounds__(256) k_gram(BigArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// CTA-parallel cyclic Jacobi (256 threads) on the n2 x n2 symmetric matrix Ac (shared memory, ld JLD, n2 even <= JN); Qc
+// accumulates the rotations (identity on entry).  Round-robin ordering: n2 - 1 rounds of n2 / 2 disjoint pairs; per round the
+// first n2 / 2 threads compute the rotations, then all row updates, then all column updates of Ac and Qc (all loads of a phase
+// are issued before its first store: the pairs are disjoint).  The thread -> (pair, column) map is division-free.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int JN = 2 * PM, JLD = JN + 1;
+__device__ __forceinline__ void jacobi_cta(double* Ac, double* Qc, int n2, int max_sweeps, double off_tol, double amax, double* cs, int* pq,
+                                           int* flag, double* red) {
+  const int tid = threadIdx.x;
+  const int npair = n2 >> 1;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    double off = 0.0;
+    {
+      const int cj = tid & (JN - 1);
+      if (cj < n2)
+        for (int i = tid >> 6; i < n2; i += 4)
+          if (i != cj) off = fmax(off, fabs(Ac[i * JLD + cj]));
+    }
+    off = block_max(off, red);
+    if (off <= off_tol || off < 1e-300) break;
+    for (int rnd = 0; rnd < n2 - 1; ++rnd) {
+      if (tid == 0) flag[0] = 0;
+      __syncthreads();
+      if (tid < npair) {
+        int p_, q_;
+        if (tid == 0) { p_ = n2 - 1; q_ = rnd; }
+        else { p_ = (rnd + tid) % (n2 - 1); q_ = (rnd + n2 - 1 - tid) % (n2 - 1); }
+        if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
+        const double apq = Ac[p_ * JLD + q_], app = Ac[p_ * JLD + p_], aqq = Ac[q_ * JLD + q_];
+        double c_ = 1.0, s_ = 0.0;
+        if (fabs(apq) > 1e-16 * amax && fabs(apq) > 1e-17 * (fabs(app) + fabs(aqq))) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t_ = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c_ = rsqrt(1.0 + t_ * t_);
+          s_ = t_ * c_;
+          flag[0] = 1;
+        }
+        cs[tid * 2 + 0] = c_; cs[tid * 2 + 1] = s_;
+        pq[tid * 2 + 0] = p_; pq[tid * 2 + 1] = q_;
+      }
+      __syncthreads();
+      if (!flag[0]) continue;
+      constexpr int PPT = PM / 4;     // pairs per thread
+      const int cc = tid & (JN - 1), g0 = tid >> 6;
+      double ap[PPT], aq[PPT], qp[PPT], qq[PPT];
+      if (cc < n2) {
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+          const int i = g0 + 4 * u;
+          if (i < npair) { ap[u] = Ac[pq[2 * i] * JLD + cc]; aq[u] = Ac[pq[2 * i + 1] * JLD + cc]; }
+        }
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+          const int i = g0 + 4 * u;
+          if (i < npair) {
+            const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
+            Ac[pq[2 * i] * JLD + cc] = c_ * ap[u] - s_ * aq[u];
+            Ac[pq[2 * i + 1] * JLD + cc] = s_ * ap[u] + c_ * aq[u];
+          }
+        }
+      }
+      __syncthreads();
+      if (cc < n2) {
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+          const int i = g0 + 4 * u;
+          if (i < npair) {
+            const int p_ = pq[2 * i], q_ = pq[2 * i + 1];
+            ap[u] = Ac[cc * JLD + p_]; aq[u] = Ac[cc * JLD + q_];
+            qp[u] = Qc[cc * JLD + p_]; qq[u] = Qc[cc * JLD + q_];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+          const int i = g0 + 4 * u;
+          if (i < npair) {
+            const int p_ = pq[2 * i], q_ = pq[2 * i + 1];
+            const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
+            Ac[cc * JLD + p_] = c_ * ap[u] - s_ * aq[u];
+            Ac[cc * JLD + q_] = s_ * ap[u] + c_ * aq[u];
+            Qc[cc * JLD + p_] = c_ * qp[u] - s_ * qq[u];
+            Qc[cc * JLD + q_] = s_ * qp[u] + c_ * qq[u];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // k_rr: one CTA (256 threads) per (node, block).  M = R'R (saved by k_gram) -> guarded Cholesky -> T = D^-1 L~^-T; the second
 // product gave partA = Z'(V R), partB = R'(V R): Xc = (Z'VR) T, C = T'(R'VR) T; Rayleigh-Ritz on [[H, Xc], [Xc', C]]
 // (2 PM x 2 PM) by a CTA-parallel cyclic Jacobi (round-robin pairs; per round: PM rotations, then all row updates, then all
@@ -916,7 +1034,6 @@ __global__ void __launch_bounds__(256) k_gram(BigArgs a) {
 // locked on (off-diagonal = Ritz residual), so `jacobi_sweeps` = 3 resolves it to rounding there, and an unconverged
 // start-phase Rayleigh-Ritz is finished by the following tracker steps.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int JN = 2 * PM, JLD = JN + 1;
 constexpr size_t RR_SMEM = ((size_t)2 * JN * JLD + 3 * PM * ZLD + 2 * PM + JN + 64) * sizeof(double) + (3 * PM + 2 * JN + 8) * sizeof(int);
 
 __global__ void __launch_bounds__(256) k_rr(BigArgs a) {
@@ -1025,71 +1142,7 @@ __global__ void __launch_bounds__(256) k_rr(BigArgs a) {
   __syncthreads();
   const int npair = n2 >> 1;
   // ---- cyclic Jacobi on Ac (n2 x n2)
-  const double off_tol = ((NI[I_CONFIRM] || a.it >= a.o.max_iter) ? 1e-14 : 1e-12) * amax;
-  for (int sweep = 0; sweep < a.o.jacobi_sweeps; ++sweep) {
-    double off = 0.0;
-    {
-      const int cj = tid & (JN - 1);
-      if (cj < n2)
-        for (int i = tid >> 6; i < n2; i += 4)
-          if (i != cj) off = fmax(off, fabs(Ac[i * JLD + cj]));
-    }
-    off = block_max(off, red);
-    if (off <= off_tol || off < 1e-300) break;
-    for (int rnd = 0; rnd < n2 - 1; ++rnd) {
-      if (tid == 0) flag[0] = 0;
-      __syncthreads();
-      if (tid < npair) {
-        int p_, q_;
-        if (tid == 0) { p_ = n2 - 1; q_ = rnd; }
-        else { p_ = (rnd + tid) % (n2 - 1); q_ = (rnd + n2 - 1 - tid) % (n2 - 1); }
-        if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
-        const double apq = Ac[p_ * JLD + q_], app = Ac[p_ * JLD + p_], aqq = Ac[q_ * JLD + q_];
-        double c_ = 1.0, s_ = 0.0;
-        if (fabs(apq) > 1e-16 * amax && fabs(apq) > 1e-17 * sqrt(fabs(app * aqq))) {
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double t_ = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c_ = rsqrt(1.0 + t_ * t_);
-          s_ = t_ * c_;
-          flag[0] = 1;
-        }
-        cs[tid * 2 + 0] = c_; cs[tid * 2 + 1] = s_;
-        pq[tid * 2 + 0] = p_; pq[tid * 2 + 1] = q_;
-      }
-      __syncthreads();
-      if (!flag[0]) continue;
-      // rows: Ac <- J' Ac.  item = (pair i, column c); division-free map: column = tid & 63, pairs strided by 4
-      const int cc = tid & (JN - 1), g0 = tid >> 6;
-      if (cc < n2) {
-        for (int i = g0; i < npair; i += 4) {
-          const double s_ = cs[2 * i + 1];
-          if (s_ == 0.0) continue;
-          const double c_ = cs[2 * i];
-          const int p_ = pq[2 * i], q_ = pq[2 * i + 1];
-          const double ap = Ac[p_ * JLD + cc], aq = Ac[q_ * JLD + cc];
-          Ac[p_ * JLD + cc] = c_ * ap - s_ * aq;
-          Ac[q_ * JLD + cc] = s_ * ap + c_ * aq;
-        }
-      }
-      __syncthreads();
-      // columns: Ac <- Ac J, Qc <- Qc J.  item = (pair i, row r)
-      for (int i = g0; i < npair; i += 4) {
-        const int r = cc;
-        if (r >= n2) break;
-        const double s_ = cs[2 * i + 1];
-        if (s_ == 0.0) continue;
-        const double c_ = cs[2 * i];
-        const int p_ = pq[2 * i], q_ = pq[2 * i + 1];
-        const double ap = Ac[r * JLD + p_], aq = Ac[r * JLD + q_];
-        Ac[r * JLD + p_] = c_ * ap - s_ * aq;
-        Ac[r * JLD + q_] = s_ * ap + c_ * aq;
-        const double qp = Qc[r * JLD + p_], qq = Qc[r * JLD + q_];
-        Qc[r * JLD + p_] = c_ * qp - s_ * qq;
-        Qc[r * JLD + q_] = s_ * qp + c_ * qq;
-      }
-      __syncthreads();
-    }
-  }
+  jacobi_cta(Ac, Qc, n2, a.o.jacobi_sweeps, ((NI[I_CONFIRM] || a.it >= a.o.max_iter) ? 1e-14 : 1e-12) * amax, amax, cs, pq, flag, red);
   if (tid < n2) lam[tid] = Ac[tid * JLD + tid];
   __syncthreads();
   // rank by value (descending, ties by index); the padding index sits at the bottom
@@ -1820,6 +1873,193 @@ __global__ void __launch_bounds__(256) k_extract(BigArgs a, int B, double* outX,
     lower_bound[slot] = S[L.scal + S_LB];
     objective[slot] = (st == OMC_STATUS_CUTOFF) ? S[L.scal + S_LB] : S[L.scal + S_OBJP];
     res[2 * slot] = S[L.scal + S_RP]; res[2 * slot + 1] = S[L.scal + S_RD];
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_lanczos: separation oracle for n beyond the in-SM eigensolver (omc_eigsep.cuh, n <= 104): the smallest one or two
+// eigenpairs of M = U U' - Y (OMC.jl:2466-2477; feasibility test lambda_min >= -1e-6, OMC.jl:1272-1277) by restarted
+// Lanczos with full reorthogonalisation on Aop = Y - U U' (largest of Aop = - smallest of M).  One CTA per node; the
+// matrix-vector product never forms U U' (y = Y v - U (U'v)): one warp per row of Y, lanes along the row, warp-shuffle
+// reduction.  LM = 48 steps per cycle; the LM x LM tridiagonal is diagonalised by the CTA Jacobi; a cycle restarts from the
+// Ritz vector until |beta_m s_m| <= tol |theta|.  The second pair (nev = 2) is found by a second run deflated against the
+// first vector.  Y, U column-major per node (Y symmetric).  ws: per node (LM + 3) * n doubles.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int LM = 48;
+constexpr size_t LANCZOS_SMEM_FIXED = ((size_t)2 * LM * JLD + 4 * LM + 2 * PM + 64 + 16) * sizeof(double) + (2 * PM + 16) * sizeof(int);
+
+__global__ void __launch_bounds__(256) k_lanczos(int n, int k, int B, const double* __restrict__ Y, const double* __restrict__ U, int nev,
+                                                 double* __restrict__ ws, double* __restrict__ lam_out, double* __restrict__ vec_out,
+                                                 double* __restrict__ bp_out, int* __restrict__ feas_out, double tol, int max_cycles) {
+  extern __shared__ __align__(16) double sm[];
+  double* T = sm;                        // [LM][JLD]
+  double* E = T + LM * JLD;              // [LM][JLD] eigenvectors of T
+  double* alpha = E + LM * JLD;          // [LM]
+  double* beta = alpha + LM;             // [LM + 1]
+  double* coef = beta + LM + 1;          // [LM + 2]
+  double* cs = coef + LM + 2;            // [2 PM]
+  double* red = cs + 2 * PM;             // [64]
+  double* tk = red + 64;                 // [16] U'v
+  double* vs = tk + 16;                  // [n]  current vector
+  int* pq = reinterpret_cast<int*>(vs + n);
+  int* flag = pq + 2 * PM;
+  const int node = blockIdx.x;
+  if (node >= B) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* Yn = Y + (size_t)node * n * n;
+  const double* Un = U + (size_t)node * n * k;
+  double* Qv = ws + (size_t)node * (LM + 3) * n;     // Lanczos vectors q_0 .. q_LM
+  double* X0 = Qv + (size_t)(LM + 1) * n;             // converged vectors
+  double* X1 = X0 + n;
+  double theta[2] = {0.0, 0.0};
+  for (int want = 0; want < nev; ++want) {
+    double* Xw = want ? X1 : X0;
+    // start vector: deterministic pseudo-random, deflated
+    for (int i = tid; i < n; i += 256) vs[i] = hash_unit((unsigned long long)i, (unsigned long long)(7 + want), 777ull);
+    __syncthreads();
+    double th = 0.0, resid = 1e300;
+    for (int cyc = 0; cyc < max_cycles; ++cyc) {
+      // q_0 = normalised (deflated) vs
+      if (want == 1) {
+        double d = 0.0;
+        for (int i = tid; i < n; i += 256) d += X0[i] * vs[i];
+        d = block_sum(d, red);
+        for (int i = tid; i < n; i += 256) vs[i] -= d * X0[i];
+        __syncthreads();
+      }
+      double nr = 0.0;
+      for (int i = tid; i < n; i += 256) nr += vs[i] * vs[i];
+      nr = sqrt(block_sum(nr, red));
+      for (int i = tid; i < n; i += 256) { vs[i] /= nr; Qv[i] = vs[i]; }
+      __syncthreads();
+      int mdone = 0;
+      for (int j = 0; j < LM; ++j) {
+        // w = Aop q_j  -> Qv[j + 1]
+        if (warp < 8) {
+          for (int c = warp; c < k; c += 8) {
+            double d = 0.0;
+            for (int i = lane; i < n; i += 32) d += Un[(size_t)c * n + i] * vs[i];
+            d = warp_sum(d);
+            if (lane == 0) tk[c] = d;
+          }
+        }
+        __syncthreads();
+        double* w = Qv + (size_t)(j + 1) * n;
+        for (int i = warp; i < n; i += 8) {
+          const double* yr = Yn + (size_t)i * n;
+          double d = 0.0;
+          for (int c = lane; c < n; c += 32) d = fma(yr[c], vs[c], d);
+          d = warp_sum(d);
+          if (lane == 0) {
+            for (int c = 0; c < k; ++c) d -= Un[(size_t)c * n + i] * tk[c];
+            w[i] = d;
+          }
+        }
+        __syncthreads();
+        // alpha_j, full reorthogonalisation against q_0..q_j (and the deflated vector), twice
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int q = warp; q <= j + want; q += 8) {
+            const double* qq = (q <= j) ? Qv + (size_t)q * n : X0;
+            double d = 0.0;
+            for (int i = lane; i < n; i += 32) d = fma(qq[i], w[i], d);
+            d = warp_sum(d);
+            if (lane == 0) coef[q] = d;
+          }
+          __syncthreads();
+          if (pass == 0 && tid == 0) alpha[j] = coef[j];
+          for (int i = tid; i < n; i += 256) {
+            double v = w[i];
+            for (int q = 0; q <= j; ++q) v = fma(-coef[q], Qv[(size_t)q * n + i], v);
+            if (want == 1) v = fma(-coef[j + 1], X0[i], v);
+            w[i] = v;
+          }
+          __syncthreads();
+          if (pass == 1 && tid == 0) alpha[j] += coef[j];
+        }
+        double bn = 0.0;
+        for (int i = tid; i < n; i += 256) bn += w[i] * w[i];
+        bn = sqrt(block_sum(bn, red));
+        if (tid == 0) beta[j + 1] = bn;
+        mdone = j + 1;
+        if (bn < 1e-13) break;              // invariant subspace found
+        for (int i = tid; i < n; i += 256) { const double v = w[i] / bn; w[i] = v; vs[i] = v; }
+        __syncthreads();
+      }
+      // T (mdone x mdone, padded to even) -> Jacobi
+      const int mm = mdone, n2 = mm + (mm & 1);
+      for (int e = tid; e < n2 * JLD; e += 256) { T[e] = 0.0; E[e] = 0.0; }
+      __syncthreads();
+      if (tid < n2) {
+        E[tid * JLD + tid] = 1.0;
+        if (tid < mm) {
+          T[tid * JLD + tid] = alpha[tid];
+          if (tid + 1 < mm) { T[tid * JLD + tid + 1] = beta[tid + 1]; T[(tid + 1) * JLD + tid] = beta[tid + 1]; }
+        } else T[tid * JLD + tid] = -1e300;     // padding index at the bottom
+      }
+      __syncthreads();
+      double amax = 0.0;
+      if (tid < mm) amax = fmax(fabs(alpha[tid]), (tid + 1 < mm) ? fabs(beta[tid + 1]) : 0.0);
+      amax = block_max(amax, red);
+      if (n2 > mm && tid == 0) T[(n2 - 1) * JLD + n2 - 1] = -64.0 * (amax + 1.0);
+      __syncthreads();
+      jacobi_cta(T, E, n2, 30, 1e-15 * amax, amax, cs, pq, flag, red);
+      // largest Ritz value (the padding sits far below)
+      if (tid == 0) {
+        int best = 0;
+        for (int i = 1; i < mm; ++i) if (T[i * JLD + i] > T[best * JLD + best]) best = i;
+        flag[1] = best;
+      }
+      __syncthreads();
+      const int best = flag[1];
+      th = T[best * JLD + best];
+      resid = fabs(beta[mm] * E[(mm - 1) * JLD + best]);
+      // Ritz vector -> vs (and Xw)
+      for (int i = tid; i < n; i += 256) {
+        double v = 0.0;
+        for (int q = 0; q < mm; ++q) v = fma(E[q * JLD + best], Qv[(size_t)q * n + i], v);
+        vs[i] = v;
+      }
+      __syncthreads();
+      if (resid <= tol * fmax(1.0, fabs(th)) || mm < LM) break;
+    }
+    double nr = 0.0;
+    for (int i = tid; i < n; i += 256) nr += vs[i] * vs[i];
+    nr = sqrt(block_sum(nr, red));
+    for (int i = tid; i < n; i += 256) Xw[i] = vs[i] / nr;
+    __syncthreads();
+    theta[want] = th;
+  }
+  // outputs: eigenvalues of M ascending (= -theta), vectors with the largest-|.| component positive, breakpoint vector
+  double sgn[2] = {1.0, 1.0};
+  for (int q = 0; q < nev; ++q) {
+    const double* Xq = q ? X1 : X0;
+    double bv = 0.0; int bi = n;
+    for (int i = tid; i < n; i += 256) { const double av = fabs(Xq[i]); if (av > bv) { bv = av; bi = i; } }
+    // block arg-max (first index on ties)
+    const double bmax = block_max(bv, red);
+    int cand = (bv == bmax) ? bi : n;
+    __syncthreads();
+    if (tid == 0) flag[2] = n;
+    __syncthreads();
+    atomicMin(&flag[2], cand);
+    __syncthreads();
+    sgn[q] = (Xq[flag[2]] < 0.0) ? -1.0 : 1.0;
+    __syncthreads();
+  }
+  const double l0 = -theta[0], l1 = (nev == 2) ? -theta[1] : 0.0;
+  double w0 = 1.0, w1 = 0.0;
+  if (nev == 2 && l1 < -1e-10) { const double nr = sqrt(l0 * l0 + l1 * l1); w0 = fabs(l0) / nr; w1 = fabs(l1) / nr; }   // OMC.jl:2471-2473
+  for (int i = tid; i < n; i += 256) {
+    const double v0 = sgn[0] * X0[i], v1 = (nev == 2) ? sgn[1] * X1[i] : 0.0;
+    vec_out[(size_t)node * n * nev + i] = v0;
+    if (nev == 2) vec_out[(size_t)node * n * nev + n + i] = v1;
+    bp_out[(size_t)node * n + i] = w0 * v0 + w1 * v1;
+  }
+  if (tid == 0) {
+    lam_out[(size_t)node * nev] = l0;
+    if (nev == 2) lam_out[(size_t)node * nev + 1] = l1;
+    feas_out[node] = (l0 >= -1e-6) ? 1 : 0;        // OMC.jl:1274-1276
   }
 }
 

@@ -20,7 +20,7 @@ struct BigProblemView {
 };
 
 struct BigTuning {
-  int steps_max, steps_start, seed, infeasible_by_bound, jacobi_sweeps;
+  int steps_max, steps_start, seed, infeasible_by_bound, jacobi_sweeps, window;
   double track_tol, confirm_tol;
 };
 
@@ -44,5 +44,8 @@ const BigStats* big_stats(const BigFrontier* f);
 // 15 X, 16 Y, 17 T, 18 U (scaled variables, row-major).  Returns the number of doubles (cap = capacity of out), < 0 on error.
 long long big_debug_fetch(BigFrontier* f, int node, int which, double* out, long long cap);
 void big_destroy(BigFrontier* f);
+// separation oracle for n > 104 (restarted Lanczos, one CTA per node); device pointers, column-major Y / U per node
+int big_smallest_eigvecs(int n, int k, int B, const double* dY, const double* dU, int nev, double* dlam, double* dvec, double* dbp,
+                         int* dfeas, cudaStream_t st);
 
 }  // namespace omcbig

@@ -27,9 +27,9 @@ STATUS_CUTOFF = 4
 
 
 class BigOptions(Options):
-    def __init__(self, pm=32, pm3=16, steps_max=3, steps_start=6, track_tol=1e-3, confirm_tol=1e-9, cutoff=np.inf, seed=1, **kw):
+    def __init__(self, pm=32, pm3=16, window=2, steps_max=3, steps_start=6, track_tol=1e-3, confirm_tol=1e-9, cutoff=np.inf, seed=1, **kw):
         super().__init__(**kw)
-        self.pm, self.pm3, self.steps_max, self.steps_start = pm, pm3, steps_max, steps_start
+        self.pm, self.pm3, self.window, self.steps_max, self.steps_start = pm, pm3, window, steps_max, steps_start
         self.track_tol, self.confirm_tol, self.cutoff, self.seed = track_tol, confirm_tol, cutoff, seed
 
 
@@ -94,8 +94,9 @@ def cholqr(R, piv_rel=1e-12, floor2=0.0, rel_small=0.0, probe=-1):
 class Tracker:
     """Top-``p`` eigenpairs of side * V for a slowly varying symmetric V (one PSD block)."""
 
-    def __init__(self, N, pm, side, seed, Z0=None, th0=None):
+    def __init__(self, N, pm, side, seed, Z0=None, th0=None, window=0):
         self.N, self.side = N, side
+        self.window = window      # > 0: only the r + window leading Ritz pairs (and the probe) take part in a step
         self.p = p = min(pm, N)          # N <= pm: the panel is a complete eigenbasis and the projection is exact
         self.Z = start_basis(N, p, seed) if Z0 is None else Z0.copy()
         self.th = np.zeros(p) if th0 is None else th0.copy()
@@ -110,6 +111,18 @@ class Tracker:
         H = Z.T @ W
         R = W - Z @ H
         pc = self.p - 1
+        # residual window: only the residuals of the positive Ritz pairs and of the first `window` guard columns (and the
+        # probe) enter the trial space; the Rayleigh-Ritz still runs over ALL of Z, so no Ritz value ever gets worse -- the
+        # far guard columns are simply not refined by their own residuals (they are rotated with everything else)
+        p = self.p
+        na = p
+        if self.window > 0 and tag >= 128:
+            na = min(p, int((self.th > 0).sum()) + self.window)
+        if na < p:
+            keep = R[:, pc].copy() if pc >= na else None
+            R[:, na:] = 0.0
+            if keep is not None:
+                R[:, pc] = keep
         if pc > 0:
             # the trial space [Z, R] stays generic: an eigenvector exactly orthogonal to Z and to every residual (the identity
             # corner of [Y U; U' I] at a node without cuts) would otherwise never be found again once it left the panel
@@ -131,7 +144,6 @@ class Tracker:
         Rt, valid = cholqr(R, piv_rel=1e-10, floor2=1e-20 * hs2, rel_small=1e-10, probe=pc if pc > 0 else -1)
         W2 = sd * (V @ Rt)
         self.nprod += 2
-        p = self.p
         G = np.zeros((2 * p, 2 * p))
         G[:p, :p] = 0.5 * (H + H.T)
         Xc = Z.T @ W2
@@ -181,7 +193,8 @@ class BigState:
         self.vv = np.zeros((0, k)); self.vg = np.zeros(0)
         # panel widths: 32 columns for [Y X; X' Theta] and [Y U; U' I] (deep nodes of config 4 hold up to ~28 positive
         # eigenvalues), 16 for the negative side of aI - Y (a handful)
-        self.tr = [Tracker(n + m, o.pm, +1, o.seed), Tracker(n + k, o.pm, +1, o.seed + 1), Tracker(n, min(o.pm, o.pm3), -1, o.seed + 2)]
+        self.tr = [Tracker(n + m, o.pm, +1, o.seed, window=o.window), Tracker(n + k, o.pm, +1, o.seed + 1, window=o.window),
+                   Tracker(n, min(o.pm, o.pm3), -1, o.seed + 2, window=o.window)]
         # block 2 starts at E2 = diag(0, I_k): its positive side is spanned by the last k unit vectors
         t2 = self.tr[1]
         q = min(k, t2.p)

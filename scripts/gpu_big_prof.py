@@ -7,18 +7,21 @@ from omc_b200.synthetic import generate_matrix_completion_data
 omc.init(0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 60
-k, n, m = 3, 100, 100
-A, mask = generate_matrix_completion_data(k, n, m, 3000, 0)
-p = omc.Problem(k, A, mask, 80.0, "linear3")
+import os
+if os.environ.get("CFG", "C4") == "C5":
+    k, n, m, nidx, ct, labs = 5, 1000, 1000, 200000, "linear", ["left", "right"]
+else:
+    k, n, m, nidx, ct, labs = 3, 100, 100, 3000, "linear3", ["left", "inner_left", "inner_right", "right"]
+A, mask = generate_matrix_completion_data(k, n, m, nidx, 0)
+p = omc.Problem(k, A, mask, 80.0, ct)
 rng = np.random.default_rng(0)
-labs = ["left", "inner_left", "inner_right", "right"]
 node_cuts = []
 for b in range(B):
     cuts = []
     for l in range(1 + b % 3):
         x = rng.standard_normal(n); x /= np.linalg.norm(x)
         Uh = 0.3 * rng.standard_normal((n, k))
-        cuts.append(omc.Cut(p.add_cut(x, Uh), x, Uh, [labs[rng.integers(3)] for _ in range(k)]))
+        cuts.append(omc.Cut(p.add_cut(x, Uh), x, Uh, [labs[rng.integers(max(1, len(labs) - 1))] for _ in range(k)]))
     node_cuts.append(cuts)
 f = p.frontier(node_cuts, engine="batched")
 ms = f.relax(omc.default_opts(eps_abs=1e-12, eps_rel=1e-12, max_iter=iters))
