@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- nodes relaxed / second of the B200 bounding engine.
 
-Workload ("config.workload", default BASELINE.json config 4 = the largest configuration whose 1184-node frontier fits one
-GPU; OMC_BENCH_CFG=C5 runs config 5's shape with a smaller per-GPU batch, OMC_BENCH_CFG=C2 the round-1 line):
-k = 3, 100 x 100 noisy Gaussian low-rank data, 3000 observed entries, gamma = 80, linear3 cuts, smallest_2_eigvec
-breakpoints.  A *step* is one pass of the hot path -- the relaxation of every node of one frontier batch of open
-branch-and-bound nodes (replaces matrix_completion_SDP_relaxation, OMC.jl:1431-1943), each from a cold start to
-eps = 1e-8 -- through the batched large-block engine (csrc/omc_big.cuh): the frontier advances in lockstep, one short
-kernel sequence per ADMM iteration.  The frontier is built once, untimed, by best-first disjunctive expansion from the
-root with the incumbent withheld.
+Workload ("config.workload"): BASELINE.json config 5, the configuration the metric is quoted on -- k = 5, 1000 x 1000 noisy
+Gaussian low-rank data, 200 000 observed entries (20 %), gamma = 80, linear cuts, smallest_1_eigvec breakpoints; PSD blocks
+2000 / 1005 / 1000, 85.5 MB of ADMM state per node.  The 4096-node frontier batch of the north star is 350 GB of state, so
+one GPU relaxes a 128-node shard of it per step (8 GPUs: 1024 nodes); OMC_BENCH_CFG=C4 / C2 run config 4 (k = 3, 100 x 100,
+linear3, smallest_2_eigvec; 1184 nodes per GPU) and config 2 the same way.  A *step* is one pass of the hot path -- the
+relaxation of every node of one frontier batch of open branch-and-bound nodes (replaces matrix_completion_SDP_relaxation,
+OMC.jl:1431-1943), each from a cold start to eps = 1e-8 with the root heuristic's incumbent as cut-off -- through the batched
+large-block engine (csrc/omc_big.cuh): the frontier advances in lockstep, one short kernel sequence per ADMM iteration.  The
+frontier is a committed fixture (tests/golden/<cfg>_frontier_pool.json, built once by best-first disjunctive expansion on
+the GPU, scripts/dump_frontier_pool.py); at N GPUs it is sharded, not rebuilt.
 
   value     nodes/s with the batch descriptors resident in HBM (CUDA events on the library's launch stream around the
             whole lockstep run); only nodes that END the pass with a terminal status count (OPTIMAL / INFEASIBLE /
@@ -39,13 +41,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = os.environ.get("OMC_BENCH_CFG", "C4")
+CFG = os.environ.get("OMC_BENCH_CFG", "C5")
 CONFIGS = {   # (k, n, m, n_indices, cut type, nev, default nodes per GPU, max_iter)
     "C2": dict(k=1, n=50, m=50, nidx=1250, ct="linear", nev=1, nodes=1184, max_iter=5000,
                name="C2: k=1, 50x50 noisy, 1250 observed, gamma=80, linear cuts, smallest_1_eigvec"),
     "C4": dict(k=3, n=100, m=100, nidx=3000, ct="linear3", nev=2, nodes=1184, max_iter=4000,
                name="C4: k=3, 100x100 noisy, 3000 observed, gamma=80, linear3 cuts, smallest_2_eigvec"),
-    "C5": dict(k=5, n=1000, m=1000, nidx=200000, ct="linear", nev=1, nodes=32, max_iter=3000,
+    "C5": dict(k=5, n=1000, m=1000, nidx=200000, ct="linear", nev=1, nodes=128, max_iter=3000,
                name="C5: k=5, 1000x1000, 20% observed, gamma=80, linear cuts, smallest_1_eigvec"),
 }
 W = CONFIGS[CFG]
@@ -251,12 +253,52 @@ def run_b200(args):
         all_cuts = all_cuts[: B]                                   # ONE fixed frontier of B nodes shared by all ranks
     else:
         all_cuts = all_cuts[: B * world]
-    mine = all_cuts[rank::world]                                   # block-cyclic shard of the one frontier
-    node_cuts = [[omc.Cut(problem.add_cut(x, vh), x, vh, d) for x, vh, d in cs] for cs in mine]
+    my_ids = list(range(len(all_cuts)))[rank::world]               # block-cyclic shard of the one frontier
+    comm = None
+    if world > 1:                                                  # the engine's own exchange (libomc_b200.so: NCCL via dlopen)
+        from omc_b200.parallel import LibraryComm
+
+        def bootstrap(raw):
+            box = [raw]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = LibraryComm(rank, world, bootstrap)
+    pool_ids = {}
+
+    def make_frontier(ids):
+        cuts = []
+        for i in ids:
+            node = []
+            for x, vh, d in all_cuts[i]:
+                key = (x.tobytes(), vh.tobytes())
+                if key not in pool_ids:
+                    pool_ids[key] = problem.add_cut(x, vh)
+                node.append(omc.Cut(pool_ids[key], x, vh, d))
+            cuts.append(node)
+        return cuts, omc.Frontier(problem, cuts)
+
+    opts = omc.default_opts(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER, cutoff=incumbent)   # the incumbent prunes, as in the B&B loop
+    node_cuts, fr = make_frontier(my_ids)
+    rebalanced = False
+    if world > 1 and not args.no_rebalance:
+        # frontier re-balancing: one untimed pass gives every node's ADMM iteration count; the counts are all-gathered and
+        # every rank takes its part of the same longest-first greedy partition (node descriptors are replicated: nothing moves)
+        from omc_b200.parallel import balanced_partition
+        fr.relax(opts)
+        its = np.array([o["iters"] for o in fr.fetch(matrices=False)], dtype=np.float64)
+        per = (len(all_cuts) + world - 1) // world
+        send = np.full(per, -1.0); send[: len(its)] = its
+        got = comm.allgather(send)
+        cost = np.zeros(len(all_cuts))
+        for r in range(world):
+            ids_r = list(range(len(all_cuts)))[r::world]
+            cost[ids_r] = got[r, : len(ids_r)]
+        my_ids = balanced_partition(cost, world)[rank]
+        fr.close()
+        node_cuts, fr = make_frontier(my_ids)
+        rebalanced = True
     setup_s = time.time() - t0
     Bl = len(node_cuts)
-    opts = omc.default_opts(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER, cutoff=incumbent)   # the incumbent prunes, as in the B&B loop
-    fr = omc.Frontier(problem, node_cuts)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
     red = torch.zeros(2, dtype=torch.float64, device="cuda")
 
@@ -270,9 +312,8 @@ def run_b200(args):
         flush.fill_(1.0)                       # L2 flush between steps (the frontier state, 1.1 MB per node, also exceeds L2)
         torch.cuda.synchronize()
         ms = fr.relax(opts)                    # CUDA events on the library stream bracket the whole lockstep run
-        if world > 1:                          # the path's only exchange: all-reduce-min of [incumbent, min LB]
-            red[0] = 1e300; red[1] = 1e300
-            dist.all_reduce(red, op=dist.ReduceOp.MIN)
+        if world > 1:                          # the path's only exchange: all-reduce-min of [incumbent, min LB] (omc_allreduce_min)
+            comm.allreduce_min(np.array([incumbent, 1e300]))
         return ms
 
     for _ in range(max(args.warmup, 0)):
@@ -340,6 +381,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             from oracle import bigblock as Bg
             t0 = time.perf_counter(); done = 0; cit = 0; term = 0
+            mine = [all_cuts[i] for i in my_ids]
             stride = max(1, len(mine) // 6)
             for cs in mine[::stride]:
                 r = Bg.solve_relaxation_big(A, mask, GAMMA, k, W["ct"], cs, opts=Bg.BigOptions(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER,
@@ -375,7 +417,9 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "engine": stats["engine"], "nodes_per_gpu": Bl, "nodes_total": int(total_nodes),
                        "nodes_terminal": int(total_terminal), "eps": EPS, "max_iter": MAX_ITER, "cutoff": incumbent,
                        "start": "cold", "l2": "flushed between steps (256 MiB fill); frontier state exceeds L2", "frontier": src,
-                       "parallelism": f"one frontier of {int(total_nodes)} nodes sharded block-cyclically over {world} GPU(s)",
+                       "parallelism": f"one frontier of {int(total_nodes)} nodes sharded over {world} GPU(s), "
+                                      + ("re-balanced by measured iterations (longest-first greedy), " if rebalanced else "block-cyclic, ")
+                                      + "no data-path collective; all-reduce-min of 2 doubles per step inside libomc_b200.so",
                        "iters_per_node_mean": total_iters / total_nodes, "cuts_per_node_mean": total_cuts / total_nodes,
                        "status_counts[opt,iterlim,infeas,time,cutoff,numerical]": status_all,
                        "frontier_setup_s": setup_s, "wall_ms_per_step": wall_ms_max, "lockstep_iterations": stats["iterations"],
@@ -434,6 +478,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nodes", type=int, default=0, help="frontier nodes per GPU (default: 1184 = 8 x 148 SMs at config 4)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: one fixed frontier of --nodes nodes shared by all GPUs")
+    ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep the block-cyclic shards")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()

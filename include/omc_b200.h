@@ -188,6 +188,20 @@ int32_t omc_shor_indexes(omc_problem* p, const int32_t* present_list, int32_t nl
  * (OMC.jl:2373-2409).  X column-major n*m.  out[0] objective, out[1] MSE in, out[2] MSE out, out[3] MSE all */
 int32_t omc_objective_mse(omc_problem* p, const double* X, double* out4);
 
+/* ---- multi-GPU exchange: one process per GPU, the frontier sharded over the processes.  No
+ * reference counterpart (OMC.jl:700-1073 is a single sequential loop).  NCCL is bound at run time (dlopen libnccl.so.2).
+ * Bootstrap: rank 0 calls omc_comm_unique_id, ships the 128 bytes to the other ranks by any host channel, every rank calls
+ * omc_comm_init after omc_init(device).  world = 1 makes every call a no-op, so single-GPU hosts need no NCCL.           */
+int32_t omc_comm_unique_id(uint8_t* id128);
+int32_t omc_comm_init(int32_t rank, int32_t world, const uint8_t* id128);
+int32_t omc_comm_info(int32_t* rank, int32_t* world);
+/* values[i] <- min over ranks (n host doubles): [incumbent upper bound, smallest open lower bound, ...] after a batch */
+int32_t omc_allreduce_min(double* values, int32_t n);
+/* recv[r * n + i] <- send[i] of rank r: per-rank load figures for the deterministic re-balancing of the open list */
+int32_t omc_allgather(const double* send, int32_t n, double* recv);
+int32_t omc_comm_destroy(void);
+const char* omc_comm_last_error(void);
+
 /* ---- diagnostics used by tests / bench ------------------------------------------------------- */
 /* batched symmetric eigendecomposition + PSD projection of B dense N x N matrices (row-major, symmetric):
  * P[B*N*N] = projection onto the PSD cone, lam[B*N] = eigenvalues (unordered), sweeps[B] */

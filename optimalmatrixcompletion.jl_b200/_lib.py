@@ -61,6 +61,13 @@ SIGNATURES = {
     "omc_altmin_batch": (_i32, [_vp, _i32, _pf64, _pi32, _pi32, _pu8, _f64, _i32, _f64, _pf64, _pf64, _pi32, _pi32, _pf64, _pf64]),
     "omc_objective_mse": (_i32, [_vp, _pf64, _pf64]),
     "omc_shor_indexes": (_i32, [_vp, _pi32, _i32, _p(C.c_int64), _pi32, _i64, _pi32, _p(C.c_int64)]),
+    "omc_comm_unique_id": (_i32, [_pu8]),
+    "omc_comm_init": (_i32, [_i32, _i32, _pu8]),
+    "omc_comm_info": (_i32, [_pi32, _pi32]),
+    "omc_allreduce_min": (_i32, [_pf64, _i32]),
+    "omc_allgather": (_i32, [_pf64, _i32, _pf64]),
+    "omc_comm_destroy": (_i32, []),
+    "omc_comm_last_error": (C.c_char_p, []),
     "omc_debug_psd_project_batch": (_i32, [_i32, _i32, _pf64, _pf64, _pf64, _pi32, _pf32]),
     "omc_measure_fp64_peak": (_i32, [_pf64]),
 }

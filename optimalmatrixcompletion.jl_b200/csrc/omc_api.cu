@@ -431,7 +431,7 @@ int32_t omc_problem_create(int32_t n, int32_t m, int32_t k, const double* A, con
   PC(p->rowptr.alloc(n + 1));
   PC(p->colptr.alloc(m + 1));
   {
-    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    const int blocks = (int)((total + 255) / 256 < g_sm_count * 8 ? (total + 255) / 256 : g_sm_count * 8);
     omc::mask_expand_kernel<<<blocks, 256, 0, g_stream>>>(p->chunks.p, p->Mk.p, total);
     omc::mask_count_kernel<<<(m * 32 + 255) / 256, 256, 0, g_stream>>>(p->chunks.p, n, m, 0, p->colptr.p);
     omc::mask_count_kernel<<<(n * 32 + 255) / 256, 256, 0, g_stream>>>(p->chunks.p, n, m, 1, p->rowptr.p);
@@ -447,13 +447,13 @@ int32_t omc_problem_create(int32_t n, int32_t m, int32_t k, const double* A, con
   omc::mask_fill_kernel<<<(m * 32 + 255) / 256, 256, 0, g_stream>>>(p->chunks.p, n, m, 0, p->colptr.p, p->rowidx.p);
   omc::mask_fill_kernel<<<(n * 32 + 255) / 256, 256, 0, g_stream>>>(p->chunks.p, n, m, 1, p->rowptr.p, p->colidx.p);
   // c0 = 1/2 sum_I A^2 (constant of the relaxation's dual objective), computed by the objective kernel with X = 0
-  PC(p->red.alloc(4 * 148 * 4 + 8));
+  PC(p->red.alloc(4 * g_sm_count * 4 + 8));
   PC(p->Xdev.alloc(total));
   PC(cudaMemsetAsync(p->Xdev.p, 0, total * sizeof(double), g_stream));
-  omc::objective_partial_kernel<<<148 * 4, 256, 0, g_stream>>>(p->Xdev.p, p->A.p, p->chunks.p, total, p->red.p);
-  omc::objective_final_kernel<<<1, 256, 0, g_stream>>>(p->red.p, 148 * 4, gamma, total, p->red.p + 4 * 148 * 4);
+  omc::objective_partial_kernel<<<g_sm_count * 4, 256, 0, g_stream>>>(p->Xdev.p, p->A.p, p->chunks.p, total, p->red.p);
+  omc::objective_final_kernel<<<1, 256, 0, g_stream>>>(p->red.p, g_sm_count * 4, gamma, total, p->red.p + 4 * g_sm_count * 4);
   double o4[4];
-  PC(cudaMemcpyAsync(o4, p->red.p + 4 * 148 * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  PC(cudaMemcpyAsync(o4, p->red.p + 4 * g_sm_count * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   PC(cudaStreamSynchronize(g_stream));
   PC(cudaGetLastError());
   p->c0 = o4[0];  // X = 0: objective = 1/2 sum_I A^2
@@ -805,10 +805,10 @@ int32_t omc_objective_mse(omc_problem* p, const double* X, double* out4) {
   if (!p || !X || !out4) return fail(OMC_ERR_ARG, "null argument");
   const long long total = (long long)p->n * p->m;
   CU(cudaMemcpyAsync(p->Xdev.p, X, total * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-  omc::objective_partial_kernel<<<148 * 4, 256, 0, g_stream>>>(p->Xdev.p, p->A.p, p->chunks.p, total, p->red.p);
-  omc::objective_final_kernel<<<1, 256, 0, g_stream>>>(p->red.p, 148 * 4, p->gamma, total, p->red.p + 4 * 148 * 4);
+  omc::objective_partial_kernel<<<g_sm_count * 4, 256, 0, g_stream>>>(p->Xdev.p, p->A.p, p->chunks.p, total, p->red.p);
+  omc::objective_final_kernel<<<1, 256, 0, g_stream>>>(p->red.p, g_sm_count * 4, p->gamma, total, p->red.p + 4 * g_sm_count * 4);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out4, p->red.p + 4 * 148 * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CU(cudaMemcpyAsync(out4, p->red.p + 4 * g_sm_count * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CU(cudaStreamSynchronize(g_stream));
   return OMC_OK;
 }

@@ -223,7 +223,7 @@ __device__ __forceinline__ void lower_tile(int t, int& I, int& J) {
 // ------------------------------------------------------------------------------------------------------------------
 // k_xt: X region (tiles 0 .. tn*tm-1) and Theta region (lower tiles), one fused pass.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_xt(BigArgs a) {
+__global__ void __launch_bounds__(256, 2) k_xt(BigArgs a) {
   extern __shared__ __align__(16) double sm[];
   const Layout& L = a.L;
   const int slot = a.active[blockIdx.y];
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) k_xt(BigArgs a) {
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
-__global__ void __launch_bounds__(256) k_y1(BigArgs a) {
+__global__ void __launch_bounds__(256, 2) k_y1(BigArgs a) {
   extern __shared__ __align__(16) double sm[];
   const Layout& L = a.L;
   const int slot = a.active[blockIdx.y];
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(128) k_small(BigArgs a) {
 // ------------------------------------------------------------------------------------------------------------------
 // k_y2: Y and U regions, pass B.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_y2(BigArgs a) {
+__global__ void __launch_bounds__(256, 2) k_y2(BigArgs a) {
   extern __shared__ __align__(16) double sm[];
   const Layout& L = a.L;
   const int slot = a.active[blockIdx.y];
@@ -1464,7 +1464,7 @@ __global__ void __launch_bounds__(256) k_minv(BigArgs a, int only_adapted) {
 //   0 rp (max), 1 rd (max), 2 n_p (max), 3 n_d (max), 4 sum Mk X^2, 5 sum Mk (X - A)^2, 6 tr T, 7 tr mu2 corner / rho,
 //   8 tr(F3) (-> a tr mu3 = -rho a tr F3), 9 box dual sum / rho.   rows_part gets the dense rows of the CURRENT (Y, U).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_check(BigArgs a) {
+__global__ void __launch_bounds__(256, 2) k_check(BigArgs a) {
   extern __shared__ __align__(16) double sm[];
   const Layout& L = a.L;
   const int slot = a.active[blockIdx.y];

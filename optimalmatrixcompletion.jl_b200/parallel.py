@@ -35,6 +35,59 @@ def allreduce_bounds(upper: float, lower: float, device=None) -> Tuple[float, fl
     return float(t[0]), float(t[1])
 
 
+class LibraryComm:
+    """The engine's own exchange (csrc/omc_comm.cu: NCCL bound at run time inside libomc_b200.so), the calls a Julia host
+    makes through the C ABI: omc_comm_unique_id / omc_comm_init / omc_allreduce_min / omc_allgather.  `bootstrap` ships the
+    128-byte NCCL id from rank 0 to the other ranks by any host channel (here: a callable, e.g. a torch.distributed
+    broadcast or a file); world = 1 needs nothing."""
+
+    def __init__(self, rank: int, world: int, bootstrap=None):
+        import ctypes as C
+        from . import _lib
+        self._C, self.lib, self.rank, self.world = C, _lib.load(), int(rank), int(world)
+        idbuf = (C.c_uint8 * 128)()
+        if world > 1:
+            if rank == 0:
+                self._check(self.lib.omc_comm_unique_id(idbuf))
+            raw = bootstrap(bytes(idbuf) if rank == 0 else None)
+            idbuf = (C.c_uint8 * 128).from_buffer_copy(raw)
+        self._check(self.lib.omc_comm_init(self.rank, self.world, idbuf))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"libomc_b200 comm error {rc}: {self.lib.omc_comm_last_error().decode()}")
+
+    def allreduce_min(self, values) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        self._check(self.lib.omc_allreduce_min(v.ctypes.data_as(self._C.POINTER(self._C.c_double)), v.size))
+        return v
+
+    def allgather(self, values) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        out = np.zeros((self.world, v.size))
+        self._check(self.lib.omc_allgather(v.ctypes.data_as(self._C.POINTER(self._C.c_double)), v.size,
+                                           out.ctypes.data_as(self._C.POINTER(self._C.c_double))))
+        return out
+
+    def close(self):
+        self.lib.omc_comm_destroy()
+
+
+def balanced_partition(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Frontier re-balancing plan: longest-predicted-first greedy (LPT) partition of node indices over `world` ranks by their
+    predicted cost (ADMM iterations of the node's last relaxation, or of its parent).  Deterministic: every rank computes the
+    same plan from the all-gathered costs, and takes its own part -- node descriptors (pool ids + direction codes) are
+    replicated, so no node data moves.  Each part is ordered longest first."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    loads = [0.0] * world
+    parts: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda q: (loads[q], len(parts[q]), q))
+        parts[r].append(i)
+        loads[r] += float(costs[i])
+    return parts
+
+
 def rebalance_counts(iters_per_rank: Sequence[int], nodes_per_rank: Sequence[int]) -> np.ndarray:
     """Frontier rebalancing plan: given each rank's measured ADMM iterations for its last shard, returns how many
     nodes of the next batch each rank should take so that predicted work (iterations per node x nodes) evens out."""

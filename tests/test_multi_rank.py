@@ -49,3 +49,28 @@ def test_frontier_sharding_and_bound_allreduce_world2():
     assert unshard_block_cyclic(shards) == list(range(101, 138))
     c = rebalance_counts([1000, 3000], [10, 10])
     assert c.sum() == 20 and c[0] > c[1]
+
+
+def test_balanced_partition_is_deterministic_and_even():
+    sys.path.insert(0, ROOT)
+    import omc_b200  # noqa: F401
+    from omc_b200.parallel import balanced_partition
+    rng = np.random.default_rng(0)
+    cost = rng.integers(200, 4000, size=1024).astype(float)
+    parts = balanced_partition(cost, 8)
+    assert sorted(i for p in parts for i in p) == list(range(1024))
+    loads = np.array([cost[p].sum() for p in parts])
+    assert loads.max() / loads.min() < 1.02                       # per-rank iteration totals within 2 %
+    assert all(cost[p[0]] >= cost[p[-1]] for p in parts)          # each rank's queue is ordered longest first
+    assert parts == balanced_partition(cost, 8)
+
+
+def test_library_comm_single_rank_is_a_noop():
+    """world = 1: the in-library exchange (omc_comm_* / omc_allreduce_min / omc_allgather) needs neither NCCL nor a GPU."""
+    sys.path.insert(0, ROOT)
+    import omc_b200  # noqa: F401
+    from omc_b200.parallel import LibraryComm
+    c = LibraryComm(0, 1)
+    assert np.array_equal(c.allreduce_min([3.0, -1.0]), [3.0, -1.0])
+    assert np.array_equal(c.allgather([1.0, 2.0, 3.0]), [[1.0, 2.0, 3.0]])
+    c.close()
