@@ -279,6 +279,8 @@ def run_b200(args):
 
     opts = omc.default_opts(eps_abs=EPS, eps_rel=EPS, max_iter=MAX_ITER, cutoff=incumbent)   # the incumbent prunes, as in the B&B loop
     node_cuts, fr = make_frontier(my_ids)
+    if os.environ.get("OMC_STEPS_MAX"):
+        fr.set_tuning(steps_max=int(os.environ["OMC_STEPS_MAX"]))
     rebalanced = False
     if world > 1 and not args.no_rebalance:
         # frontier re-balancing: one untimed pass gives every node's ADMM iteration count; the counts are all-gathered and

@@ -547,7 +547,7 @@ int32_t omc_frontier_create_ex(omc_problem* p, int32_t B, const int32_t* node_cu
   NEED_INIT();
   if (!p || !out || B <= 0 || !node_cut_ptr) return fail(OMC_ERR_ARG, "bad argument");
   if (engine < OMC_ENGINE_AUTO || engine > OMC_ENGINE_BATCHED) return fail(OMC_ERR_ARG, "engine must be 0 (auto), 1 (persistent) or 2 (batched)");
-  if (engine == OMC_ENGINE_AUTO) engine = (p->n + p->m > 104) ? OMC_ENGINE_BATCHED : OMC_ENGINE_PERSISTENT;
+  const int engine_asked = engine;
   const int E = node_cut_ptr[B];
   if (E < 0 || node_cut_ptr[0] != 0) return fail(OMC_ERR_ARG, "node_cut_ptr must start at 0 and be non-decreasing");
   if (E > 0 && (!node_cut_ids || !node_cut_dirs)) return fail(OMC_ERR_ARG, "cut ids/dirs missing");
@@ -558,6 +558,9 @@ int32_t omc_frontier_create_ex(omc_problem* p, int32_t B, const int32_t* node_cu
     if (L < 0) return fail(OMC_ERR_ARG, "node_cut_ptr not monotone at node %d", b);
     if (L > Lmax) Lmax = L;
   }
+  // auto: PSD blocks beyond one SM's shared memory, or a node deeper than the persistent engine's cut capacity -> batched engine
+  if (engine == OMC_ENGINE_AUTO) engine = (p->n + p->m > 104 || Lmax > p->Lcap) ? OMC_ENGINE_BATCHED : OMC_ENGINE_PERSISTENT;
+  (void)engine_asked;
   if (engine == OMC_ENGINE_PERSISTENT && Lmax > p->Lcap)
     return fail(OMC_ERR_UNSUPPORTED, "node with %d cuts exceeds the %d the persistent engine supports (the batched engine, engine = 2, has no such cap)", Lmax, p->Lcap);
   for (int e = 0; e < E; ++e) {

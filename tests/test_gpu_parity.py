@@ -204,11 +204,14 @@ def test_config4_shape_runs_through_the_l2_resident_block_path(omc):
     cid = p.add_cut(x, Uh)
     dirs = ["inner_left", "right", "left"]
     for cuts_g, cuts_o in (([], []), ([omc.Cut(cid, x, Uh, dirs)], [(x, Uh, dirs)])):
-        r = p.relax_batch([cuts_g], omc.default_opts(eps_abs=1e-30, eps_rel=1e-30, max_iter=20, adapt_every=0, jacobi_tol=1e-13, exact_projection=1))[0]
+        r = p.relax_batch([cuts_g], omc.default_opts(eps_abs=1e-30, eps_rel=1e-30, max_iter=20, adapt_every=0, jacobi_tol=1e-13, exact_projection=1),
+                          engine="persistent")[0]          # (engine "auto" sends n + m > 104 to the batched engine, tests/test_gpu_big.py)
         ro = R.solve_relaxation(A, mask, g, k, "linear3", cuts_o, opts=R.Options(eps_abs=1e-30, eps_rel=1e-30, max_iter=20, adaptive_rho=False))
         assert np.abs(r["X"] - ro["X"]).max() < 1e-8 and np.abs(r["Y"] - ro["Y"]).max() < 1e-8 and np.abs(r["U"] - ro["U"]).max() < 1e-8
-    full = p.relax_batch([[]], omc.default_opts(max_iter=4000))[0]
+    full = p.relax_batch([[]], omc.default_opts(max_iter=4000), engine="persistent")[0]
     assert full["termination_status"] == "OPTIMAL"
+    auto = p.relax_batch([[]], omc.default_opts(max_iter=4000))[0]            # the batched engine agrees with the persistent one
+    assert auto["termination_status"] == "OPTIMAL" and abs(auto["objective"] - full["objective"]) <= REL_BOUND * abs(full["objective"])
     X, Y, U = full["X"], full["Y"], full["U"]
     assert np.linalg.eigvalsh(np.eye(100) - Y).min() >= -1e-6 and np.trace(Y) <= k + 1e-6 and np.linalg.eigvalsh(Y).min() >= -1e-6
     assert full["lower_bound"] <= full["objective"] * (1 + 1e-6)
@@ -479,8 +482,14 @@ def test_ragged_frontier_zero_to_capacity_cuts(omc):
     uu = ustar[:, None]
     Xs = uu @ (uu.T @ np.where(mask, A, 0.0))
     assert batch[3]["objective"] <= p.objective_mse(Xs)[0] * (1 + 1e-9)
-    with pytest.raises(Exception, match="exceeds the supported"):
-        p.relax_batch([chain[:65]], opts)
+    # capacity + 1 cuts: the persistent engine refuses, engine "auto" hands the node to the batched engine (no cut cap)
+    with pytest.raises(Exception, match="exceeds the 64 the persistent engine supports"):
+        p.relax_batch([chain[:65]], opts, engine="persistent")
+    deep = p.relax_batch([chain[:65]], opts)[0]
+    assert deep["termination_status"] == "OPTIMAL" and deep["objective"] >= batch[3]["objective"] * (1 - 1e-6)
+    assert deep["objective"] <= p.objective_mse(Xs)[0] * (1 + 1e-9)
+    ro65 = R.solve_relaxation(A, mask, g, k, "linear", ocuts[:65], opts=R.Options(eps_abs=1e-8, eps_rel=1e-8, max_iter=200000))
+    assert abs(deep["objective"] - ro65["objective"]) <= REL_BOUND * ro65["objective"]
     p.close()
 
 
