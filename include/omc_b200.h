@@ -138,6 +138,16 @@ int32_t omc_frontier_fetch(omc_frontier* f, int32_t* status, double* objective, 
  * 14 / 15 = projections done by the low-rank tracker / by the full solver,
  * 16..23 = cycles in the sub-phases of the tracking step (V Z, residual, CholQR2, V R~, Gram, Jacobi, select + combine) */
 int32_t omc_frontier_fetch_profile(omc_frontier* f, double* prof);
+/* Shor valid inequalities (OMC.jl:1503-1552 variables, 1755-1828 rows, 1838-1846 objective; chosen by
+ * generate_rank1_basis_pursuit_Shor_constraints_indexes, OMC.jl:568-668): attaches the rows to every node relaxation of the
+ * problem.  minors[4*q..] = (i1, i2, j1, j2), 0-based, i1 < i2, j1 < j2 (the reference's 4-tuples minus one);
+ * soc[2*q..] = (i, j) coordinates on a rotated second-order cone row, none of them covered by a minor (OMC.jl:656-665).
+ * Frontiers of such a problem run on the batched engine; their status is OPTIMAL or ITERATION_LIMIT (no certified bound is
+ * derived with these rows: lower_bound = -1e300, no cut-off).  k <= 4.  n_minors = n_soc = 0 removes the rows.            */
+int32_t omc_problem_set_shor(omc_problem* p, int64_t n_minors, const int32_t* minors, int64_t n_soc, const int32_t* soc);
+/* Shor results of a relaxed frontier: W[B*n*m] column-major per node (result key "W", OMC.jl:1902), Xt[B*k*n*m] (k slices
+ * per node, result key "Xt", OMC.jl:1913; consumed by generate_violated_Shor_minors, OMC.jl:1099).  Either may be NULL.  */
+int32_t omc_frontier_fetch_shor(omc_frontier* f, double* W, double* Xt);
 /* out8: [0] engine, [1] kernel launches of the last relax, [2] lockstep iterations, [3] node-iterations, [4] residual checks,
  * [5] rho changes, [6] bytes of device state per node (batched engine) */
 int32_t omc_frontier_stats(omc_frontier* f, int64_t* out8);

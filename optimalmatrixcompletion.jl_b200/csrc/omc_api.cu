@@ -88,9 +88,11 @@ struct omc_problem {
   // row-major copies for the batched large-block engine (omc_big.cu), built on first use
   double* AMrm = nullptr;
   unsigned char* Mkrm = nullptr;
+  omcbig::ShorHost* shor = nullptr;   // Shor valid-inequality structure (omc_problem_set_shor)
   ~omc_problem() {
     if (AMrm) cudaFree(AMrm);
     if (Mkrm) cudaFree(Mkrm);
+    if (shor) omcbig::big_shor_destroy(shor);
   }
 };
 
@@ -559,7 +561,9 @@ int32_t omc_frontier_create_ex(omc_problem* p, int32_t B, const int32_t* node_cu
     if (L > Lmax) Lmax = L;
   }
   // auto: PSD blocks beyond one SM's shared memory, or a node deeper than the persistent engine's cut capacity -> batched engine
-  if (engine == OMC_ENGINE_AUTO) engine = (p->n + p->m > 104 || Lmax > p->Lcap) ? OMC_ENGINE_BATCHED : OMC_ENGINE_PERSISTENT;
+  if (engine == OMC_ENGINE_AUTO) engine = (p->n + p->m > 104 || Lmax > p->Lcap || p->shor) ? OMC_ENGINE_BATCHED : OMC_ENGINE_PERSISTENT;
+  if (engine == OMC_ENGINE_PERSISTENT && p->shor)
+    return fail(OMC_ERR_UNSUPPORTED, "Shor valid inequalities are rows of the batched engine only (engine = 0 or 2)");
   (void)engine_asked;
   if (engine == OMC_ENGINE_PERSISTENT && Lmax > p->Lcap)
     return fail(OMC_ERR_UNSUPPORTED, "node with %d cuts exceeds the %d the persistent engine supports (the batched engine, engine = 2, has no such cap)", Lmax, p->Lcap);
@@ -589,6 +593,7 @@ int32_t omc_frontier_create_ex(omc_problem* p, int32_t B, const int32_t* node_cu
     pv.n = p->n; pv.m = p->m; pv.k = p->k; pv.cut_type = p->cut_type; pv.gamma = p->gamma; pv.c0 = p->c0;
     pv.AMrm = p->AMrm; pv.Mkrm = p->Mkrm; pv.pool_x = p->pool_x.p; pv.pool_vhat = p->pool_vhat.p; pv.stream = g_stream;
     pv.sm_count = g_sm_count;
+    pv.shor = p->shor;
     const int rc = omcbig::big_create(pv, B, node_cut_ptr, node_cut_ids, node_cut_dirs, &f->big);
     if (rc != 0) {
       delete f;
@@ -758,6 +763,24 @@ int32_t omc_frontier_destroy(omc_frontier* f) {
   if (f->ev1) cudaEventDestroy(f->ev1);
   if (f->big) omcbig::big_destroy(f->big);
   delete f;
+  return OMC_OK;
+}
+
+int32_t omc_problem_set_shor(omc_problem* p, int64_t n_minors, const int32_t* minors, int64_t n_soc, const int32_t* soc) {
+  NEED_INIT();
+  if (!p || n_minors < 0 || n_soc < 0 || (n_minors > 0 && !minors) || (n_soc > 0 && !soc)) return fail(OMC_ERR_ARG, "bad argument");
+  if (p->shor) { omcbig::big_shor_destroy(p->shor); p->shor = nullptr; }
+  if (n_minors == 0 && n_soc == 0) return OMC_OK;
+  if (n_minors > ((int64_t)1 << 29)) return fail(OMC_ERR_UNSUPPORTED, "more than 2^29 Shor minors");
+  const int rc = omcbig::big_shor_create(p->n, p->m, p->k, n_minors, minors, n_soc, soc, &p->shor);
+  if (rc != 0) return fail(rc == -1 ? OMC_ERR_ARG : rc == -4 ? OMC_ERR_UNSUPPORTED : OMC_ERR_CUDA, "%s", omcbig::big_last_error());
+  return OMC_OK;
+}
+
+int32_t omc_frontier_fetch_shor(omc_frontier* f, double* W, double* Xt) {
+  NEED_INIT();
+  if (!f || !f->big) return fail(OMC_ERR_ARG, "the frontier has no Shor rows");
+  if (omcbig::big_fetch_shor(f->big, W, Xt) != 0) return fail(OMC_ERR_ARG, "%s", omcbig::big_last_error());
   return OMC_OK;
 }
 

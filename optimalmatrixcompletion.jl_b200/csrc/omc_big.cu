@@ -10,12 +10,27 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+#include <unordered_map>
+
 #include "omc_big.cuh"
+#include "omc_big_shor.cuh"
 #include "omc_big_host.h"
 
 namespace omcbig {
 
+struct ShorHost {   // problem-level Shor structure on the device (shared by all nodes)
+  long long nm = 0, nv1 = 0, nv2 = 0;
+  int n = 0, m = 0, k = 0;
+  int *minors = nullptr, *mv = nullptr, *cptr = nullptr, *cinc = nullptr, *v1ptr = nullptr, *v1inc = nullptr, *v2ptr = nullptr,
+      *v2inc = nullptr, *cnt = nullptr;
+  unsigned char* flags = nullptr;
+};
+
 struct BigFrontier {
+  double* SS = nullptr;        // Shor node records
+  ShorLayout SL;
+  double *outW = nullptr, *outXt = nullptr;
   BigProblemView pv;
   Layout L;
   int B = 0, E = 0, Lmax = 0;
@@ -57,6 +72,84 @@ __global__ void k_rowmajor(const double* __restrict__ A, const double* __restric
   }
 }
 
+template <typename T>
+static int upload(T** dst, const std::vector<T>& v) {
+  const size_t cnt = v.empty() ? 1 : v.size();
+  BCU(cudaMalloc(dst, cnt * sizeof(T)));
+  if (!v.empty()) BCU(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int big_shor_create(int n, int m, int k, long long nm, const int* minors, long long nsoc, const int* soc, ShorHost** out) {
+  if (k > 4) { g_berr = "Shor rows: k > 4 unsupported ((k+1) x (k+1) blocks are projected in registers up to order 5)"; return -4; }
+  ShorHost* h = new ShorHost();
+  h->n = n; h->m = m; h->k = k; h->nm = nm;
+  const size_t C = (size_t)n * m;
+  std::vector<unsigned char> flags(C, 0);
+  std::vector<int> cnt(C, 0), mvec((size_t)4 * nm), mv((size_t)4 * nm);
+  std::unordered_map<unsigned long long, int> id1, id2;
+  id1.reserve((size_t)nm); id2.reserve((size_t)nm);
+  auto key3 = [](int a_, int b_, int c_) { return ((unsigned long long)a_ << 42) | ((unsigned long long)b_ << 21) | (unsigned long long)c_; };
+  for (long long q = 0; q < nm; ++q) {
+    const int i1 = minors[4 * q], i2 = minors[4 * q + 1], j1 = minors[4 * q + 2], j2 = minors[4 * q + 3];
+    if (i1 < 0 || i1 >= i2 || i2 >= n || j1 < 0 || j1 >= j2 || j2 >= m) { delete h; g_berr = "Shor minor out of range (need 0 <= i1 < i2 < n, 0 <= j1 < j2 < m)"; return -1; }
+    for (int e = 0; e < 4; ++e) mvec[4 * q + e] = minors[4 * q + e];
+    const size_t cc[4] = {(size_t)i1 * m + j1, (size_t)i1 * m + j2, (size_t)i2 * m + j1, (size_t)i2 * m + j2};
+    for (int e = 0; e < 4; ++e) { flags[cc[e]] |= 1; cnt[cc[e]] += 1; }
+    auto get = [](std::unordered_map<unsigned long long, int>& mp, unsigned long long key) {
+      auto it = mp.find(key);
+      if (it != mp.end()) return it->second;
+      const int id = (int)mp.size();
+      mp.emplace(key, id);
+      return id;
+    };
+    mv[4 * q + 0] = get(id1, key3(i1, j1, j2)); mv[4 * q + 1] = get(id1, key3(i2, j1, j2));
+    mv[4 * q + 2] = get(id2, key3(i1, i2, j1)); mv[4 * q + 3] = get(id2, key3(i1, i2, j2));
+  }
+  for (long long q = 0; q < nsoc; ++q) {
+    const int i = soc[2 * q], j = soc[2 * q + 1];
+    if (i < 0 || i >= n || j < 0 || j >= m) { delete h; g_berr = "Shor SOC coordinate out of range"; return -1; }
+    if (flags[(size_t)i * m + j] & 1) { delete h; g_berr = "a SOC coordinate is covered by a minor (OMC.jl:656-665 lists only uncovered ones)"; return -1; }
+    flags[(size_t)i * m + j] |= 2;
+  }
+  h->nv1 = (long long)id1.size(); h->nv2 = (long long)id2.size();
+  // incidence lists (CSR): coordinates <- (minor, slot), V1 ids <- (minor, which), V2 ids <- (minor, which)
+  std::vector<int> cptr(C + 1, 0), cinc((size_t)4 * nm), v1ptr(h->nv1 + 1, 0), v1inc((size_t)2 * nm), v2ptr(h->nv2 + 1, 0), v2inc((size_t)2 * nm);
+  for (size_t c = 0; c < C; ++c) cptr[c + 1] = cptr[c] + cnt[c];
+  {
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (long long q = 0; q < nm; ++q) {
+      const int i1 = mvec[4 * q], i2 = mvec[4 * q + 1], j1 = mvec[4 * q + 2], j2 = mvec[4 * q + 3];
+      const size_t cc[4] = {(size_t)i1 * m + j1, (size_t)i1 * m + j2, (size_t)i2 * m + j1, (size_t)i2 * m + j2};
+      for (int e = 0; e < 4; ++e) cinc[fill[cc[e]]++] = (int)(q * 4 + e);
+    }
+  }
+  for (long long q = 0; q < nm; ++q) { v1ptr[mv[4 * q] + 1]++; v1ptr[mv[4 * q + 1] + 1]++; v2ptr[mv[4 * q + 2] + 1]++; v2ptr[mv[4 * q + 3] + 1]++; }
+  for (long long v = 0; v < h->nv1; ++v) v1ptr[v + 1] += v1ptr[v];
+  for (long long v = 0; v < h->nv2; ++v) v2ptr[v + 1] += v2ptr[v];
+  {
+    std::vector<int> f1(v1ptr.begin(), v1ptr.end() - 1), f2(v2ptr.begin(), v2ptr.end() - 1);
+    for (long long q = 0; q < nm; ++q) {
+      v1inc[f1[mv[4 * q]]++] = (int)(q * 2); v1inc[f1[mv[4 * q + 1]]++] = (int)(q * 2 + 1);
+      v2inc[f2[mv[4 * q + 2]]++] = (int)(q * 2); v2inc[f2[mv[4 * q + 3]]++] = (int)(q * 2 + 1);
+    }
+  }
+  if (upload(&h->minors, mvec) || upload(&h->mv, mv) || upload(&h->cptr, cptr) || upload(&h->cinc, cinc) || upload(&h->v1ptr, v1ptr) ||
+      upload(&h->v1inc, v1inc) || upload(&h->v2ptr, v2ptr) || upload(&h->v2inc, v2inc) || upload(&h->cnt, cnt) || upload(&h->flags, flags)) {
+    delete h;
+    return -2;
+  }
+  *out = h;
+  return 0;
+}
+
+void big_shor_destroy(ShorHost* h) {
+  if (!h) return;
+  cudaFree(h->minors); cudaFree(h->mv); cudaFree(h->cptr); cudaFree(h->cinc); cudaFree(h->v1ptr); cudaFree(h->v1inc);
+  cudaFree(h->v2ptr); cudaFree(h->v2inc); cudaFree(h->cnt); cudaFree(h->flags);
+  delete h;
+}
+
 size_t big_node_bytes(int n, int m, int k, int Lmax) { return make_layout(n, m, k, Lmax > 0 ? Lmax : 0).total * sizeof(double); }
 
 int big_create(const BigProblemView& pv, int B, const int* node_cut_ptr, const int* node_cut_ids, const unsigned char* node_cut_dirs,
@@ -88,6 +181,18 @@ int big_create(const BigProblemView& pv, int B, const int* node_cut_ptr, const i
     snprintf(buf, sizeof buf, "large-block engine: %d nodes x %.1f MB exceed the free device memory (%.1f GB); relax the frontier in chunks",
              B, L.total * 8.0 / 1048576.0, free_b / 1073741824.0);
     g_berr = buf; delete f; return -4;
+  }
+  if (pv.shor) {
+    f->SL = make_shor_layout(pv.n, pv.m, pv.k, pv.shor->nm, pv.shor->nv1, pv.shor->nv2);
+    const size_t need_s = (size_t)B * f->SL.total * sizeof(double);
+    if (need + need_s + ((size_t)1 << 30) > free_b) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "Shor rows: %d nodes x %.1f MB exceed the free device memory; relax the frontier in chunks", B, f->SL.total * 8.0 / 1048576.0);
+      g_berr = buf; delete f; return -4;
+    }
+    BCU(cudaMalloc(&f->SS, need_s));
+    BCU(cudaMalloc(&f->outW, (size_t)B * pv.n * pv.m * sizeof(double)));
+    BCU(cudaMalloc(&f->outXt, (size_t)B * pv.k * pv.n * pv.m * sizeof(double)));
   }
   BCU(cudaMalloc(&f->S, need));
   BCU(cudaMalloc(&f->I, (size_t)B * ISTR * sizeof(int)));
@@ -127,6 +232,7 @@ int big_create(const BigProblemView& pv, int B, const int* node_cut_ptr, const i
 
 void big_destroy(BigFrontier* f) {
   if (!f) return;
+  cudaFree(f->SS); cudaFree(f->outW); cudaFree(f->outXt);
   cudaFree(f->S); cudaFree(f->I); cudaFree(f->active); cudaFree(f->counters);
   cudaFree(f->cut_ptr); cudaFree(f->cut_ids); cudaFree(f->cut_dirs);
   for (int b = 0; b < 3; ++b) cudaFree(f->base[b]);
@@ -153,6 +259,17 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
   a.o.jacobi_sweeps = tune->jacobi_sweeps;
   a.o.window = tune->window;
   a.o.steps_max = tune->steps_max; a.o.steps_start = tune->steps_start; a.o.infeasible_by_bound = tune->infeasible_by_bound;
+  const bool shor = pv.shor != nullptr;
+  if (shor) {
+    const ShorHost* h = pv.shor;
+    a.sh.on = 1; a.sh.SL = f->SL; a.sh.SS = f->SS; a.sh.minors = h->minors; a.sh.mv = h->mv; a.sh.cptr = h->cptr; a.sh.cinc = h->cinc;
+    a.sh.v1ptr = h->v1ptr; a.sh.v1inc = h->v1inc; a.sh.v2ptr = h->v2ptr; a.sh.v2inc = h->v2inc; a.sh.flags = h->flags; a.sh.cnt = h->cnt;
+  }
+  const ShorLayout& SL = f->SL;
+  const long long nblk5 = shor ? (long long)SL.k * SL.nm : 0, nvv = shor ? SL.nv1 + SL.nv2 + SL.nm : 0;
+  const unsigned g5 = (unsigned)std::max<long long>(1, (nblk5 + 127) / 128), gc128 = shor ? (unsigned)((SL.C + 127) / 128) : 1,
+                 gc256 = shor ? (unsigned)((SL.C + 255) / 256) : 1, gcw = shor ? (unsigned)((SL.C + 7) / 8) : 1,
+                 gv = (unsigned)std::max<long long>(1, (nvv + 255) / 256), gvr = (unsigned)std::max<long long>(1, ((long long)SL.k * nvv + 255) / 256);
   const auto t_start = std::chrono::steady_clock::now();
   BCU(cudaEventRecord(f->ev0, st));
   // ---- setup: start bases, node records, Woodbury inverses
@@ -162,6 +279,10 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
   sa.pool_x = pv.pool_x; sa.pool_vhat = pv.pool_vhat; sa.cut_ptr = f->cut_ptr; sa.cut_ids = f->cut_ids; sa.cut_dirs = f->cut_dirs;
   for (int b = 0; b < 3; ++b) sa.base[b] = f->base[b];
   k_node_init<<<B, 256, f->smem_init, st>>>(a, sa);
+  if (shor) {
+    BCU(cudaMemsetAsync(f->SS, 0, (size_t)B * SL.total * sizeof(double), st));
+    k_shor_init<<<dim3(std::max(g5, gc256), B), 256, 0, st>>>(a);
+  }
   std::vector<int> act(B);
   for (int b = 0; b < B; ++b) act[b] = b;
   BCU(cudaMemcpyAsync(f->active, act.data(), (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -177,10 +298,24 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
   while (nact > 0 && it < a.o.max_iter) {
     ++it;
     a.it = it; a.force = force; a.step = 0;
+    if (shor) {     // Shor rows: projections of the moment blocks, adjoint sums into the variables (omc_big_shor.cuh)
+      k_shor_proj5<<<dim3(g5, nact), 128, 0, st>>>(a, 0);
+      k_shor_proj9<<<dim3(gc128, nact), 128, 0, st>>>(a, 0);
+      k_shor_gather_c<<<dim3(gcw, nact), 256, 0, st>>>(a, 0);
+      k_shor_gather_v<<<dim3(gv, nact), 256, 0, st>>>(a, 0);
+      stt.launches += 4;
+    }
     k_xt<<<dim3(L.tilesXT, nact), 256, f->smem_xt, st>>>(a);
+    if (shor) { k_shor_col<<<dim3(L.m, nact), 128, 0, st>>>(a); stt.launches += 1; }
     k_y1<<<dim3(L.tilesYU, nact), 256, f->smem_y, st>>>(a);
     k_small<<<nact, 128, f->smem_small, st>>>(a);
     k_y2<<<dim3(L.tilesYU, nact), 256, f->smem_y, st>>>(a);
+    if (shor) {
+      k_shor_v5<<<dim3(g5, nact), 128, 0, st>>>(a);
+      k_shor_vc<<<dim3(gc256, nact), 256, 0, st>>>(a);
+      k_shor_relax_v<<<dim3(gvr, nact), 256, 0, st>>>(a);
+      stt.launches += 3;
+    }
     const bool check = (it % a.o.check_every == 0) || it >= a.o.max_iter;
     // steps_start rounds at the first iteration and, when some node has a termination decision pending, in check iterations
     const int rounds = (it == 1 || (check && force) || it >= a.o.max_iter) ? a.o.steps_start : a.o.steps_max;
@@ -201,13 +336,30 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
     if (!check) continue;
     k_reorth<<<dim3(nact, 3), 256, 0, st>>>(a);
     BCU(cudaMemsetAsync(f->counters, 0, 8 * sizeof(int), st));
+    if (shor) {     // multipliers mu / rho = v - P(v) of the Shor rows and their adjoint sums
+      k_shor_zero_chk<<<nact, 32, 0, st>>>(a);
+      k_shor_proj5<<<dim3(g5, nact), 128, 0, st>>>(a, 1);
+      k_shor_proj9<<<dim3(gc128, nact), 128, 0, st>>>(a, 1);
+      k_shor_gather_c<<<dim3(gcw, nact), 256, 0, st>>>(a, 1);
+      k_shor_gather_v<<<dim3(gv, nact), 256, 0, st>>>(a, 1);
+    }
     k_check<<<dim3(L.tilesAll, nact), 256, f->smem_y, st>>>(a);
+    if (shor) {
+      k_shor_check_c<<<dim3(gc256, nact), 256, 0, st>>>(a);
+      k_shor_check_5<<<dim3(g5, nact), 128, 0, st>>>(a);
+      k_shor_check_col<<<dim3((L.m + 127) / 128, nact), 128, 0, st>>>(a);
+      stt.launches += 8;
+    }
     k_decide<<<nact, 128, (size_t)L.rcap * sizeof(double), st>>>(a, f->counters);
     stt.launches += 3; stt.checks += 1;
     BCU(cudaMemcpyAsync(h_cnt, f->counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     BCU(cudaStreamSynchronize(st));
     BCU(cudaGetLastError());
     if (h_cnt[2] > 0) {
+      if (shor) {
+        k_shor_rescale5<<<dim3(g5, nact), 128, 0, st>>>(a);
+        k_shor_rescale_c<<<dim3(gc256, nact), 256, 0, st>>>(a);
+      }
       k_rescale<<<dim3(ntmax, nact, 4), 256, 0, st>>>(a);
       k_rescale_theta<<<nact, 3 * PM, 0, st>>>(a);
       k_minv<<<nact, 256, 0, st>>>(a, 1);
@@ -229,6 +381,7 @@ int big_relax(BigFrontier* f, const omc_relax_opts* ro, const BigTuning* tune, f
   }
   stt.iterations = it;
   k_extract<<<B, 256, 0, st>>>(a, B, f->outX, f->outY, f->outU, nullptr, f->status, f->iters, f->objective, f->lower_bound, f->res);
+  if (shor) k_shor_extract<<<dim3(gc256, B), 256, 0, st>>>(a, B, f->outW, f->outXt);
   BCU(cudaGetLastError());
   BCU(cudaEventRecord(f->ev1, st));
   BCU(cudaStreamSynchronize(st));
@@ -260,6 +413,16 @@ int big_fetch(BigFrontier* f, int* status, double* objective, double* lower_boun
 }
 
 const BigStats* big_stats(const BigFrontier* f) { return &f->stats; }
+
+int big_fetch_shor(BigFrontier* f, double* W, double* Xt) {
+  if (!f->SS) { g_berr = "the frontier has no Shor rows"; return -3; }
+  const BigProblemView& pv = f->pv;
+  const size_t B = f->B, C = (size_t)pv.n * pv.m;
+  if (W) BCU(cudaMemcpyAsync(W, f->outW, B * C * sizeof(double), cudaMemcpyDeviceToHost, pv.stream));
+  if (Xt) BCU(cudaMemcpyAsync(Xt, f->outXt, B * pv.k * C * sizeof(double), cudaMemcpyDeviceToHost, pv.stream));
+  BCU(cudaStreamSynchronize(pv.stream));
+  return 0;
+}
 
 long long big_debug_fetch(BigFrontier* f, int node, int which, double* out, long long cap) {
   const Layout& L = f->L;

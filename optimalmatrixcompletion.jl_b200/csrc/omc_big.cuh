@@ -120,6 +120,47 @@ inline Layout make_layout(int n, int m, int k, int Lcap) {
   return L;
 }
 
+constexpr int B5 = 15;
+// ---- per-node Shor record (doubles), stride SL.total ---------------------------------------------------------------
+struct ShorLayout {
+  int k, npair, K9;          // K9 = (k+1)(k+2)/2 packed entries of the (k+1) x (k+1) block
+  long long C, nm, nv1, nv2;
+  size_t Xt, Wd, H, V1, V2, V3, Xtt, Wdt, Ht, V1t, V2t, V3t, GX, GW, GH, vB, TB, v9, T9, v6, v7, vs, Ts, gTd, Fd, chk, total;
+};
+inline ShorLayout make_shor_layout(int n, int m, int k, long long nm, long long nv1, long long nv2) {
+  ShorLayout S;
+  S.k = k; S.npair = k * (k - 1) / 2; S.K9 = (k + 1) * (k + 2) / 2;
+  S.C = (long long)n * m; S.nm = nm; S.nv1 = nv1; S.nv2 = nv2;
+  size_t o = 0;
+  auto take = [&](size_t cnt) { size_t r = o; o = al4(o + cnt); return r; };
+  const size_t C = (size_t)S.C;
+  S.Xt = take(k * C); S.Wd = take(k * C); S.H = take((size_t)S.npair * C + 1);
+  S.V1 = take((size_t)k * nv1 + 1); S.V2 = take((size_t)k * nv2 + 1); S.V3 = take((size_t)k * nm + 1);
+  S.Xtt = take(k * C); S.Wdt = take(k * C); S.Ht = take((size_t)S.npair * C + 1);
+  S.V1t = take((size_t)k * nv1 + 1); S.V2t = take((size_t)k * nv2 + 1); S.V3t = take((size_t)k * nm + 1);
+  S.GX = take(k * C); S.GW = take(k * C); S.GH = take((size_t)S.npair * C + 1);
+  S.vB = take((size_t)k * nm * B5 + 1); S.TB = take((size_t)k * nm * B5 + 1);
+  S.v9 = take(C * S.K9); S.T9 = take(C * S.K9);
+  S.v6 = take(m); S.v7 = take(k * C); S.vs = take(C * 3); S.Ts = take(C * 3);
+  S.gTd = take(m); S.Fd = take(m); S.chk = take(64 * 8);
+  S.total = o;
+  return S;
+}
+
+struct ShorDev {          // problem-level structure (shared by all nodes) + per-node records
+  int on;
+  ShorLayout SL;
+  double* SS;             // node Shor records
+  const int* minors;      // [nm][4]
+  const int* mv;          // [nm][4]: V1 id (row i1), V1 id (row i2), V2 id (col j1), V2 id (col j2)
+  const int* cptr; const int* cinc;     // coordinate incidence: entries minor * 4 + slot
+  const int* v1ptr; const int* v1inc;   // V1 incidence: minor * 2 + which (0: entry (2,1), 1: entry (4,3))
+  const int* v2ptr; const int* v2inc;   // V2 incidence: minor * 2 + which (0: entry (3,1), 1: entry (4,2))
+  const unsigned char* flags;           // per coordinate: bit 0 covered, bit 1 SOC
+  const int* cnt;                       // minors per coordinate
+};
+
+
 struct Opts {
   double eps_abs, eps_rel, sigma, alpha, rho0, cutoff, track_tol, confirm_tol, adapt_thresh;
   int max_iter, check_every, adapt_every, steps_max, steps_start, fix_linear3_right, cut_type, infeasible_by_bound, jacobi_sweeps, window;
@@ -137,6 +178,7 @@ struct BigArgs {
   int it;               // current iteration (1-based)
   int step;             // tracker step within the iteration
   int force;            // this iteration is followed by an off-schedule check (confirm pending somewhere)
+  ShorDev sh;           // Shor valid-inequality rows (omc_big_shor.cuh); sh.on = 0 without them
 };
 
 __device__ __forceinline__ double* node_ptr(const BigArgs& a, int slot) { return a.S + (size_t)slot * a.L.total; }
@@ -255,7 +297,29 @@ __global__ void __launch_bounds__(256, 2) k_xt(BigArgs a) {
           const size_t e = (size_t)i * m + j, ev = (size_t)i * N1 + n + j;
           const double D = V1[ev], x = S[L.X + e], mk = (double)a.Mk[e], am = a.AM[e];
           const double gX = -2.0 * rho * (D - 2.0 * F[r][c]);
-          const double xt = (sig * x + am + gX) / (mk + sig + 2.0 * rho);
+          double xt;
+          if (!a.sh.on) {
+            xt = (sig * x + am + gX) / (mk + sig + 2.0 * rho);
+          } else {
+            // Shor rows: X = sum_t Xt[t], linear objective -A X on Omega; per-coordinate Sherman-Morrison over the k slices
+            //   (sig + 2 rho (cnt + [k>1] cov)) x_t + (2 rho + rho soc) sum_s x_s = sig Xt[t] + A mask + gX + rho GX[t]
+            const ShorLayout& SL = a.sh.SL;
+            double* Q = a.sh.SS + (size_t)slot * SL.total;
+            const unsigned char fl = a.sh.flags[e];
+            const int kk = SL.k;
+            const double dX = sig + 2.0 * rho * (a.sh.cnt[e] + ((kk > 1 && (fl & 1)) ? 1.0 : 0.0));
+            const double cpl = 2.0 * rho + ((fl & 2) ? rho : 0.0);
+            double sum = 0.0;
+            for (int t = 0; t < kk; ++t) sum += sig * Q[SL.Xt + (size_t)t * SL.C + e] + am + gX + rho * Q[SL.GX + (size_t)t * SL.C + e];
+            const double Ssum = sum / (dX + cpl * kk);
+            xt = 0.0;
+            for (int t = 0; t < kk; ++t) {
+              const double rhs = sig * Q[SL.Xt + (size_t)t * SL.C + e] + am + gX + rho * Q[SL.GX + (size_t)t * SL.C + e];
+              const double xtt = (rhs - cpl * Ssum) / dX;
+              Q[SL.Xtt + (size_t)t * SL.C + e] = xtt;
+              xt += xtt;
+            }
+          }
           const double vn = D + al * (xt - F[r][c]);
           V1[ev] = vn;
           vnew[r][c] = vn;
@@ -284,6 +348,12 @@ __global__ void __launch_bounds__(256, 2) k_xt(BigArgs a) {
           const size_t e = (size_t)i * m + j, ev = (size_t)i * N1 + j;
           const double D = V1T[ev], tt0 = T[e];
           const double gT = -rho * (D - 2.0 * F[r][c]);
+          if (a.sh.on && i == j) {       // Shor rows couple Theta~_jj to column j of W: k_shor_col updates this entry
+            double* Q = a.sh.SS + (size_t)slot * a.sh.SL.total;
+            Q[a.sh.SL.gTd + j] = gT; Q[a.sh.SL.Fd + j] = F[r][c];
+            vnew[r][c] = D; tnew[r][c] = tt0;
+            continue;
+          }
           const double tt = (sig * tt0 - ((i == j) ? a.cT : 0.0) + gT) / (sig + rho);
           const double vn = D + al * (tt - F[r][c]);
           const double tn_ = al * tt + (1.0 - al) * tt0;
@@ -1512,11 +1582,17 @@ __global__ void __launch_bounds__(256, 2) k_check(BigArgs a) {
           rp = fmax(rp, fabs(x - F[r][c]));
           np_ = fmax(np_, fabs(F[r][c]));
           const double gX = -2.0 * mu;
-          rd = fmax(rd, fabs(mk * x - am - gX));
-          nd_ = fmax(nd_, fmax(fabs(mk * x), fmax(fabs(am), fabs(gX))));
-          s4 += mk * x * x;
-          const double d = mk * x - am;     // mk (x - A)
-          s5 += d * d;
+          if (a.sh.on) {                    // Shor form: linear objective; the X_t stationarity is finished by k_shor_check_c
+            a.sh.SS[(size_t)slot * a.sh.SL.total + a.sh.SL.Xtt + e] = gX;
+            nd_ = fmax(nd_, fmax(fabs(am), fabs(gX)));
+            s5 += am * x;                   // sum_Omega A X
+          } else {
+            rd = fmax(rd, fabs(mk * x - am - gX));
+            nd_ = fmax(nd_, fmax(fabs(mk * x), fmax(fabs(am), fabs(gX))));
+            s4 += mk * x * x;
+            const double d = mk * x - am;     // mk (x - A)
+            s5 += d * d;
+          }
         }
       }
   } else if (t < nX + nT) {
@@ -1538,7 +1614,8 @@ __global__ void __launch_bounds__(256, 2) k_check(BigArgs a) {
           rp = fmax(rp, fabs(tt - F[r][c]));
           np_ = fmax(np_, fabs(F[r][c]));
           const double gT = -mu;
-          rd = fmax(rd, fabs(((i == j) ? a.cT : 0.0) - gT));
+          if (a.sh.on && i == j) a.sh.SS[(size_t)slot * a.sh.SL.total + a.sh.SL.gTd + j] = gT;     // finished by k_shor_check_col
+          else rd = fmax(rd, fabs(((i == j) ? a.cT : 0.0) - gT));
           nd_ = fmax(nd_, fabs(gT));
           if (i == j) s6 += tt;
         }
@@ -1737,8 +1814,14 @@ __global__ void __launch_bounds__(128) k_decide(BigArgs a, int* counters /* [0] 
   rp = fmax(rp, fabs((a.ktr - R0[0]) - s4r));
   np_ = fmax(np_, fmax(fabs(s4r), fmax(a.a, a.ktr)));
   nd_ = fmax(nd_, a.cT);
-  const double dual = -0.5 * s4 + a.c0 + rho * s7 - rho * a.a * s8 + a.ktr * m4 + dsum - s9;
-  const double objp = 0.5 * s5 + a.cT * s6;
+  double dual = -0.5 * s4 + a.c0 + rho * s7 - rho * a.a * s8 + a.ktr * m4 + dsum - s9;
+  double objp = 0.5 * s5 + a.cT * s6;
+  if (a.sh.on) {      // Shor form (OMC.jl:1838-1846, 1961-1968): 1/2 sum_I (A^2 - 2 A X + W) + cT tr Theta~; rows' residuals from k_shor_check_*
+    const double* Qc = a.sh.SS + (size_t)slot * a.sh.SL.total + a.sh.SL.chk;
+    rd = fmax(rd, Qc[0]); rp = fmax(rp, Qc[1]);
+    dual += Qc[2];
+    objp = a.c0 - s5 + 0.5 * Qc[3] + a.cT * s6;
+  }
   const double ub = (a.o.cutoff < 1e299) ? a.o.cutoff : 2.0 * fmax(fabs(objp), fabs(dual)) + 1.0;
   auto w1 = [&](double trTb) { return (double)n * a.ktr + sqrt((double)n * m * a.ktr * trTb) + (double)m * trTb + (double)n * k * a.sa; };
   const double bound = dual - rd * w1(ub / a.cT);
@@ -1753,15 +1836,16 @@ __global__ void __launch_bounds__(128) k_decide(BigArgs a, int* counters /* [0] 
   // mu lies in the dual cone only when the trackers hold every eigenvalue of the minority side (a guard column is left) and
   // are converged: the certified bound is reported from such checks only (it never decreases)
   const bool tracked_ok = (was_confirm || a.it >= a.o.max_iter) && guard_ok && resmax <= 10.0 * a.o.confirm_tol;
-  if (tracked_ok) S[L.scal + S_LB] = fmax(S[L.scal + S_LB], bound);
+  if (tracked_ok && !a.sh.on) S[L.scal + S_LB] = fmax(S[L.scal + S_LB], bound);
   int decision = -1;
   if (!(fabs(objp) < 1e300 && fabs(dual) < 1e300 && rp < 1e300 && rd < 1e300)) {
     NI[I_STATUS] = OMC_STATUS_NUMERICAL; NI[I_DONE] = 1;
     return;
   }
+  // (with Shor rows ||w*||_1 is not bounded by the formula above: no certified bound, no cut-off / infeasibility by bound)
   if (rp <= a.o.eps_abs + a.o.eps_rel * np_ && rd <= a.o.eps_abs + a.o.eps_rel * nd_) decision = OMC_STATUS_OPTIMAL;
-  else if (a.o.cutoff < 1e299 && bound > a.o.cutoff) decision = OMC_STATUS_CUTOFF;
-  else if (a.o.infeasible_by_bound && Lc > 0 && bound_c0 > a.c0 * (1.0 + 1e-9) + 1e-12) decision = OMC_STATUS_INFEASIBLE;
+  else if (!a.sh.on && a.o.cutoff < 1e299 && bound > a.o.cutoff) decision = OMC_STATUS_CUTOFF;
+  else if (!a.sh.on && a.o.infeasible_by_bound && Lc > 0 && bound_c0 > a.c0 * (1.0 + 1e-9) + 1e-12) decision = OMC_STATUS_INFEASIBLE;
   if (decision >= 0) {
     if (tracked_ok || a.it >= a.o.max_iter) {
       NI[I_STATUS] = tracked_ok ? decision : OMC_STATUS_ITERATION_LIMIT;

@@ -7,6 +7,7 @@
 namespace omcbig {
 
 struct BigFrontier;
+struct ShorHost;
 
 struct BigProblemView {
   int n, m, k, cut_type;
@@ -17,6 +18,7 @@ struct BigProblemView {
   const double* pool_vhat;     // cut pool: [cap][k]               (device)
   cudaStream_t stream;
   int sm_count;
+  const ShorHost* shor;        // Shor valid-inequality structure of the problem (nullptr: none)
 };
 
 struct BigTuning {
@@ -44,6 +46,10 @@ const BigStats* big_stats(const BigFrontier* f);
 // 15 X, 16 Y, 17 T, 18 U (scaled variables, row-major).  Returns the number of doubles (cap = capacity of out), < 0 on error.
 long long big_debug_fetch(BigFrontier* f, int node, int which, double* out, long long cap);
 void big_destroy(BigFrontier* f);
+// Shor rows (OMC.jl:1503-1552, 1755-1828): minors [nm][4] = (i1, i2, j1, j2) and SOC coordinates [nsoc][2], 0-based host arrays
+int big_shor_create(int n, int m, int k, long long nm, const int* minors, long long nsoc, const int* soc, ShorHost** out);
+void big_shor_destroy(ShorHost* h);
+int big_fetch_shor(BigFrontier* f, double* W, double* Xt);
 // separation oracle for n > 104 (restarted Lanczos, one CTA per node); device pointers, column-major Y / U per node
 int big_smallest_eigvecs(int n, int k, int B, const double* dY, const double* dU, int nev, double* dlam, double* dvec, double* dbp,
                          int* dfeas, cudaStream_t st);

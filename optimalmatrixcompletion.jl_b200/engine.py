@@ -124,6 +124,16 @@ class Problem:
                                            _ptr(colptr, C.c_int32), _ptr(rowidx, C.c_int32), C.byref(nnz)))
         return rowptr, colidx[: nnz.value], colptr, rowidx[: nnz.value]
 
+    # ---- Shor valid inequalities --------------------------------------------------------------
+    def set_shor(self, minors, soc_coords):
+        """add_Shor_valid_inequalities = true (OMC.jl:1503-1552, 1755-1846): minors (N, 4) = (i1, i2, j1, j2) and SOC coordinates
+        (M, 2), both 0-based as shor_constraint_indexes returns them.  Empty lists remove the rows."""
+        mn = np.ascontiguousarray(np.asarray(minors, np.int32).reshape(-1, 4))
+        sc = np.ascontiguousarray(np.asarray(soc_coords, np.int32).reshape(-1, 2))
+        check(self.lib.omc_problem_set_shor(self.handle, len(mn), _ptr(mn, C.c_int32) if len(mn) else None,
+                                            len(sc), _ptr(sc, C.c_int32) if len(sc) else None))
+        self.has_shor = len(mn) + len(sc) > 0
+
     # ---- cut pool -------------------------------------------------------------------------
     def add_cut(self, x: np.ndarray, Uhat: np.ndarray) -> int:
         """Registers (breakpoint_vec, Uhat) created at OMC.jl:2522; only vhat = Uhat'x is uploaded (OMC.jl:1577)."""
@@ -192,6 +202,13 @@ class Frontier:
                                                  _ptr(dirs, C.c_uint8), _ptr(w, C.c_int32), _ptr(s, C.c_int32),
                                                  _lib.ENGINES[engine], C.byref(self.handle)))
         self.kernel_ms = None
+
+    def fetch_shor(self):
+        """Shor results per node (OMC.jl:1902, 1913): W (B, n, m) and Xt (B, k, n, m)."""
+        p, B = self.p, self.B
+        W = np.zeros((B, p.m, p.n)); Xt = np.zeros((B, p.k, p.m, p.n))
+        check(p.lib.omc_frontier_fetch_shor(self.handle, _ptr(W, C.c_double), _ptr(Xt, C.c_double)))
+        return W.transpose(0, 2, 1).copy(), Xt.transpose(0, 1, 3, 2).copy()
 
     def stats(self) -> dict:
         """omc_frontier_stats: engine, kernel launches, lockstep iterations, node-iterations, checks, rho changes, bytes per node."""
