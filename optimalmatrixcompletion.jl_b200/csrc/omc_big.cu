@@ -426,7 +426,7 @@ int big_fetch_shor(BigFrontier* f, double* W, double* Xt) {
 
 long long big_debug_fetch(BigFrontier* f, int node, int which, double* out, long long cap) {
   const Layout& L = f->L;
-  if (node < 0 || node >= f->B || which < 0 || which > 18) return -1;
+  if (node < 0 || node >= f->B || which < 0 || which > 19) return -1;
   size_t off = 0, cnt = 0;
   const int b = which % 3;
   if (which < 3) { off = L.V[b]; cnt = (size_t)L.N[b] * L.N[b]; }
@@ -437,6 +437,7 @@ long long big_debug_fetch(BigFrontier* f, int node, int which, double* out, long
   else if (which == 15) { off = L.X; cnt = (size_t)L.n * L.m; }
   else if (which == 16) { off = L.Y; cnt = (size_t)L.n * L.n; }
   else if (which == 17) { off = L.T; cnt = (size_t)L.m * L.m; }
+  else if (which == 19) { off = L.scal; cnt = SSTR; }
   else { off = L.U; cnt = (size_t)L.n * L.k; }
   if ((long long)cnt > cap) return -1;
   if (cudaMemcpy(out, f->S + (size_t)node * L.total + off, cnt * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;

@@ -1825,7 +1825,9 @@ __global__ void __launch_bounds__(128) k_decide(BigArgs a, int* counters /* [0] 
   const double ub = (a.o.cutoff < 1e299) ? a.o.cutoff : 2.0 * fmax(fabs(objp), fabs(dual)) + 1.0;
   auto w1 = [&](double trTb) { return (double)n * a.ktr + sqrt((double)n * m * a.ktr * trTb) + (double)m * trTb + (double)n * k * a.sa; };
   const double bound = dual - rd * w1(ub / a.cT);
-  const double bound_c0 = dual - rd * w1(a.c0 / a.cT);
+  // infeasibility: a feasible node holds the point X = 0, Theta~ = 0 (and W = 0, every Shor variable 0) of value c0.  Without Shor
+  // rows the optimum w* has tr Theta~ <= c0 / cT; with them the test point itself (||w||_1 <= w1(0)) bounds the dual value.
+  const double bound_c0 = dual - rd * w1(a.sh.on ? 0.0 : a.c0 / a.cT);
   S[L.scal + S_RP] = rp; S[L.scal + S_RD] = rd; S[L.scal + S_OBJP] = objp; S[L.scal + S_OBJD] = dual;
   S[L.scal + S_NP] = np_; S[L.scal + S_ND] = nd_;
   NI[I_ITERS] = a.it;
@@ -1842,10 +1844,10 @@ __global__ void __launch_bounds__(128) k_decide(BigArgs a, int* counters /* [0] 
     NI[I_STATUS] = OMC_STATUS_NUMERICAL; NI[I_DONE] = 1;
     return;
   }
-  // (with Shor rows ||w*||_1 is not bounded by the formula above: no certified bound, no cut-off / infeasibility by bound)
+  // (with Shor rows ||w*||_1 is not bounded by the formula above: no certified bound and no cut-off)
   if (rp <= a.o.eps_abs + a.o.eps_rel * np_ && rd <= a.o.eps_abs + a.o.eps_rel * nd_) decision = OMC_STATUS_OPTIMAL;
   else if (!a.sh.on && a.o.cutoff < 1e299 && bound > a.o.cutoff) decision = OMC_STATUS_CUTOFF;
-  else if (!a.sh.on && a.o.infeasible_by_bound && Lc > 0 && bound_c0 > a.c0 * (1.0 + 1e-9) + 1e-12) decision = OMC_STATUS_INFEASIBLE;
+  else if (a.o.infeasible_by_bound && Lc > 0 && bound_c0 > a.c0 * (1.0 + 1e-9) + 1e-12) decision = OMC_STATUS_INFEASIBLE;
   if (decision >= 0) {
     if (tracked_ok || a.it >= a.o.max_iter) {
       NI[I_STATUS] = tracked_ok ? decision : OMC_STATUS_ITERATION_LIMIT;

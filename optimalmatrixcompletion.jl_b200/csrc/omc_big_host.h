@@ -43,7 +43,7 @@ int big_fetch(BigFrontier* f, int* status, double* objective, double* lower_boun
               double* U);
 const BigStats* big_stats(const BigFrontier* f);
 // diagnostics: copies one array of a node record to the host.  which: 0..2 V_b, 3..5 Z_b, 6..8 theta_b, 9..11 R_b, 12..14 W_b,
-// 15 X, 16 Y, 17 T, 18 U (scaled variables, row-major).  Returns the number of doubles (cap = capacity of out), < 0 on error.
+// 15 X, 16 Y, 17 T, 18 U (scaled variables, row-major), 19 the node scalars (rho, v4, rp, rd, objp, objd, lb, ...).  Returns the number of doubles (cap = capacity of out), < 0 on error.
 long long big_debug_fetch(BigFrontier* f, int node, int which, double* out, long long cap);
 void big_destroy(BigFrontier* f);
 // Shor rows (OMC.jl:1503-1552, 1755-1828): minors [nm][4] = (i1, i2, j1, j2) and SOC coordinates [nsoc][2], 0-based host arrays

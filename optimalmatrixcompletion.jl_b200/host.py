@@ -256,7 +256,14 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
                                      gap: float = 1e-4, use_disjunctive_cuts: bool = True,
                                      disjunctive_cuts_type: Optional[str] = None,
                                      disjunctive_cuts_breakpoints: Optional[str] = None,
-                                     add_Shor_valid_inequalities: bool = False, root_only: bool = False,
+                                     add_Shor_valid_inequalities: bool = False,
+                                     Shor_valid_inequalities_noisy_rank1_num_entries_present=(1, 2, 3, 4),
+                                     add_Shor_valid_inequalities_fraction: float = 1.0,
+                                     add_Shor_valid_inequalities_iterative: bool = False,
+                                     max_update_Shor_indices_probability: float = 1.0,
+                                     min_update_Shor_indices_probability: float = 0.1,
+                                     update_Shor_indices_probability_decay_rate: float = 1.1,
+                                     update_Shor_indices_n_minors: int = 100, root_only: bool = False,
                                      altmin_flag: bool = True, max_altmin_probability: float = 1.0,
                                      min_altmin_probability: float = 0.005, altmin_probability_decay_rate: float = 1.1,
                                      altmin_root_n_iters: int = 1, use_max_steps: bool = False, max_steps: int = 1000000,
@@ -273,7 +280,16 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
     if not use_disjunctive_cuts:
         raise NotImplementedError("use_disjunctive_cuts = false (McCormick path) is out of scope (SURVEY.md section 2)")
     if add_Shor_valid_inequalities:
-        raise NotImplementedError("add_Shor_valid_inequalities = true (K4) is not built yet (DESIGN.md section 8)")
+        if not 0.0 <= add_Shor_valid_inequalities_fraction <= 1.0:                                            # OMC.jl:256-263
+            raise ValueError(f"Argument `add_Shor_valid_inequalities_fraction` = {add_Shor_valid_inequalities_fraction} out of bounds [0.0, 1.0].")
+        if add_Shor_valid_inequalities_iterative:
+            # OMC.jl:670-676, 956-982, 2495-2540: the minors grow from parent to child, i.e. every node has its own row structure;
+            # the engine shares one structure per problem (omc_problem_set_shor)
+            raise NotImplementedError("add_Shor_valid_inequalities_iterative = true is out of scope (DESIGN.md section 8)")
+    else:
+        add_Shor_valid_inequalities_fraction = None                                                           # OMC.jl:264-266
+    max_update_Shor_indices_probability = min_update_Shor_indices_probability = None                         # OMC.jl:325-330
+    update_Shor_indices_probability_decay_rate = update_Shor_indices_n_minors = None
     if disjunctive_cuts_type not in ("linear", "linear2", "linear3"):
         raise ValueError('Invalid input for disjunctive cuts type.\nDisjunctive cuts type must be either "linear" or '
                          f'"linear2" or "linear3";\n{disjunctive_cuts_type} supplied instead.')         # OMC.jl:218-224
@@ -307,6 +323,19 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
     start_time = time.time()
     pool = max(4, 4 * frontier_batch) if warm_start else 0
     problem = Problem(k, A, indices, gamma, disjunctive_cuts_type, state_pool_capacity=pool, device=device)
+    if add_Shor_valid_inequalities:
+        # OMC.jl:646-669: all 2 x 2 minors with the listed numbers of observed entries, a random fraction of them, and an RSOC row
+        # on every coordinate no kept minor covers
+        from .engine import shor_constraint_indexes as _shor_idx
+        minors, soc = _shor_idx(problem, list(Shor_valid_inequalities_noisy_rank1_num_entries_present), with_soc=True)
+        if add_Shor_valid_inequalities_fraction < 1.0:
+            minors = minors[rng.random(len(minors)) < add_Shor_valid_inequalities_fraction]                   # randsubseq
+            cov = np.zeros((n, m), bool)
+            cov[minors[:, 0], minors[:, 2]] = cov[minors[:, 0], minors[:, 3]] = True
+            cov[minors[:, 1], minors[:, 2]] = cov[minors[:, 1], minors[:, 3]] = True
+            soc = np.argwhere(~cov).astype(np.int32)
+        problem.set_shor(minors, soc)
+        instance_shor = dict(constraints_indexes=minors, SOC_constraints_indexes=soc)
     solve_time_altmin = solve_time_relaxation = 0.0
     dict_solve_times_altmin, dict_num_iterations_altmin, dict_solve_times_relaxation = [], [], []
     cnt = dict(nodes_dominated=0, nodes_relax_infeasible=0, nodes_relax_feasible=0, nodes_relax_feasible_pruned=0,
@@ -516,6 +545,13 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
         altmin_root_n_iters=altmin_root_n_iters, use_max_steps=use_max_steps, max_steps=max_steps, time_limit=time_limit,
         use_disjunctive_cuts=use_disjunctive_cuts, disjunctive_cuts_type=disjunctive_cuts_type,
         disjunctive_cuts_breakpoints=disjunctive_cuts_breakpoints, add_Shor_valid_inequalities=add_Shor_valid_inequalities,
+        add_Shor_valid_inequalities_fraction=add_Shor_valid_inequalities_fraction,
+        add_Shor_valid_inequalities_iterative=add_Shor_valid_inequalities_iterative,
+        max_update_Shor_indices_probability=max_update_Shor_indices_probability,
+        min_update_Shor_indices_probability=min_update_Shor_indices_probability,
+        update_Shor_indices_probability_decay_rate=update_Shor_indices_probability_decay_rate,
+        update_Shor_indices_n_minors=update_Shor_indices_n_minors,
+        Shor_valid_inequalities_noisy_rank1_num_entries_present=list(Shor_valid_inequalities_noisy_rank1_num_entries_present),
         start_time=start_time, end_time=end_time, time_taken=end_time - start_time,
         solve_time_altmin=solve_time_altmin, dict_solve_times_altmin=dict_solve_times_altmin,
         dict_num_iterations_altmin=dict_num_iterations_altmin, solve_time_relaxation_feasibility=0.0,
@@ -525,4 +561,6 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
     instance["tree"] = tree
     instance["open_nodes"] = [tree.nodes[i] for i in sorted(tree.nodes)]
     instance["problem"] = problem
+    if add_Shor_valid_inequalities:
+        instance["Shor_info"] = instance_shor                      # BBNodeShorInfo of the root (shared by every node), 0-based
     return solution, printlist, instance

@@ -1,0 +1,112 @@
+"""GPU parity tests of the Shor valid-inequality rows (K4: OMC.jl:1503-1552, 1755-1846) in the batched engine, through the
+C ABI (omc_problem_set_shor / omc_frontier_fetch_shor), against oracle/shor_relax.py (same program, exact projections).
+
+Tolerance: 1e-5 relative on the bound at eps 1e-7 (the program is a linear objective over many small cones: the optimal
+value is flatter in the iterate than the plain relaxation's; observed 2e-7 .. 5e-6), 1e-4 absolute on X, 2e-3 on W."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def omc():
+    import omc_b200
+    omc_b200.init(0)
+    return omc_b200
+
+
+def _structure(mask, pattern):
+    from oracle import shor as SI
+    n, m = mask.shape
+    minors = [tuple(v - 1 for v in t) for t in SI.shor_constraint_indexes(mask, pattern)] if pattern else []
+    cov = np.zeros((n, m), bool)
+    for (i1, i2, j1, j2) in minors:
+        cov[i1, j1] = cov[i1, j2] = cov[i2, j1] = cov[i2, j2] = True
+    return minors, [(i, j) for i in range(n) for j in range(m) if not cov[i, j]]
+
+
+@pytest.mark.parametrize("k,n,m,nidx,seed,pattern", [(1, 5, 6, 18, 3, [1, 2, 3, 4]), (2, 5, 6, 20, 3, [1, 2, 3, 4]),
+                                                      (1, 6, 7, 22, 2, []), (2, 6, 7, 26, 1, [4]), (3, 5, 6, 22, 2, [3, 4])])
+def test_shor_rows_match_oracle(omc, k, n, m, nidx, seed, pattern):
+    from oracle import relaxation as R, shor_relax as SR
+    from oracle.datagen import generate_matrix_completion_data
+    A, mask = generate_matrix_completion_data(k, n, m, nidx, seed)
+    minors, soc = _structure(mask, pattern)
+    ref = SR.solve_relaxation_shor(A, mask, 20.0, k, minors, soc, opts=R.Options(eps_abs=1e-7, eps_rel=1e-7, max_iter=60000))
+    assert ref["status"] == R.STATUS_OPTIMAL
+    p = omc.Problem(k, A, mask, 20.0)
+    p.set_shor(minors, soc)
+    fr = p.frontier([[]])
+    assert fr.stats()["engine"] == "batched"
+    fr.relax(omc.default_opts(eps_abs=1e-7, eps_rel=1e-7, max_iter=60000))
+    r = fr.fetch()[0]
+    W, Xt = fr.fetch_shor()
+    assert r["termination_status"] == "OPTIMAL", r
+    assert abs(r["objective"] - ref["objective"]) <= 1e-5 * abs(ref["objective"]), (r["objective"], ref["objective"])
+    assert r["iters"] <= 1.3 * ref["iters"] + 100, (r["iters"], ref["iters"])
+    # (W is not unique where it costs nothing -- unobserved coordinates of a column whose Theta_jj has slack -- hence the looser pin)
+    assert np.abs(r["X"] - ref["X"]).max() <= 1e-4 and np.abs(W[0] - ref["W"]).max() <= 2e-3
+    assert np.abs(Xt[0].sum(axis=0) - r["X"]).max() <= 1e-6           # X = sum_t Xt (OMC.jl:1492-1493)
+    assert r["lower_bound"] == float("-inf")                          # no certified bound with these rows (include/omc_b200.h)
+    # Theta_jj = sum_i W_ij and W >= X^2 hold at the returned point (OMC.jl:1757-1767): the objective is then >= the plain one
+    assert (W[0] >= r["X"] ** 2 - 1e-5).all()
+    fr.close()
+    # removing the rows gives the plain relaxation back
+    p.set_shor([], [])
+    r0 = p.relax_batch([[]], omc.default_opts(eps_abs=1e-7, eps_rel=1e-7, max_iter=60000), engine="batched")[0]
+    ro = R.solve_relaxation(A, mask, 20.0, k, opts=R.Options(eps_abs=1e-7, eps_rel=1e-7, max_iter=60000))
+    assert abs(r0["objective"] - ro["objective"]) <= 1e-6 * abs(ro["objective"])
+    assert r["objective"] >= r0["objective"] * (1 - 1e-5)             # the inequalities tighten
+
+
+def test_shor_rows_with_cut_nodes_batch_equals_singles(omc):
+    """Two cut nodes (chains of 4 and 3 linear2 cuts) relaxed in one batch == relaxed alone (bit for bit) == the oracle."""
+    from conftest import feasible_chain
+    from oracle import relaxation as R, shor_relax as SR
+    from oracle.datagen import generate_matrix_completion_data
+    k, n, m = 2, 6, 7
+    A, mask = generate_matrix_completion_data(k, n, m, 26, 1)
+    minors, soc = _structure(mask, [3, 4])
+    nodes = [feasible_chain("linear2", n, k, 4, np.random.default_rng(2)), feasible_chain("linear2", n, k, 3, np.random.default_rng(3))]
+    p = omc.Problem(k, A, mask, 20.0, "linear2")
+    p.set_shor(minors, soc)
+    gnodes = [[omc.Cut(p.add_cut(x, Uh), x, Uh, d) for x, Uh, d in nd] for nd in nodes]
+    o = omc.default_opts(eps_abs=1e-7, eps_rel=1e-7, max_iter=60000)
+    both = p.relax_batch(gnodes, o)
+    for q, nd in enumerate(nodes):
+        one = p.relax_batch([gnodes[q]], o)[0]
+        assert one["objective"] == both[q]["objective"] and one["iters"] == both[q]["iters"]
+        ref = SR.solve_relaxation_shor(A, mask, 20.0, k, minors, soc, "linear2", nd, opts=R.Options(eps_abs=1e-7, eps_rel=1e-7, max_iter=60000))
+        assert ref["status"] == R.STATUS_OPTIMAL and both[q]["termination_status"] == "OPTIMAL"
+        assert abs(both[q]["objective"] - ref["objective"]) <= 1e-5 * abs(ref["objective"]), (q, both[q]["objective"], ref["objective"])
+
+
+def test_shor_argument_checks(omc):
+    from oracle.datagen import generate_matrix_completion_data
+    A, mask = generate_matrix_completion_data(1, 5, 6, 18, 3)
+    p = omc.Problem(1, A, mask, 20.0)
+    with pytest.raises(RuntimeError, match="out of range"):
+        p.set_shor([(0, 7, 0, 1)], [])
+    with pytest.raises(RuntimeError, match="covered"):
+        p.set_shor([(0, 1, 0, 1)], [(0, 0)])
+    p.set_shor([(0, 1, 0, 1)], [(2, 2)])
+    with pytest.raises(RuntimeError, match="batched engine only"):
+        p.frontier([[]], engine="persistent")
+
+
+def test_branchandbound_with_shor_rows_certifies_same_optimum(omc):
+    """matrix_completion_branchandbound(...; add_Shor_valid_inequalities = true) on a test-scale instance reaches the same
+    certified optimum as without the rows (they are valid for every rank-k point), with a root bound at least as tight."""
+    from oracle.datagen import generate_matrix_completion_data
+    k, n, m = 1, 6, 7
+    A, mask = generate_matrix_completion_data(k, n, m, 26, 1)
+    kw = dict(node_selection="bestfirst", disjunctive_cuts_type="linear", disjunctive_cuts_breakpoints="smallest_1_eigvec",
+              gap=1e-3, max_steps=400, use_max_steps=True, time_limit=300,
+              relax_opts=omc.default_opts(eps_abs=1e-7, eps_rel=1e-7, max_iter=20000))
+    s0, _, i0 = omc.matrix_completion_branchandbound(k, A, mask, 20.0, **kw)
+    s1, _, i1 = omc.matrix_completion_branchandbound(k, A, mask, 20.0, add_Shor_valid_inequalities=True, **kw)
+    assert abs(s1["objective"] - s0["objective"]) <= 2e-3 * abs(s0["objective"])
+    assert i1["run_log"][0][3] >= i0["run_log"][0][3] * (1 - 1e-5)           # root lower bound
+    assert i1["run_details"]["nodes_explored"] <= i0["run_details"]["nodes_explored"] + 2
+    assert len(i1["Shor_info"]["constraints_indexes"]) > 0
