@@ -295,7 +295,10 @@ def run_b200(args):
         for r in range(world):
             ids_r = list(range(len(all_cuts)))[r::world]
             cost[ids_r] = got[r, : len(ids_r)]
-        my_ids = balanced_partition(cost, world)[rank]
+        # lockstep cost model: below ~floor nodes an iteration costs its launch latencies (measured: a lone C5 node iterates at
+        # ~0.8 ms, a node inside a batch at ~0.165 ms), so the shard that holds the longest node gets fewer node-iterations
+        floor_nodes = int(os.environ.get("OMC_BALANCE_FLOOR", {"C5": 5}.get(CFG, 32)))
+        my_ids = balanced_partition(cost, world, floor_nodes)[rank]
         fr.close()
         node_cuts, fr = make_frontier(my_ids)
         rebalanced = True
@@ -420,7 +423,7 @@ def run_b200(args):
                        "nodes_terminal": int(total_terminal), "eps": EPS, "max_iter": MAX_ITER, "cutoff": incumbent,
                        "start": "cold", "l2": "flushed between steps (256 MiB fill); frontier state exceeds L2", "frontier": src,
                        "parallelism": f"one frontier of {int(total_nodes)} nodes sharded over {world} GPU(s), "
-                                      + ("re-balanced by measured iterations (longest-first greedy), " if rebalanced else "block-cyclic, ")
+                                      + ("re-balanced by measured iterations (longest-first greedy, lockstep cost model), " if rebalanced else "block-cyclic, ")
                                       + "no data-path collective; all-reduce-min of 2 doubles per step inside libomc_b200.so",
                        "iters_per_node_mean": total_iters / total_nodes, "cuts_per_node_mean": total_cuts / total_nodes,
                        "status_counts[opt,iterlim,infeas,time,cutoff,numerical]": status_all,

@@ -73,18 +73,34 @@ class LibraryComm:
         self.lib.omc_comm_destroy()
 
 
-def balanced_partition(costs: Sequence[float], world: int) -> List[List[int]]:
+def lockstep_cost(costs_desc: Sequence[float], floor_nodes: int) -> float:
+    """Predicted time of one lockstep relaxation of a shard (batched engine): iteration `it` costs max(active(it), floor_nodes)
+    node-units -- below `floor_nodes` active nodes an iteration is bound by its launch latencies, not by the nodes' bytes.
+    With iteration counts c_1 >= c_2 >= ... that is  floor_nodes * c_1 + sum_{j > floor_nodes} c_j."""
+    if not costs_desc:
+        return 0.0
+    f = max(int(floor_nodes), 0)
+    if f == 0:
+        return float(sum(costs_desc))
+    return f * float(costs_desc[0]) + float(sum(costs_desc[f:]))
+
+
+def balanced_partition(costs: Sequence[float], world: int, floor_nodes: int = 0) -> List[List[int]]:
     """Frontier re-balancing plan: longest-predicted-first greedy (LPT) partition of node indices over `world` ranks by their
     predicted cost (ADMM iterations of the node's last relaxation, or of its parent).  Deterministic: every rank computes the
     same plan from the all-gathered costs, and takes its own part -- node descriptors (pool ids + direction codes) are
-    replicated, so no node data moves.  Each part is ordered longest first."""
+    replicated, so no node data moves.  Each part is ordered longest first.  floor_nodes > 0 uses the lockstep cost model
+    (lockstep_cost): a shard holding a straggler gets fewer node-iterations, because the straggler's tail runs alone."""
     order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
-    loads = [0.0] * world
     parts: List[List[int]] = [[] for _ in range(world)]
+    vals: List[List[float]] = [[] for _ in range(world)]
+    loads = [0.0] * world
     for i in order:
-        r = min(range(world), key=lambda q: (loads[q], len(parts[q]), q))
+        c = float(costs[i])
+        r = min(range(world), key=lambda q: (lockstep_cost(vals[q] + [c], floor_nodes) if floor_nodes > 0 else loads[q], len(parts[q]), q))
         parts[r].append(i)
-        loads[r] += float(costs[i])
+        vals[r].append(c)
+        loads[r] += c
     return parts
 
 

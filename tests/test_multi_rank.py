@@ -65,6 +65,26 @@ def test_balanced_partition_is_deterministic_and_even():
     assert parts == balanced_partition(cost, 8)
 
 
+def test_balanced_partition_lockstep_cost_model_offloads_the_straggler_rank():
+    """One straggler (2150 iterations among ~260-iteration nodes, the C5 frontier's profile): with floor_nodes = 5 the rank that
+    holds it gets fewer node-iterations, and the predicted lockstep times of the ranks even out."""
+    sys.path.insert(0, ROOT)
+    import omc_b200  # noqa: F401
+    from omc_b200.parallel import balanced_partition, lockstep_cost
+    rng = np.random.default_rng(1)
+    cost = rng.integers(200, 330, size=256).astype(float)
+    cost[17] = 2150.0
+    plain = balanced_partition(cost, 2)
+    model = balanced_partition(cost, 2, floor_nodes=5)
+    assert sorted(i for p in model for i in p) == list(range(256))
+    t_plain = [lockstep_cost(sorted(cost[p], reverse=True), 5) for p in plain]
+    t_model = [lockstep_cost(sorted(cost[p], reverse=True), 5) for p in model]
+    assert max(t_model) < max(t_plain) and max(t_model) / min(t_model) < 1.02
+    r = [q for q in range(2) if 17 in model[q]][0]
+    assert cost[model[r]].sum() < cost[model[1 - r]].sum()
+    assert lockstep_cost([10.0, 4.0, 2.0], 0) == 16.0 and lockstep_cost([10.0, 4.0, 2.0], 2) == 22.0
+
+
 def test_library_comm_single_rank_is_a_noop():
     """world = 1: the in-library exchange (omc_comm_* / omc_allreduce_min / omc_allgather) needs neither NCCL nor a GPU."""
     sys.path.insert(0, ROOT)
