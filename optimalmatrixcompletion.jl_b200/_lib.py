@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libomc_b200.so")
+LIB_PATH = os.environ.get("OMC_B200_LIB") or os.path.join(_HERE, "libomc_b200.so")   # (override: A/B builds during development)
 
 OK = 0
 STATUS_OPTIMAL, STATUS_ITERATION_LIMIT, STATUS_INFEASIBLE, STATUS_TIME_LIMIT, STATUS_CUTOFF, STATUS_NUMERICAL = 0, 1, 2, 3, 4, 5

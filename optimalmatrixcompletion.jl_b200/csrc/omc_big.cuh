@@ -1012,9 +1012,16 @@ __global__ void __launch_bounds__(256) k_gram(BigArgs a) {
 constexpr int JN = 2 * PM, JLD = JN + 1;
 __device__ __forceinline__ void jacobi_cta(double* Ac, double* Qc, int n2, int max_sweeps, double off_tol, double amax, double* cs, int* pq,
                                            int* flag, double* red) {
-  const int tid = threadIdx.x;
+  // Cyclic Jacobi, round-robin ordering, n2 / 2 disjoint rotations per round.  Two barriers per round: the rotation parameters
+  // (one warp), then ONE pass that applies J' A J block-wise -- the 2 x 2 block (pair i, pair j) needs only its own four
+  // entries for the row rotation of pair i followed by the column rotation of pair j -- and the column rotations of Q.
+  // flag[3..5] rotate over the rounds (a round whose rotations are all identities is skipped without a barrier).
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int npair = n2 >> 1;
+  int* rf = flag + 3;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    __syncthreads();
+    if (tid < 3) rf[tid] = 0;
     double off = 0.0;
     {
       const int cj = tid & (JN - 1);
@@ -1025,11 +1032,10 @@ __device__ __forceinline__ void jacobi_cta(double* Ac, double* Qc, int n2, int m
     off = block_max(off, red);
     if (off <= off_tol || off < 1e-300) break;
     for (int rnd = 0; rnd < n2 - 1; ++rnd) {
-      if (tid == 0) flag[0] = 0;
-      __syncthreads();
+      const int fcur = rnd % 3;
       if (tid < npair) {
         int p_, q_;
-        if (tid == 0) { p_ = n2 - 1; q_ = rnd; }
+        if (tid == 0) { p_ = n2 - 1; q_ = rnd; rf[(rnd + 1) % 3] = 0; }
         else { p_ = (rnd + tid) % (n2 - 1); q_ = (rnd + n2 - 1 - tid) % (n2 - 1); }
         if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
         const double apq = Ac[p_ * JLD + q_], app = Ac[p_ * JLD + p_], aqq = Ac[q_ * JLD + q_];
@@ -1039,59 +1045,44 @@ __device__ __forceinline__ void jacobi_cta(double* Ac, double* Qc, int n2, int m
           const double t_ = ((tau >= 0.0) ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
           c_ = rsqrt(1.0 + t_ * t_);
           s_ = t_ * c_;
-          flag[0] = 1;
+          rf[fcur] = 1;
         }
         cs[tid * 2 + 0] = c_; cs[tid * 2 + 1] = s_;
         pq[tid * 2 + 0] = p_; pq[tid * 2 + 1] = q_;
       }
       __syncthreads();
-      if (!flag[0]) continue;
-      constexpr int PPT = PM / 4;     // pairs per thread
-      const int cc = tid & (JN - 1), g0 = tid >> 6;
-      double ap[PPT], aq[PPT], qp[PPT], qq[PPT];
-      if (cc < n2) {
+      if (!rf[fcur]) continue;
+      // lane = pair j (its rotation stays in registers for the whole pass), warp + 8 u = pair i: no index arithmetic beyond
+      // two row offsets per block; consecutive lanes hold consecutive columns (round-robin ordering), so the shared-memory
+      // accesses of a warp fall in distinct banks except at the wrap-around
+      if (lane < npair) {
+        const int pj = pq[2 * lane], qj = pq[2 * lane + 1];
+        const double cj = cs[2 * lane], sj = cs[2 * lane + 1];
 #pragma unroll
-        for (int u = 0; u < PPT; ++u) {
-          const int i = g0 + 4 * u;
-          if (i < npair) { ap[u] = Ac[pq[2 * i] * JLD + cc]; aq[u] = Ac[pq[2 * i + 1] * JLD + cc]; }
-        }
-#pragma unroll
-        for (int u = 0; u < PPT; ++u) {
-          const int i = g0 + 4 * u;
+        for (int u = 0; u < PM / 8; ++u) {
+          const int i = wrp + 8 * u;
           if (i < npair) {
-            const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
-            Ac[pq[2 * i] * JLD + cc] = c_ * ap[u] - s_ * aq[u];
-            Ac[pq[2 * i + 1] * JLD + cc] = s_ * ap[u] + c_ * aq[u];
+            double* rp = Ac + pq[2 * i] * JLD;
+            double* rq = Ac + pq[2 * i + 1] * JLD;
+            const double ci = cs[2 * i], si = cs[2 * i + 1];
+            const double app = rp[pj], apq = rp[qj], aqp = rq[pj], aqq = rq[qj];
+            const double rpp = ci * app - si * aqp, rqp = si * app + ci * aqp;
+            const double rpq = ci * apq - si * aqq, rqq = si * apq + ci * aqq;
+            rp[pj] = cj * rpp - sj * rpq; rp[qj] = sj * rpp + cj * rpq;
+            rq[pj] = cj * rqp - sj * rqq; rq[qj] = sj * rqp + cj * rqq;
           }
         }
-      }
-      __syncthreads();
-      if (cc < n2) {
-#pragma unroll
-        for (int u = 0; u < PPT; ++u) {
-          const int i = g0 + 4 * u;
-          if (i < npair) {
-            const int p_ = pq[2 * i], q_ = pq[2 * i + 1];
-            ap[u] = Ac[cc * JLD + p_]; aq[u] = Ac[cc * JLD + q_];
-            qp[u] = Qc[cc * JLD + p_]; qq[u] = Qc[cc * JLD + q_];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < PPT; ++u) {
-          const int i = g0 + 4 * u;
-          if (i < npair) {
-            const int p_ = pq[2 * i], q_ = pq[2 * i + 1];
-            const double c_ = cs[2 * i], s_ = cs[2 * i + 1];
-            Ac[cc * JLD + p_] = c_ * ap[u] - s_ * aq[u];
-            Ac[cc * JLD + q_] = s_ * ap[u] + c_ * aq[u];
-            Qc[cc * JLD + p_] = c_ * qp[u] - s_ * qq[u];
-            Qc[cc * JLD + q_] = s_ * qp[u] + c_ * qq[u];
-          }
+        for (int row = wrp; row < n2; row += 8) {
+          double* qr = Qc + row * JLD;
+          const double qp = qr[pj], qq = qr[qj];
+          qr[pj] = cj * qp - sj * qq;
+          qr[qj] = sj * qp + cj * qq;
         }
       }
       __syncthreads();
     }
   }
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
