@@ -197,6 +197,10 @@ int32_t omc_shor_indexes(omc_problem* p, const int32_t* present_list, int32_t nl
 /* ---- fused objective + MSE: replaces evaluate_objective (OMC.jl:2330-2359) and compute_MSE
  * (OMC.jl:2373-2409).  X column-major n*m.  out[0] objective, out[1] MSE in, out[2] MSE out, out[3] MSE all */
 int32_t omc_objective_mse(omc_problem* p, const double* X, double* out4);
+/* measurement only (bench.py secondary roofline entries): mean device time in ms over `reps` back-to-back repetitions of
+ * out_ms[0] the fused objective + MSE reduction on the last staged X, out_ms[1] the mask compaction sequence (expansion,
+ * counts, scans, CSR / CSC fill) into scratch buffers.  CUDA events on the library stream.                                */
+int32_t omc_profile_kernels(omc_problem* p, int32_t reps, float* out_ms);
 
 /* ---- multi-GPU exchange: one process per GPU, the frontier sharded over the processes.  No
  * reference counterpart (OMC.jl:700-1073 is a single sequential loop).  NCCL is bound at run time (dlopen libnccl.so.2).

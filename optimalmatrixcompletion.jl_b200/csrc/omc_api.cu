@@ -839,6 +839,47 @@ int32_t omc_objective_mse(omc_problem* p, const double* X, double* out4) {
   return OMC_OK;
 }
 
+int32_t omc_profile_kernels(omc_problem* p, int32_t reps, float* out_ms) {
+  NEED_INIT();
+  if (!p || !out_ms || reps <= 0) return fail(OMC_ERR_ARG, "bad argument");
+  const int n = p->n, m = p->m;
+  const long long total = (long long)n * m;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  // [0] fused objective + MSE reduction (K9) on the staged X
+  CU(cudaEventRecord(e0, g_stream));
+  for (int r = 0; r < reps; ++r) {
+    omc::objective_partial_kernel<<<g_sm_count * 4, 256, 0, g_stream>>>(p->Xdev.p, p->A.p, p->chunks.p, total, p->red.p);
+    omc::objective_final_kernel<<<1, 256, 0, g_stream>>>(p->red.p, g_sm_count * 4, p->gamma, total, p->red.p + 4 * g_sm_count * 4);
+  }
+  CU(cudaEventRecord(e1, g_stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaEventElapsedTime(&out_ms[0], e0, e1));
+  out_ms[0] /= reps;
+  // [1] mask compaction (K6): expansion, row / column counts, scans, CSR / CSC fill -- into scratch copies
+  DevBuf<int> rp, cp, ci, ri;
+  DevBuf<double> mk;
+  CU(rp.alloc(n + 1)); CU(cp.alloc(m + 1)); CU(ci.alloc(p->nnz > 0 ? p->nnz : 1)); CU(ri.alloc(p->nnz > 0 ? p->nnz : 1)); CU(mk.alloc(total));
+  const int blocks = (int)((total + 255) / 256 < g_sm_count * 8 ? (total + 255) / 256 : g_sm_count * 8);
+  CU(cudaEventRecord(e0, g_stream));
+  for (int r = 0; r < reps; ++r) {
+    omc::mask_expand_kernel<<<blocks, 256, 0, g_stream>>>(p->chunks.p, mk.p, total);
+    omc::mask_count_kernel<<<(m * 32 + 255) / 256, 256, 0, g_stream>>>(p->chunks.p, n, m, 0, cp.p);
+    omc::mask_count_kernel<<<(n * 32 + 255) / 256, 256, 0, g_stream>>>(p->chunks.p, n, m, 1, rp.p);
+    omc::scan_inclusive_kernel<<<1, 1024, 0, g_stream>>>(cp.p, m);
+    omc::scan_inclusive_kernel<<<1, 1024, 0, g_stream>>>(rp.p, n);
+    omc::mask_fill_kernel<<<(m * 32 + 255) / 256, 256, 0, g_stream>>>(p->chunks.p, n, m, 0, cp.p, ri.p);
+    omc::mask_fill_kernel<<<(n * 32 + 255) / 256, 256, 0, g_stream>>>(p->chunks.p, n, m, 1, rp.p, ci.p);
+  }
+  CU(cudaEventRecord(e1, g_stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaEventElapsedTime(&out_ms[1], e0, e1));
+  out_ms[1] /= reps;
+  CU(cudaGetLastError());
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return OMC_OK;
+}
+
 int32_t omc_debug_psd_project_batch(int32_t N, int32_t B, const double* Vin, double* P, double* lam, int32_t* sweeps,
                                     float* kernel_ms) {
   NEED_INIT();

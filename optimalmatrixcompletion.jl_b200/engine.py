@@ -124,6 +124,12 @@ class Problem:
                                            _ptr(colptr, C.c_int32), _ptr(rowidx, C.c_int32), C.byref(nnz)))
         return rowptr, colidx[: nnz.value], colptr, rowidx[: nnz.value]
 
+    def profile_kernels(self, reps: int = 20):
+        """omc_profile_kernels: mean device ms of (objective + MSE reduction, mask compaction) -- measurement only."""
+        out = np.zeros(2, np.float32)
+        check(self.lib.omc_profile_kernels(self.handle, int(reps), _ptr(out, C.c_float)))
+        return float(out[0]), float(out[1])
+
     # ---- Shor valid inequalities --------------------------------------------------------------
     def set_shor(self, minors, soc_coords):
         """add_Shor_valid_inequalities = true (OMC.jl:1503-1552, 1755-1846): minors (N, 4) = (i1, i2, j1, j2) and SOC coordinates
