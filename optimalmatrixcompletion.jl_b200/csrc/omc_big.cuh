@@ -265,7 +265,7 @@ __device__ __forceinline__ void lower_tile(int t, int& I, int& J) {
 // ------------------------------------------------------------------------------------------------------------------
 // k_xt: X region (tiles 0 .. tn*tm-1) and Theta region (lower tiles), one fused pass.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) k_xt(BigArgs a) {
+__global__ void __launch_bounds__(256, 3) k_xt(BigArgs a) {
   extern __shared__ __align__(16) double sm[];
   const Layout& L = a.L;
   const int slot = a.active[blockIdx.y];
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(256, 2) k_y2(BigArgs a) {
 // of one (node, block): V streams through shared memory in 64 x 32 chunks (register-prefetched).  Epilogue: partial Gram
 // matrices of this row tile, partA = Z_tile' Wout_tile and (which = 1) partB = R_tile' Wout_tile.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int KC = 32, VLD = 36, PLD = PM + 8;
+constexpr int KC = 32, VLD = 36, PLD = PM + 4;   // 36 = 4 mod 16: the 8 x 4 (row / k, column) fragment loads of a half-warp fall in 16 distinct bank pairs
 constexpr int NTL = PM / 8;     // DMMA n-tiles per warp
 
 __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
@@ -728,6 +728,20 @@ __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
   double* Wout = S + (which ? L.W2[b] : L.W[b]);
   const int r0 = blockIdx.x * TS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  // live 8-column tiles of the panel: Z has p columns (16 for the third block); R only the window k_resid kept (the
+  // residuals of the positive Ritz pairs, `window` guard columns and the probe) -- the other columns are exact zeros
+  unsigned ntmask = 0;
+  {
+    const int p = L.p[b];
+    int na = p;
+    if (which && a.o.window > 0 && a.it >= 2) {
+      int rprev = 0;
+      for (int cc = 0; cc < p; ++cc) rprev += (S[L.th[b] + cc] > 0.0) ? 1 : 0;
+      na = min(p, rprev + a.o.window);
+    }
+    for (int nt = 0; nt < NTL; ++nt)
+      if (nt * 8 < na || (which && p > 1 && nt == (p - 1) / 8)) ntmask |= 1u << nt;
+  }
   double c[2][NTL][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -768,9 +782,11 @@ __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
       const double a0 = Vs[(rb + g) * VLD + kk * 4 + t4], a1 = Vs[(rb + 8 + g) * VLD + kk * 4 + t4];
 #pragma unroll
       for (int nt = 0; nt < NTL; ++nt) {
-        const double bb = Ps[(kk * 4 + t4) * PLD + nt * 8 + g];
-        dmma884(c[0][nt][0], c[0][nt][1], a0, bb, c[0][nt][0], c[0][nt][1]);
-        dmma884(c[1][nt][0], c[1][nt][1], a1, bb, c[1][nt][0], c[1][nt][1]);
+        if ((ntmask >> nt) & 1u) {
+          const double bb = Ps[(kk * 4 + t4) * PLD + nt * 8 + g];
+          dmma884(c[0][nt][0], c[0][nt][1], a0, bb, c[0][nt][0], c[0][nt][1]);
+          dmma884(c[1][nt][0], c[1][nt][1], a1, bb, c[1][nt][0], c[1][nt][1]);
+        }
       }
     }
   }
