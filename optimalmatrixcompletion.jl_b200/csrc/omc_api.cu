@@ -576,6 +576,18 @@ int32_t omc_frontier_create_ex(omc_problem* p, int32_t B, const int32_t* node_cu
     if (warm_ids && warm_ids[b] >= p->state_cap) return fail(OMC_ERR_ARG, "warm id out of range");
     if (save_ids && save_ids[b] >= p->state_cap) return fail(OMC_ERR_ARG, "save id out of range");
   }
+  if (save_ids && p->state_cap > 0) {   // a record written by one node must not be read or written by another node of the same launch
+    std::vector<char> used((size_t)p->state_cap, 0);
+    for (int b = 0; b < B; ++b)
+      if (save_ids[b] >= 0) {
+        if (used[save_ids[b]]) return fail(OMC_ERR_ARG, "save id %d appears twice in one frontier", save_ids[b]);
+        used[save_ids[b]] = 1;
+      }
+    if (warm_ids)
+      for (int b = 0; b < B; ++b)
+        if (warm_ids[b] >= 0 && used[warm_ids[b]] && save_ids[b] != warm_ids[b])
+          return fail(OMC_ERR_ARG, "state record %d is read by node %d and written by another node of the same frontier", warm_ids[b], b);
+  }
   if (engine == OMC_ENGINE_BATCHED) {
     if (warm_ids || save_ids) {
       for (int b = 0; b < B; ++b)

@@ -198,6 +198,20 @@ __device__ __forceinline__ double hash_unit(unsigned long long i, unsigned long 
   return (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
 }
 
+// L2 prefetch of the 64 x 64 tile (i0, j0) of a row-major array in the thread-to-entry mapping of the region kernels (one lane per
+// 32-byte sector).  Issued before the panels are staged and the low-rank tile is computed, so that the tile's DRAM latency
+// overlaps that FP64 work instead of stalling the element loop: a prefetch holds no register.
+__device__ __forceinline__ void prefetch_tile(const double* __restrict__ base, size_t ld, int i0, int j0, int rows, int cols, int ty, int tx) {
+  if (tx & 3) return;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = i0 + ty + 16 * r, j = j0 + tx + 16 * c;
+      if (i < rows && j < cols) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * ld + j));
+    }
+}
+
 // stage the first nc columns of rows [row0, row0 + 64) of a panel (global ld PM) into shared memory (ld), column a scaled
 // by sc[a] (sqrt(theta+) -> the low-rank term becomes a plain inner product, bitwise symmetric in (i, j))
 __device__ __forceinline__ void stage_panel(double* dst, int ld, const double* __restrict__ P, int row0, int nrows, const double* sc, int nc) {
@@ -282,6 +296,8 @@ __global__ void __launch_bounds__(256, 3) k_xt(BigArgs a) {
   if (t < L.tn * L.tm) {
     const int I = t / L.tm, J = t - I * L.tm;
     const int i0 = I * TS, j0 = J * TS;
+    prefetch_tile(V1 + n, N1, i0, j0, n, m, ty, tx);
+    prefetch_tile(S + L.X, m, i0, j0, n, m, ty, tx);
     stage_panel(Zi, ZLD, S + L.Z[0], i0, n, sc, nc);
     stage_panel(Zj, ZLD, S + L.Z[0] + (size_t)n * PM, j0, m, sc, nc);
     __syncthreads();
@@ -331,6 +347,8 @@ __global__ void __launch_bounds__(256, 3) k_xt(BigArgs a) {
     int I, J;
     lower_tile(t - L.tn * L.tm, I, J);
     const int i0 = I * TS, j0 = J * TS;
+    prefetch_tile(V1 + (size_t)n * N1 + n, N1, i0, j0, m, m, ty, tx);
+    prefetch_tile(S + L.T, m, i0, j0, m, m, ty, tx);
     stage_panel(Zi, ZLD, S + L.Z[0] + (size_t)n * PM, i0, m, sc, nc);
     stage_panel(Zj, ZLD, S + L.Z[0] + (size_t)n * PM, j0, m, sc, nc);
     __syncthreads();
@@ -409,6 +427,10 @@ __global__ void __launch_bounds__(256, 2) k_y1(BigArgs a) {
     int I, J;
     lower_tile(t, I, J);
     const int i0 = I * TS, j0 = J * TS;
+    prefetch_tile(S + L.V[0], N1, i0, j0, n, n, ty, tx);
+    prefetch_tile(S + L.V[1], N2, i0, j0, n, n, ty, tx);
+    prefetch_tile(S + L.V[2], n, i0, j0, n, n, ty, tx);
+    prefetch_tile(S + L.Y, n, i0, j0, n, n, ty, tx);
     for (int b = 0; b < 3; ++b) {
       stage_panel(Zi_[b], ld_[b], S + L.Z[b], i0, n, sc + b * PM, nc_[b]);
       stage_panel(Zj_[b], ld_[b], S + L.Z[b], j0, n, sc + b * PM, nc_[b]);
@@ -613,6 +635,11 @@ __global__ void __launch_bounds__(256, 2) k_y2(BigArgs a) {
     int I, J;
     lower_tile(t, I, J);
     const int i0 = I * TS, j0 = J * TS;
+    prefetch_tile(S + L.Yt, n, i0, j0, n, n, ty, tx);
+    prefetch_tile(S + L.V[0], N1, i0, j0, n, n, ty, tx);
+    prefetch_tile(S + L.V[1], N2, i0, j0, n, n, ty, tx);
+    prefetch_tile(S + L.V[2], n, i0, j0, n, n, ty, tx);
+    prefetch_tile(S + L.Y, n, i0, j0, n, n, ty, tx);
     for (int b = 0; b < 3; ++b) {
       stage_panel(Zi_[b], ld_[b], S + L.Z[b], i0, n, sc + b * PM, nc_[b]);
       stage_panel(Zj_[b], ld_[b], S + L.Z[b], j0, n, sc + b * PM, nc_[b]);

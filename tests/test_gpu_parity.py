@@ -140,6 +140,11 @@ def test_relaxation_batch_c2_against_oracle_and_properties(omc):
     # any feasible rank-k point bounds the relaxation from above
     u, s, vt = np.linalg.svd(np.where(mask, A, 0.0)); Xr = (u[:, :k] * s[:k]) @ vt[:k]
     assert root["objective"] <= p.objective_mse(Xr)[0]
+    # state-pool ids of one launch: a record is written by at most one node and not read by another (cross-CTA race otherwise)
+    with pytest.raises(RuntimeError, match="appears twice"):
+        p.relax_batch(kids, opts, save_ids=[1, 1])
+    with pytest.raises(RuntimeError, match="written by another node"):
+        p.relax_batch(kids, opts, warm_ids=[0, 2], save_ids=[2, 3])
     p.close()
 
 
