@@ -202,6 +202,67 @@ function shor_constraint_indexes(p::Problem, num_entries_present_list::Vector{In
     return [ntuple(q -> Int(tuples[q, t]) + 1, 4) for t in 1:cnt[]], [(Int(soc[1, t]) + 1, Int(soc[2, t]) + 1) for t in 1:nsoc[]]
 end
 
+"""`add_Shor_valid_inequalities = true` (non-iterative mode): attaches the root's `BBNodeShorInfo` (OMC.jl:646-669; 1-based tuples
+as the reference holds them) to the problem, so that every `relax_batch` of it carries the Shor rows of OMC.jl:1755-1828.
+Empty lists remove the rows.  (UNTESTED: no Julia in the build image; the Python mirror `engine.py:Problem.set_shor` is.)"""
+function set_shor!(p::Problem, constraints_indexes::Vector{NTuple{4, Int}}, SOC_constraints_indexes::Vector{Tuple{Int, Int}})
+    mn = Int32[t[q] - 1 for q in 1:4, t in constraints_indexes]            # 4 x N, 0-based, column = one minor
+    sc = Int32[t[q] - 1 for q in 1:2, t in SOC_constraints_indexes]
+    check(ccall((:omc_problem_set_shor, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int32}, Int64, Ptr{Int32}),
+                p.handle, size(mn, 2), mn, size(sc, 2), sc))
+end
+
+"""Relaxation of a batch of nodes WITH the Shor rows: `relax_batch` plus the result keys "W" and "Xt" (OMC.jl:1902, 1913)."""
+function relax_batch_shor(p::Problem, nodes; opts::RelaxOpts = default_opts())
+    B = length(nodes)
+    ptr, ids, dirs = flatten(p, [nd.disjunctive_cuts.cuts for nd in nodes])
+    fr = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:omc_frontier_create_ex, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{UInt8}, Ptr{Int32}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
+                p.handle, B, ptr, ids, dirs, C_NULL, C_NULL, 0, fr))
+    status = zeros(Int32, B); iters = zeros(Int32, B); objective = zeros(B); lower = zeros(B); res = zeros(2B)
+    X = zeros(p.n, p.m, B); Y = zeros(p.n, p.n, B); U = zeros(p.n, p.k, B)
+    W = zeros(p.n, p.m, B); Xt = zeros(p.n, p.m, p.k, B)
+    ms = Ref{Float32}(0)
+    try
+        t = @elapsed check(ccall((:omc_frontier_relax, LIB), Int32, (Ptr{Cvoid}, Ref{RelaxOpts}, Ref{Float32}), fr[], opts, ms))
+        check(ccall((:omc_frontier_fetch, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    fr[], status, objective, lower, iters, res, X, Y, U, C_NULL))
+        check(ccall((:omc_frontier_fetch_shor, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), fr[], W, Xt))
+        return [Dict{String, Any}(
+            "model" => nothing, "solve_time" => t / B, "termination_status" => STATUS_TO_MOI[Int(status[b])],
+            "feasible" => status[b] != 2, "objective" => objective[b],
+            "Y" => Y[:, :, b], "U" => U[:, :, b], "X" => X[:, :, b], "Θ" => nothing, "W" => W[:, :, b],
+            "Xt" => Xt[:, :, :, b], "iterations" => iters[b],
+        ) for b in 1:B]
+    finally
+        ccall((:omc_frontier_destroy, LIB), Int32, (Ptr{Cvoid},), fr[])
+    end
+end
+
+# ---- multi-GPU exchange inside the library (INTEGRATION.md section 4): one Julia process per GPU -----------------------------
+"""Rank 0 creates the 128-byte id; ship it to the other workers by any channel, then every rank calls `comm_init`."""
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:omc_comm_unique_id, LIB), Int32, (Ptr{UInt8},), id))
+    return id
+end
+comm_init(id::Vector{UInt8}, rank::Integer, world::Integer) =
+    check(ccall((:omc_comm_init, LIB), Int32, (Int32, Int32, Ptr{UInt8}), rank, world, id))
+comm_destroy() = check(ccall((:omc_comm_destroy, LIB), Int32, ()))
+"""In-place all-reduce-min over the ranks, e.g. of `[incumbent, min lower bound]` after a batch."""
+function allreduce_min!(v::Vector{Float64})
+    check(ccall((:omc_allreduce_min, LIB), Int32, (Ptr{Float64}, Int32), v, length(v)))
+    return v
+end
+"""All-gather of `cnt` doubles per rank (per-node iteration counts for `balanced_partition`)."""
+function allgather(v::Vector{Float64}, world::Integer)
+    out = zeros(length(v) * world)
+    check(ccall((:omc_allgather, LIB), Int32, (Ptr{Float64}, Int32, Ptr{Float64}), v, length(v), out))
+    return reshape(out, length(v), world)
+end
+
 """Fused `evaluate_objective` (OMC.jl:2330-2359) + `compute_MSE` (OMC.jl:2373-2409): (objective, in, out, all)."""
 function objective_mse(p::Problem, X::Matrix{Float64})
     out = zeros(4)
