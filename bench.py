@@ -196,7 +196,10 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     A, mask = instance(0)
     sample = max(2, min(cores, 64))
-    cuts, incumbent = load_frontier_pool(limit=args.nodes or W["nodes"])   # the GPU arm's single-GPU shard ...
+    if os.path.exists(FIXTURE):
+        cuts, incumbent = load_frontier_pool(limit=args.nodes or W["nodes"])   # the GPU arm's single-GPU shard ...
+    else:                                                          # config 2: the committed first nodes of the round-1 frontier
+        cuts, incumbent = load_frontier_fixture(), float("inf")
     stride = max(1, len(cuts) // sample)
     cuts = cuts[::stride][:sample]                                 # ... every stride-th node of it: like for like
     jobs = [(A, mask, GAMMA, W["k"], W["ct"], c, MAX_ITER, incumbent) for c in cuts]
@@ -217,7 +220,7 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "nodes_per_step": len(jobs), "eps": EPS, "max_iter": MAX_ITER,
                        "nodes_terminal_per_step": done / steps_done,
-                       "cutoff": incumbent,
+                       "cutoff": incumbent if np.isfinite(incumbent) else None,
                        "note": "CPU restatement of the relaxation (NumPy/LAPACK, oracle/bigblock.py: same ADMM, same cut-off and infeasibility rules as the "
                                "GPU arm), not Mosek: Julia and Mosek are absent; only nodes ending with a terminal status count, as in the GPU arm"},
             "cpu_baseline": {"value": value, "unit": "nodes/s", "cores": min(cores, len(jobs)), "kind": "port",
@@ -246,10 +249,18 @@ def run_b200(args):
     B = args.nodes or W["nodes"]
     # ---- the frontier: taken from the committed fixture when it holds enough nodes, else built ONCE on rank 0 and broadcast
     t0 = time.time()
-    all_cuts, incumbent = load_frontier_pool()
-    if len(all_cuts) < B * world:
+    if os.path.exists(FIXTURE):
+        all_cuts, incumbent = load_frontier_pool()
+    else:
+        # config 2 has no committed pool: with the incumbent as cut-off its tree closes after 3 nodes, so (as in round 1) a wide
+        # frontier is expanded on the GPU with the incumbent WITHHELD -- deterministically, by every rank for itself
+        need = B if args.scaling == "strong" else B * world
+        built = build_frontier_gpu(problem, need, omc, cutoff=float("inf"))
+        all_cuts = [[(np.asarray(c.x), np.asarray(c.Uhat).T @ np.asarray(c.x), list(c.directions)) for c in nd.disjunctive_cuts] for nd in built]
+        incumbent = float("inf")
+    if len(all_cuts) < B * world and args.scaling != "strong":
         raise SystemExit(f"the committed frontier holds {len(all_cuts)} nodes, {B * world} asked (scripts/dump_frontier_pool.py builds a larger one)")
-    src = os.path.relpath(FIXTURE, ROOT)
+    src = os.path.relpath(FIXTURE, ROOT) if os.path.exists(FIXTURE) else "expanded on the GPU at start-up (incumbent withheld)"
     if args.scaling == "strong":
         all_cuts = all_cuts[: B]                                   # ONE fixed frontier of B nodes shared by all ranks
     else:
@@ -421,7 +432,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "engine": stats["engine"], "nodes_per_gpu": Bl, "nodes_total": int(total_nodes),
-                       "nodes_terminal": int(total_terminal), "eps": EPS, "max_iter": MAX_ITER, "cutoff": incumbent,
+                       "nodes_terminal": int(total_terminal), "eps": EPS, "max_iter": MAX_ITER, "cutoff": incumbent if np.isfinite(incumbent) else None,
                        "start": "cold", "l2": "flushed between steps (256 MiB fill); frontier state exceeds L2", "frontier": src,
                        "parallelism": f"one frontier of {int(total_nodes)} nodes sharded over {world} GPU(s), "
                                       + ("re-balanced by measured iterations (longest-first greedy, lockstep cost model), " if rebalanced else "block-cyclic, ")

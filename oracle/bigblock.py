@@ -1,4 +1,6 @@
 """CPU restatement of the batched large-block relaxation engine (csrc/omc_big.cuh).  TEST INFRASTRUCTURE ONLY.
+PARITY UNPINNED by the reference (it ships no tests or golden vectors; Julia and Mosek are absent -- oracle/__init__.py): this
+restatement is pinned against oracle/relaxation.py (exact eigh projections) and the closed-form roots of oracle/kat.py instead.
 
 Same mathematical program and the same conic ADMM as ``oracle/relaxation.py`` (the reference's node relaxation,
 OMC.jl:1491-1499, 1554-1561, 1564-1685, 1848-1856; COSMO/OSQP form, scaling Y~ = a Y, U~ = sqrt(a) U, Theta~ = Theta/a),

@@ -1,4 +1,6 @@
 """CPU restatement of the node relaxation WITH Shor valid inequalities.  TEST INFRASTRUCTURE ONLY.
+PARITY UNPINNED by the reference (no tests or golden vectors; Julia and Mosek are absent -- oracle/__init__.py): pinned by the
+algorithm-independent properties listed at the end of this header.
 
 The reference's program (OMC.jl:1491-1499 variables, 1503-1552 Shor variables, 1554-1561 main cones, 1564-1685 cut rows,
 1755-1828 Shor rows, 1838-1846 objective), for any k:
