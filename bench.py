@@ -197,7 +197,10 @@ def run_reference(args):
     A, mask = instance(0)
     sample = max(2, min(cores, 64))
     if os.path.exists(FIXTURE):
-        cuts, incumbent = load_frontier_pool(limit=args.nodes or W["nodes"])   # the GPU arm's single-GPU shard ...
+        cuts, incumbent = load_frontier_pool()
+        want = args.nodes or W["nodes"]
+        ps = max(1, len(cuts) // want) if os.environ.get("OMC_BENCH_SAMPLE") == "strided" else 1
+        cuts = cuts[::ps][:want]                                   # the GPU arm's single-GPU shard ...
     else:                                                          # config 2: the committed first nodes of the round-1 frontier
         cuts, incumbent = load_frontier_fixture(), float("inf")
     stride = max(1, len(cuts) // sample)
@@ -261,10 +264,16 @@ def run_b200(args):
     if len(all_cuts) < B * world and args.scaling != "strong":
         raise SystemExit(f"the committed frontier holds {len(all_cuts)} nodes, {B * world} asked (scripts/dump_frontier_pool.py builds a larger one)")
     src = os.path.relpath(FIXTURE, ROOT) if os.path.exists(FIXTURE) else "expanded on the GPU at start-up (incumbent withheld)"
-    if args.scaling == "strong":
-        all_cuts = all_cuts[: B]                                   # ONE fixed frontier of B nodes shared by all ranks
-    else:
-        all_cuts = all_cuts[: B * world]
+    # The pool is ordered best bound first -- the order in which a best-first branch-and-bound pops its batches -- so the frontier
+    # of a run is the PREFIX of B x world nodes (weak) or B nodes (strong).  Nodes get harder down the list (more cuts, more
+    # ADMM iterations: mean 254 over the first 128 C5 nodes, 328 over the first 512), so nodes/s of a larger job is not N x the
+    # single-GPU figure even when the ranks are balanced; config.node_iterations_per_s is the mix-independent rate.
+    # OMC_BENCH_SAMPLE=strided takes an evenly strided sample of the pool instead (same statistical mix per GPU at every N).
+    want = B if args.scaling == "strong" else B * world
+    pool_stride = 1
+    if os.environ.get("OMC_BENCH_SAMPLE") == "strided" and os.path.exists(FIXTURE):
+        pool_stride = max(1, len(all_cuts) // max(want, 1))
+    all_cuts = all_cuts[::pool_stride][:want]
     my_ids = list(range(len(all_cuts)))[rank::world]               # block-cyclic shard of the one frontier
     comm = None
     if world > 1:                                                  # the engine's own exchange (libomc_b200.so: NCCL via dlopen)
@@ -421,7 +430,9 @@ def run_b200(args):
         except Exception:
             pass
         traffic = None
-        try:   # DRAM bytes per node-iteration from the committed ncu capture of the same workload (profiles/)
+        try:   # DRAM bytes per node-iteration from the committed ncu capture of the same workload (profiles/; config 5 only)
+            if CFG != "C5" or stats["engine"] != "batched":
+                raise KeyError("no capture for this workload")
             with open(os.path.join(ROOT, "profiles", "r02_ncu_big_summary.json")) as f:
                 traffic = float(json.load(f)["dram_bytes_per_node_iteration"]) * total_iters / max(1, world)
         except Exception:
@@ -433,7 +444,8 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "engine": stats["engine"], "nodes_per_gpu": Bl, "nodes_total": int(total_nodes),
                        "nodes_terminal": int(total_terminal), "eps": EPS, "max_iter": MAX_ITER, "cutoff": incumbent if np.isfinite(incumbent) else None,
-                       "start": "cold", "l2": "flushed between steps (256 MiB fill); frontier state exceeds L2", "frontier": src,
+                       "start": "cold", "l2": "flushed between steps (256 MiB fill); frontier state exceeds L2", "frontier": src + (f", every {pool_stride}th node" if pool_stride > 1 else ", prefix in best-first order"),
+                       "node_iterations_per_s": total_iters / (dev_ms_max * 1e-3),
                        "parallelism": f"one frontier of {int(total_nodes)} nodes sharded over {world} GPU(s), "
                                       + ("re-balanced by measured iterations (longest-first greedy, lockstep cost model), " if rebalanced else "block-cyclic, ")
                                       + "no data-path collective; all-reduce-min of 2 doubles per step inside libomc_b200.so",
@@ -444,7 +456,9 @@ def run_b200(args):
             "e2e": {"value": total_terminal / (e2e_ms_max * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(stats["launches"]) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "note": "batched engine, whole lockstep run (its kernels stream every node record once per pass): algorithmic bytes = node-iterations x "
+                         "note": ("persistent engine (node state lives in shared memory / L2 for the whole ADMM): the HBM byte model of the batched engine "
+                                  "does not describe it -- see DESIGN.md section 5, round-1 history, for its FP64 model; " if stats["engine"] != "batched" else "")
+                                 + "batched engine, whole lockstep run (its kernels stream every node record once per pass): algorithmic bytes = node-iterations x "
                                  f"{node_iteration_bytes(n, m, k, 0):.0f} B (+ cut vectors), DESIGN.md section 4b; peak = {peak_src}; traffic = DRAM bytes measured by ncu "
                                  "per node-iteration (profiles/r02_ncu_big_summary.json) x node-iterations of this run"},
             "clocks": sampler.summary(),
