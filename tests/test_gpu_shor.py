@@ -110,3 +110,28 @@ def test_branchandbound_with_shor_rows_certifies_same_optimum(omc):
     assert i1["run_log"][0][3] >= i0["run_log"][0][3] * (1 - 1e-5)           # root lower bound
     assert i1["run_details"]["nodes_explored"] <= i0["run_details"]["nodes_explored"] + 2
     assert len(i1["Shor_info"]["constraints_indexes"]) > 0
+
+
+def test_shor_rows_on_the_config3_mask_properties(omc):
+    """BASELINE config 3 (k = 2, 30 x 30, pattern [1, 2, 3, 4]: 177 853 minors, 355 706 moment blocks) is out of the exact oracle's
+    reach, so the full size is pinned by size-independent properties: the root converges; X = sum_t Xt; W >= X^2 everywhere
+    (implied by the (k+1) blocks, OMC.jl:1810-1826); plain bound <= Shor bound <= objective of a rank-k point (validity)."""
+    from oracle.datagen import config_instance
+    k, A, mask, g = config_instance("C3", 0)
+    p = omc.Problem(k, A, mask, g, "linear2")
+    o = omc.default_opts(eps_abs=1e-6, eps_rel=1e-6, max_iter=40000)
+    plain = p.relax_batch([[]], o, engine="batched")[0]
+    minors, soc = omc.shor_constraint_indexes(p, [1, 2, 3, 4])
+    assert len(minors) > 170000 and len(soc) == 0
+    p.set_shor(minors, soc)
+    fr = p.frontier([[]])
+    fr.relax(o)
+    r = fr.fetch()[0]
+    W, Xt = fr.fetch_shor()
+    assert r["termination_status"] == "OPTIMAL", r["iters"]
+    assert np.abs(Xt[0].sum(axis=0) - r["X"]).max() <= 1e-6
+    assert (W[0] >= r["X"] ** 2 - 1e-3).all()
+    U0 = np.linalg.svd(np.where(mask, A, 0.0))[0][:, :k]
+    am = omc.alternating_minimization(p, U0)
+    ub = p.objective_mse(am["U"] @ am["V"])[0]
+    assert plain["objective"] * (1 - 1e-4) <= r["objective"] <= ub * (1 + 1e-6), (plain["objective"], r["objective"], ub)
