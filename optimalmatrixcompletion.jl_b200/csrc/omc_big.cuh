@@ -1138,16 +1138,18 @@ __device__ __forceinline__ void jacobi_cta(double* Ac, double* Qc, int n2, int m
 // locked on (off-diagonal = Ritz residual), so `jacobi_sweeps` = 3 resolves it to rounding there, and an unconverged
 // start-phase Rayleigh-Ritz is finished by the following tracker steps.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr size_t RR_SMEM = ((size_t)2 * JN * JLD + 3 * PM * ZLD + 2 * PM + JN + 64) * sizeof(double) + (3 * PM + 2 * JN + 8) * sizeof(int);
+// shared memory of k_rr: the two 2p x 2p matrices only (69 KB: three CTAs per SM).  The p x p work matrices of the set-up (M, the
+// Cholesky factor, T = L~^-1, X0, C0, C0 T) live inside the second matrix before the Jacobi needs it, T is parked in the
+// bottom half of the node's Q' output during the Jacobi and comes back for the last product.
+constexpr int RR_X0 = 0, RR_C0 = PM * PM, RR_TM = 2 * PM * PM, RR_MM = 2 * PM * PM + PM * ZLD;   // offsets inside the Q region
+static_assert(RR_MM + PM * ZLD <= JN * JLD, "k_rr set-up matrices must fit the second Jacobi matrix");
+constexpr size_t RR_SMEM = ((size_t)2 * JN * JLD + 2 * PM + JN + 64) * sizeof(double) + (3 * PM + 2 * JN + 8) * sizeof(int);
 
-__global__ void __launch_bounds__(256) k_rr(BigArgs a) {
+__global__ void __launch_bounds__(256, 3) k_rr(BigArgs a) {
   extern __shared__ __align__(16) double sm[];
   double* A = sm;                       // [JN][JLD]
-  double* Q = A + JN * JLD;             // [JN][JLD]   (scratch for X0 / C0 before the Jacobi)
-  double* Mm = Q + JN * JLD;            // [PM][ZLD]
-  double* Lm = Mm + PM * ZLD;
-  double* Tm = Lm + PM * ZLD;
-  double* cs = Tm + PM * ZLD;           // [PM][2]
+  double* Q = A + JN * JLD;             // [JN][JLD]   (set-up matrices before the Jacobi, see RR_*)
+  double* cs = Q + JN * JLD;            // [PM][2]
   double* lam = cs + 2 * PM;            // [JN]
   double* red = lam + JN;               // [64]
   int* valid = reinterpret_cast<int*>(red + 64);   // [PM]
@@ -1162,31 +1164,39 @@ __global__ void __launch_bounds__(256) k_rr(BigArgs a) {
   if (a.step > 0 && !NI[I_MORE + b]) return;
   double* S = node_ptr(a, slot);
   const int tid = threadIdx.x, lane = tid & 31, p = L.p[b];
-  double* X0 = Q; double* C0 = Q + PM * ZLD;
+  // ---- set-up, stage 1: M (Gram matrix of the residual panel) -> guarded Cholesky-QR factor T.  M at 0, L at RR_MM, T at RR_TM.
+  double* Tm = Q + RR_TM;               // [PM][ZLD]
+  {
+    double* M0 = Q; double* L0 = Q + RR_MM;
+    for (int e = tid; e < PM * PM; e += 256) M0[(e / PM) * ZLD + (e % PM)] = S[L.Q[b] + e];
+    __syncthreads();
+    // residual of the minority columns (before this step; column p - 1 holds the probe) and the scale of H
+    double r2 = 0.0, h2 = 0.0;
+    if (tid < PM) {
+      if (tid < p - 1 && S[L.th[b] + tid] > 0.0) r2 = M0[tid * ZLD + tid];
+      double h = 0.0;
+      for (int i = 0; i < PM; ++i) { const double v = S[L.H[b] + i * PM + tid]; h += v * v; }
+      h2 = h;
+    }
+    r2 = block_sum(r2, red);
+    h2 = block_max(h2, red);
+    if (tid == 0) { lam[0] = r2; lam[1] = h2; }
+    __syncthreads();
+    if (tid < 32) chol_guard_warp(M0, L0, Tm, valid, lane, 1e-10, 1e-20 * lam[1], p, 1e-10, (p > 1) ? p - 1 : -1);
+    __syncthreads();
+  }
+  const double res2 = lam[0];
+  // ---- stage 2: X0 = Z'W2, C0 = R'W2 (sums of the row tiles' partials, ld PM) over the dead M; Y = C0 T over the dead L (ld PM)
+  double* X0 = Q + RR_X0; double* C0 = Q + RR_C0; double* Ym = Q + RR_MM;
   for (int e = tid; e < PM * PM; e += 256) {
-    const int i = e / PM, j = e % PM;
-    Mm[i * ZLD + j] = S[L.Q[b] + e];
     double sx = 0.0, sc_ = 0.0;
     for (int t = 0; t < L.nt[b]; ++t) {
       sx += S[L.partA[b] + (size_t)t * PM * PM + e];
       sc_ += S[L.partB[b] + (size_t)t * PM * PM + e];
     }
-    X0[i * ZLD + j] = sx; C0[i * ZLD + j] = sc_;
+    X0[e] = sx; C0[e] = sc_;
   }
-  __syncthreads();
-  // residual of the minority columns (before this step; column p - 1 holds the probe) and the scale of H
-  double res2 = 0.0, hs2 = 0.0;
-  if (tid < PM) {
-    if (tid < p - 1 && S[L.th[b] + tid] > 0.0) res2 = Mm[tid * ZLD + tid];
-    double h = 0.0;
-    for (int i = 0; i < PM; ++i) { const double v = S[L.H[b] + i * PM + tid]; h += v * v; }
-    hs2 = h;
-  }
-  res2 = block_sum(res2, red);
-  hs2 = block_max(hs2, red);
-  if (tid < 32) chol_guard_warp(Mm, Lm, Tm, valid, lane, 1e-10, 1e-20 * hs2, p, 1e-10, (p > 1) ? p - 1 : -1);
-  __syncthreads();
-  // A = [[sym(H), X0 T], [., T' C0 T]];  Y = C0 T goes to Mm (M is dead)
+  // A = [[sym(H), X0 T], [., T' C0 T]]
   for (int e = tid; e < JN * JLD; e += 256) A[e] = 0.0;
   __syncthreads();
   for (int e = tid; e < PM * PM; e += 256) {
@@ -1195,23 +1205,22 @@ __global__ void __launch_bounds__(256) k_rr(BigArgs a) {
     double s = 0.0, y = 0.0;
     for (int c = 0; c < PM; ++c) {
       const double t = Tm[c * ZLD + j];
-      s = fma(X0[i * ZLD + c], t, s);
-      y = fma(C0[i * ZLD + c], t, y);
+      s = fma(X0[i * PM + c], t, s);
+      y = fma(C0[i * PM + c], t, y);
     }
     A[i * JLD + PM + j] = s; A[(PM + j) * JLD + i] = s;
-    Mm[i * ZLD + j] = y;
+    Ym[i * PM + j] = y;
   }
   __syncthreads();
   for (int e = tid; e < PM * PM; e += 256) {
     const int i = e / PM, j = e % PM;
-    double s = 0.0;
-    for (int c = 0; c < PM; ++c) s = fma(Tm[c * ZLD + i], Mm[c * ZLD + j], s);
-    Lm[i * ZLD + j] = s;                         // T' C0 T (L is dead)
-  }
-  __syncthreads();
-  for (int e = tid; e < PM * PM; e += 256) {
-    const int i = e / PM, j = e % PM;
-    A[(PM + i) * JLD + PM + j] = 0.5 * (Lm[i * ZLD + j] + Lm[j * ZLD + i]);
+    double sij = 0.0, sji = 0.0;                  // (T' C0 T)_ij and its transpose entry: the block is symmetrised on the fly
+    for (int c = 0; c < PM; ++c) {
+      sij = fma(Tm[c * ZLD + i], Ym[c * PM + j], sij);
+      sji = fma(Tm[c * ZLD + j], Ym[c * PM + i], sji);
+    }
+    A[(PM + i) * JLD + PM + j] = 0.5 * (sij + sji);
+    S[L.Q[b] + (size_t)PM * PM + e] = Tm[i * ZLD + j];     // park T (the bottom half of Q' is written last)
   }
   __syncthreads();
   double amax = 0.0;
@@ -1269,8 +1278,13 @@ __global__ void __launch_bounds__(256) k_rr(BigArgs a) {
   }
   __syncthreads();
   // Q' (2 PM x PM): column c = eigenvector sel[c] scattered back to the original indices; bottom half multiplied by T.
-  // Mm receives the bottom halves first (compact -> original residual index), then T is applied.
-  for (int e = tid; e < PM * PM; e += 256) Mm[(e / PM) * ZLD + (e % PM)] = 0.0;
+  // Mm receives the bottom halves first (compact -> original residual index), then T is applied.  The compact matrix is dead:
+  // Mm and T (back from where it was parked) take its place.
+  double* Mm = Q; double* Tend = Q + PM * ZLD;
+  for (int e = tid; e < PM * PM; e += 256) {
+    Mm[(e / PM) * ZLD + (e % PM)] = 0.0;
+    Tend[(e / PM) * ZLD + (e % PM)] = S[L.Q[b] + (size_t)PM * PM + e];
+  }
   for (int e = tid; e < JN * PM; e += 256) if (e < PM * PM) S[L.Q[b] + e] = 0.0;
   __syncthreads();
   for (int e = tid; e < nl * p; e += 256) {
@@ -1284,7 +1298,7 @@ __global__ void __launch_bounds__(256) k_rr(BigArgs a) {
   for (int e = tid; e < PM * PM; e += 256) {
     const int ii = e / PM, c = e % PM;
     double v = 0.0;
-    if (c < p) for (int j = 0; j < PM; ++j) v = fma(Tm[ii * ZLD + j], Mm[j * ZLD + c], v);
+    if (c < p) for (int j = 0; j < PM; ++j) v = fma(Tend[ii * ZLD + j], Mm[j * ZLD + c], v);
     S[L.Q[b] + (size_t)(PM + ii) * PM + c] = v;
   }
   double thn = -1e300;
