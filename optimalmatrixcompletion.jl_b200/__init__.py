@@ -7,6 +7,6 @@ from . import _lib  # noqa: F401
 from .engine import (Problem, Frontier, Cut, default_opts, init, build_flags, bitmatrix_chunks,  # noqa: F401
                      matrix_completion_SDP_relaxation, evaluate_objective, compute_MSE,
                      matrix_completion_master_feasible, smallest_eigvecs_batch, psd_project_batch,
-                     measure_fp64_peak, alternating_minimization, alternating_minimization_batch, shor_constraint_indexes, LABELS, MOI_STATUS)
+                     measure_fp64_peak, alternating_minimization, alternating_minimization_batch, shor_constraint_indexes, generate_violated_Shor_minors, LABELS, MOI_STATUS)
 from .host import (BBNode, BBTree, JuliaPriorityQueue, child_directions, create_matrix_cut_child_nodes,  # noqa: F401,E402
                    expand_frontier, shard_block_cyclic, matrix_completion_branchandbound)

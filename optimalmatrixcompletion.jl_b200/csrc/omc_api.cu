@@ -10,6 +10,7 @@
 #include <math.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/omc_b200.h"
 #include "omc_device.cuh"
@@ -848,6 +849,55 @@ int32_t omc_objective_mse(omc_problem* p, const double* X, double* out4) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out4, p->red.p + 4 * g_sm_count * 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CU(cudaStreamSynchronize(g_stream));
+  return OMC_OK;
+}
+
+int32_t omc_shor_score_minors(omc_problem* p, const double* Xt, int64_t n_cand, const int32_t* cand, int64_t n_excl, const int32_t* excl,
+                              int64_t n_minors, int64_t* count, int32_t* tuples, double* scores) {
+  NEED_INIT();
+  if (!p || !Xt || n_cand < 0 || n_excl < 0 || n_minors < 0 || !count || (n_cand > 0 && !cand) || (n_excl > 0 && !excl))
+    return fail(OMC_ERR_ARG, "bad argument");
+  if (p->n > 65535 || p->m > 65535) return fail(OMC_ERR_UNSUPPORTED, "n, m <= 65535 (16-bit minor keys)");
+  *count = 0;
+  if (n_cand == 0 || n_minors == 0) return OMC_OK;
+  const int n = p->n, m = p->m, k = p->k;
+  for (int64_t q = 0; q < n_cand; ++q) {
+    const int32_t* c = cand + 4 * q;
+    if (c[0] < 0 || c[0] >= c[1] || c[1] >= n || c[2] < 0 || c[2] >= c[3] || c[3] >= m) return fail(OMC_ERR_ARG, "candidate minor %lld out of range", (long long)q);
+  }
+  std::vector<unsigned long long> keys((size_t)n_excl);
+  for (int64_t q = 0; q < n_excl; ++q)
+    keys[q] = ((unsigned long long)excl[4 * q] << 48) | ((unsigned long long)excl[4 * q + 1] << 32) | ((unsigned long long)excl[4 * q + 2] << 16) |
+              (unsigned long long)excl[4 * q + 3];
+  std::sort(keys.begin(), keys.end());
+  DevBuf<int> dc;
+  DevBuf<double> dX, ds;
+  DevBuf<unsigned long long> dk;
+  CU(dc.alloc((size_t)4 * n_cand)); CU(dX.alloc((size_t)k * n * m)); CU(ds.alloc((size_t)n_cand)); CU(dk.alloc(keys.empty() ? 1 : keys.size()));
+  CU(cudaMemcpyAsync(dc.p, cand, (size_t)4 * n_cand * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+  CU(cudaMemcpyAsync(dX.p, Xt, (size_t)k * n * m * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  if (!keys.empty()) CU(cudaMemcpyAsync(dk.p, keys.data(), keys.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, g_stream));
+  omc::shor_score_kernel<<<(unsigned)((n_cand + 255) / 256), 256, 0, g_stream>>>(dc.p, n_cand, dX.p, k, n, m, dk.p, (long long)keys.size(), ds.p);
+  CU(cudaGetLastError());
+  std::vector<double> hs((size_t)n_cand);
+  CU(cudaMemcpyAsync(hs.data(), ds.p, (size_t)n_cand * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CU(cudaStreamSynchronize(g_stream));
+  // top n_minors by (score, tuple), both descending: sort(...; rev = true) / partialsort!(...; rev = true) of OMC.jl:2634-2639
+  std::vector<int64_t> idx;
+  idx.reserve((size_t)n_cand);
+  for (int64_t q = 0; q < n_cand; ++q) if (hs[q] >= 0.0) idx.push_back(q);
+  auto before = [&](int64_t a_, int64_t b_) {
+    if (hs[a_] != hs[b_]) return hs[a_] > hs[b_];
+    for (int e = 0; e < 4; ++e) if (cand[4 * a_ + e] != cand[4 * b_ + e]) return cand[4 * a_ + e] > cand[4 * b_ + e];
+    return false;
+  };
+  const size_t take = std::min<size_t>(idx.size(), (size_t)n_minors);
+  std::partial_sort(idx.begin(), idx.begin() + take, idx.end(), before);
+  *count = (int64_t)take;
+  for (size_t q = 0; q < take; ++q) {
+    if (tuples) for (int e = 0; e < 4; ++e) tuples[4 * q + e] = cand[4 * idx[q] + e];
+    if (scores) scores[q] = hs[idx[q]];
+  }
   return OMC_OK;
 }
 

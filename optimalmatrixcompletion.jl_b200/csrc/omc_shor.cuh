@@ -173,4 +173,32 @@ __global__ void shor_soc_kernel(const unsigned int* __restrict__ covered, long l
   if (threadIdx.x == 0) *nsoc = base;
 }
 
+// generate_violated_Shor_minors (OMC.jl:2614-2640): score of every candidate minor, sum_t |Xt[i1,j1] Xt[i2,j2] - Xt[i1,j2] Xt[i2,j1]|,
+// one thread per candidate; minors already in the node (sorted 64-bit keys, binary search) get -1.  Products and the difference
+// are rounded separately (no FMA contraction), so the scores equal the reference's expression bit for bit and the top-n order
+// does not depend on the device.  Xt: k column-major n x m slices.
+__device__ __forceinline__ unsigned long long shor_key(int i1, int i2, int j1, int j2) {
+  return ((unsigned long long)i1 << 48) | ((unsigned long long)i2 << 32) | ((unsigned long long)j1 << 16) | (unsigned long long)j2;
+}
+__global__ void __launch_bounds__(256) shor_score_kernel(const int* __restrict__ cand, long long ncand, const double* __restrict__ Xt, int k, int n, int m,
+                                                         const unsigned long long* __restrict__ excl, long long nexcl, double* __restrict__ score) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ncand) return;
+  const int i1 = cand[4 * q], i2 = cand[4 * q + 1], j1 = cand[4 * q + 2], j2 = cand[4 * q + 3];
+  const unsigned long long key = shor_key(i1, i2, j1, j2);
+  long long lo = 0, hi = nexcl;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (excl[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  if (lo < nexcl && excl[lo] == key) { score[q] = -1.0; return; }
+  double sacc = 0.0;
+  for (int t = 0; t < k; ++t) {
+    const double* X = Xt + (size_t)t * n * m;
+    const double x11 = X[(size_t)j1 * n + i1], x22 = X[(size_t)j2 * n + i2], x12 = X[(size_t)j2 * n + i1], x21 = X[(size_t)j1 * n + i2];
+    sacc = __dadd_rn(sacc, fabs(__dsub_rn(__dmul_rn(x11, x22), __dmul_rn(x12, x21))));
+  }
+  score[q] = sacc;
+}
+
 }  // namespace omc

@@ -241,6 +241,22 @@ function relax_batch_shor(p::Problem, nodes; opts::RelaxOpts = default_opts())
     end
 end
 
+"""Drop-in for `generate_violated_Shor_minors(X, indices, pattern, Shor_constraints_indexes, n_minors)` (OMC.jl:2614-2640): same
+return value, a Vector of `(score, (i1, i2, j1, j2))` (1-based) in the reference's order.  `candidates` is the result of
+`shor_constraint_indexes(p, pattern)[1]`, which depends on the mask only: compute it once per run.  (UNTESTED in Julia.)"""
+function generate_violated_Shor_minors(p::Problem, X::Array{Float64, 3}, candidates::Vector{NTuple{4, Int}},
+                                       Shor_constraints_indexes::Vector{NTuple{4, Int}}, n_minors::Int)
+    Xs = permutedims(X, (2, 3, 1))                                          # (k, n, m) -> k column-major n x m slices
+    cand = Int32[t[q] - 1 for q in 1:4, t in candidates]
+    excl = Int32[t[q] - 1 for q in 1:4, t in Shor_constraints_indexes]
+    cap = max(1, min(n_minors, size(cand, 2)))
+    tuples = zeros(Int32, 4, cap); scores = zeros(cap); cnt = Ref{Int64}(0)
+    check(ccall((:omc_shor_score_minors, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Int32}, Int64, Ptr{Int32}, Int64, Ref{Int64}, Ptr{Int32}, Ptr{Float64}),
+                p.handle, Xs, size(cand, 2), cand, size(excl, 2), excl, n_minors, cnt, tuples, scores))
+    return [(scores[q], ntuple(e -> Int(tuples[e, q]) + 1, 4)) for q in 1:cnt[]]
+end
+
 # ---- multi-GPU exchange inside the library (INTEGRATION.md section 4): one Julia process per GPU -----------------------------
 """Rank 0 creates the 128-byte id; ship it to the other workers by any channel, then every rank calls `comm_init`."""
 function comm_unique_id()

@@ -64,3 +64,22 @@ def shor_brute_force(indices, p):
             if int(ind[i1, j1]) + int(ind[i1, j2]) + int(ind[i2, j1]) + int(ind[i2, j2]) == p:
                 s.add((i1 + 1, i2 + 1, j1 + 1, j2 + 1))
     return s
+
+
+def violated_minors(X, candidates, existing, n_minors):
+    """generate_violated_Shor_minors (OMC.jl:2614-2640) after the candidate list is built: X (k, n, m); candidates / existing are
+    0-based (i1, i2, j1, j2) tuples.  Score sum_t |X[t,i1,j1] X[t,i2,j2] - X[t,i1,j2] X[t,i2,j1]| (OMC.jl:2628-2629), candidates in
+    `existing` removed (setdiff!, OMC.jl:2625), the n_minors largest by (score, tuple), descending (OMC.jl:2634-2639)."""
+    X = np.asarray(X, float)
+    ex = {tuple(int(v) for v in t) for t in existing}
+    out = []
+    for t in candidates:
+        i1, i2, j1, j2 = (int(v) for v in t)
+        if (i1, i2, j1, j2) in ex:
+            continue
+        sc = 0.0
+        for s_ in range(X.shape[0]):
+            sc = sc + abs(X[s_, i1, j1] * X[s_, i2, j2] - X[s_, i1, j2] * X[s_, i2, j1])
+        out.append((sc, (i1, i2, j1, j2)))
+    out.sort(reverse=True)
+    return out[:n_minors]

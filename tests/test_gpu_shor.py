@@ -137,3 +137,36 @@ def test_shor_rows_on_the_config3_mask_properties(omc):
     am = omc.alternating_minimization(p, U0)
     ub = p.objective_mse(am["U"] @ am["V"])[0]
     assert plain["objective"] * (1 - 1e-4) <= r["objective"] <= ub * (1 + 1e-6), (plain["objective"], r["objective"], ub)
+
+
+def test_violated_shor_minors_match_the_reference_expression(omc):
+    """generate_violated_Shor_minors (OMC.jl:2614-2640) on the GPU vs the loop restatement: same tuples in the same order, scores
+    bit for bit (the kernel rounds the two products and their difference separately, like the reference's expression), at a
+    small shape and at the config-3 size (177 853 candidates)."""
+    from oracle import shor as SI
+    from oracle.datagen import generate_matrix_completion_data, config_instance
+    rng = np.random.default_rng(3)
+    for (k, n, m, nidx, seed, n_minors, n_ex) in ((2, 8, 9, 40, 1, 25, 40), (1, 6, 7, 22, 2, 1000, 0)):
+        A, mask = generate_matrix_completion_data(k, n, m, nidx, seed)
+        p = omc.Problem(k, A, mask, 20.0)
+        cand, _ = omc.shor_constraint_indexes(p, [1, 2, 3, 4])
+        Xt = rng.standard_normal((k, n, m))
+        ex = cand[rng.choice(len(cand), size=n_ex, replace=False)] if n_ex else np.zeros((0, 4), np.int32)
+        sc, tp = omc.generate_violated_Shor_minors(p, Xt, cand, ex, n_minors)
+        ref = SI.violated_minors(Xt, cand, ex, n_minors)
+        assert len(sc) == len(ref) == min(n_minors, len(cand) - n_ex)
+        assert [tuple(int(v) for v in t) for t in tp] == [t for _, t in ref]
+        assert np.array_equal(sc, np.array([s for s, _ in ref]))
+        p.close()
+    k, A, mask, g = config_instance("C3", 0)
+    p = omc.Problem(k, A, mask, g, "linear2")
+    cand, _ = omc.shor_constraint_indexes(p, [1, 2, 3, 4])
+    Xt = rng.standard_normal((k, 30, 30))
+    ex = cand[rng.choice(len(cand), size=1000, replace=False)]
+    sc, tp = omc.generate_violated_Shor_minors(p, Xt, cand, ex, 100)
+    d = np.abs(Xt[:, cand[:, 0], cand[:, 2]] * Xt[:, cand[:, 1], cand[:, 3]] - Xt[:, cand[:, 0], cand[:, 3]] * Xt[:, cand[:, 1], cand[:, 2]])
+    score = d[0] + d[1] if k == 2 else d.sum(axis=0)
+    exs = {tuple(t) for t in ex.tolist()}
+    keep = np.array([tuple(t) not in exs for t in cand.tolist()])
+    order = sorted(np.flatnonzero(keep).tolist(), key=lambda q: (score[q], tuple(cand[q].tolist())), reverse=True)[:100]
+    assert np.array_equal(tp, cand[order]) and np.array_equal(sc, score[order])

@@ -71,3 +71,21 @@ def test_shor_bound_between_plain_bound_and_rank_k_optimum():
         B = SR._blocks5(S, r1["Xt"], r1["Wd"], r1["V1"], r1["V2"], r1["V3"])
         assert np.linalg.eigvalsh(B).min() >= -1e-5
         assert np.abs(np.diag(r1["Theta"]) - r1["W"].sum(axis=0)).max() <= 1e-5 and r1["Wd"].min() >= -1e-6
+
+
+def test_violated_minors_restatement():
+    """Brute-force check of oracle/shor.py:violated_minors on a tiny case: a rank-1 slice scores 0 on every minor, a perturbed
+    entry raises exactly the minors through it, existing minors are skipped, order is (score, tuple) descending."""
+    rng = np.random.default_rng(0)
+    u, v = rng.standard_normal(4), rng.standard_normal(5)
+    X = np.outer(u, v)[None]
+    cands = [(i1, i2, j1, j2) for i1 in range(4) for i2 in range(i1 + 1, 4) for j1 in range(5) for j2 in range(j1 + 1, 5)]
+    top = SI.violated_minors(X, cands, [], 10)
+    assert max(s for s, _ in top) <= 1e-14
+    X2 = X.copy(); X2[0, 1, 2] += 0.5
+    top = SI.violated_minors(X2, cands, [], len(cands))
+    assert all((1 in (t[0], t[1]) and 2 in (t[2], t[3])) == (s > 1e-12) for s, t in top)
+    assert [s for s, _ in top] == sorted((s for s, _ in top), reverse=True)
+    skip = [t for _, t in top[:3]]
+    top2 = SI.violated_minors(X2, cands, skip, 5)
+    assert [t for _, t in top2] == [t for _, t in top[3:8]]
