@@ -141,10 +141,10 @@ int32_t omc_frontier_fetch_profile(omc_frontier* f, double* prof);
 /* generate_violated_Shor_minors (OMC.jl:2614-2640; call site 2495-2502): scores every candidate minor of `cand` (n_cand x 4, 0-based,
  * e.g. the list omc_shor_indexes returns -- it depends on the mask only, so the glue computes it once per run) that is not in
  * `excl` (the node's Shor_info.constraints_indexes) by sum_t |Xt[i1,j1] Xt[i2,j2] - Xt[i1,j2] Xt[i2,j1]| on the GPU and returns
- * the n_minors largest, ordered by (score, tuple) descending like the reference's sort(...; rev = true).  Xt: k column-major
- * n x m slices (omc_frontier_fetch_shor's layout).  *count <= n_minors entries are written to tuples[4*q..] / scores[q].   */
-int32_t omc_shor_score_minors(omc_problem* p, const double* Xt, int64_t n_cand, const int32_t* cand, int64_t n_excl, const int32_t* excl,
-                              int64_t n_minors, int64_t* count, int32_t* tuples, double* scores);
+ * the n_minors largest, ordered by (score, tuple) descending like the reference's sort(...; rev = true).  Xt: n_slices
+ * column-major n x m slices (omc_frontier_fetch_shor's layout; the reference's call site passes X itself as ONE slice).  *count <= n_minors entries are written to tuples[4*q..] / scores[q].   */
+int32_t omc_shor_score_minors(omc_problem* p, const double* Xt, int32_t n_slices, int64_t n_cand, const int32_t* cand, int64_t n_excl,
+                              const int32_t* excl, int64_t n_minors, int64_t* count, int32_t* tuples, double* scores);
 /* Shor valid inequalities (OMC.jl:1503-1552 variables, 1755-1828 rows, 1838-1846 objective; chosen by
  * generate_rank1_basis_pursuit_Shor_constraints_indexes, OMC.jl:568-668): attaches the rows to every node relaxation of the
  * problem.  minors[4*q..] = (i1, i2, j1, j2), 0-based, i1 < i2, j1 < j2 (the reference's 4-tuples minus one);

@@ -48,7 +48,7 @@ SIGNATURES = {
     "omc_frontier_create": (_i32, [_vp, _i32, _pi32, _pi32, _pu8, _pi32, _pi32, _p(_vp)]),
     "omc_frontier_create_ex": (_i32, [_vp, _i32, _pi32, _pi32, _pu8, _pi32, _pi32, _i32, _p(_vp)]),
     "omc_frontier_stats": (_i32, [_vp, _p(C.c_int64)]),
-    "omc_shor_score_minors": (_i32, [_vp, _pf64, _i64, _pi32, _i64, _pi32, _i64, _p(C.c_int64), _pi32, _pf64]),
+    "omc_shor_score_minors": (_i32, [_vp, _pf64, _i32, _i64, _pi32, _i64, _pi32, _i64, _p(C.c_int64), _pi32, _pf64]),
     "omc_profile_kernels": (_i32, [_vp, _i32, _pf32]),
     "omc_problem_set_shor": (_i32, [_vp, _i64, _pi32, _i64, _pi32]),
     "omc_frontier_fetch_shor": (_i32, [_vp, _pf64, _pf64]),

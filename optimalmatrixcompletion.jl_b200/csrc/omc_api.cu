@@ -852,15 +852,15 @@ int32_t omc_objective_mse(omc_problem* p, const double* X, double* out4) {
   return OMC_OK;
 }
 
-int32_t omc_shor_score_minors(omc_problem* p, const double* Xt, int64_t n_cand, const int32_t* cand, int64_t n_excl, const int32_t* excl,
-                              int64_t n_minors, int64_t* count, int32_t* tuples, double* scores) {
+int32_t omc_shor_score_minors(omc_problem* p, const double* Xt, int32_t n_slices, int64_t n_cand, const int32_t* cand, int64_t n_excl,
+                              const int32_t* excl, int64_t n_minors, int64_t* count, int32_t* tuples, double* scores) {
   NEED_INIT();
-  if (!p || !Xt || n_cand < 0 || n_excl < 0 || n_minors < 0 || !count || (n_cand > 0 && !cand) || (n_excl > 0 && !excl))
+  if (!p || !Xt || n_slices <= 0 || n_cand < 0 || n_excl < 0 || n_minors < 0 || !count || (n_cand > 0 && !cand) || (n_excl > 0 && !excl))
     return fail(OMC_ERR_ARG, "bad argument");
   if (p->n > 65535 || p->m > 65535) return fail(OMC_ERR_UNSUPPORTED, "n, m <= 65535 (16-bit minor keys)");
   *count = 0;
   if (n_cand == 0 || n_minors == 0) return OMC_OK;
-  const int n = p->n, m = p->m, k = p->k;
+  const int n = p->n, m = p->m, k = n_slices;
   for (int64_t q = 0; q < n_cand; ++q) {
     const int32_t* c = cand + 4 * q;
     if (c[0] < 0 || c[0] >= c[1] || c[1] >= n || c[2] < 0 || c[2] >= c[3] || c[3] >= m) return fail(OMC_ERR_ARG, "candidate minor %lld out of range", (long long)q);

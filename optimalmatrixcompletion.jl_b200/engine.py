@@ -399,18 +399,19 @@ def shor_constraint_indexes(problem: Problem, num_entries_present_list, with_soc
 
 
 def generate_violated_Shor_minors(problem: Problem, Xt: np.ndarray, candidates: np.ndarray, existing, n_minors: int):
-    """generate_violated_Shor_minors (OMC.jl:2614-2640) on the GPU.  Xt (k, n, m); candidates (N, 4) and existing (M, 4) 0-based
+    """generate_violated_Shor_minors (OMC.jl:2614-2640) on the GPU.  Xt (slices, n, m) -- the reference's call site (OMC.jl:2496-2502)
+    passes reshape(X, (1, n, m)); candidates (N, 4) and existing (M, 4) 0-based
     minors (candidates = shor_constraint_indexes(problem, pattern)[0], computed once per run).  Returns (scores, tuples) of the
     n_minors most violated candidates that are not in `existing`, in the reference's order."""
     Xt = np.asarray(Xt, np.float64)
-    assert Xt.shape == (problem.k, problem.n, problem.m), Xt.shape
+    assert Xt.ndim == 3 and Xt.shape[1:] == (problem.n, problem.m), Xt.shape
     Xs = np.ascontiguousarray(Xt.transpose(0, 2, 1))              # k column-major n x m slices
     cand = np.ascontiguousarray(np.asarray(candidates, np.int32).reshape(-1, 4))
     ex = np.ascontiguousarray(np.asarray(existing, np.int32).reshape(-1, 4))
     cnt = C.c_int64(0)
     cap = max(1, min(int(n_minors), len(cand)))
     tuples = np.zeros((cap, 4), np.int32); scores = np.zeros(cap)
-    check(problem.lib.omc_shor_score_minors(problem.handle, _ptr(Xs, C.c_double), len(cand), _ptr(cand, C.c_int32) if len(cand) else None,
+    check(problem.lib.omc_shor_score_minors(problem.handle, _ptr(Xs, C.c_double), int(Xt.shape[0]), len(cand), _ptr(cand, C.c_int32) if len(cand) else None,
                                             len(ex), _ptr(ex, C.c_int32) if len(ex) else None, int(n_minors), C.byref(cnt),
                                             _ptr(tuples, C.c_int32), _ptr(scores, C.c_double)))
     return scores[: cnt.value], tuples[: cnt.value]

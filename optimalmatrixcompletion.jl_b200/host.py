@@ -25,6 +25,14 @@ class BBNode:
     master_feasible: bool = False
     disjunctive_cuts: List[Cut] = field(default_factory=list)
     warm_id: int = -1          # engine extension: state-pool record of the parent's ADMM state
+    Shor_info: Optional[object] = None   # BBNodeShorInfo (OMC.jl:37-40): shared object of (constraints_indexes, SOC_constraints_indexes), 0-based
+
+
+@dataclass
+class BBNodeShorInfo:
+    """OMC.jl:37-40, 0-based: constraints_indexes (N, 4) int32 minors, SOC_constraints_indexes (M, 2) int32 coordinates."""
+    constraints_indexes: np.ndarray
+    SOC_constraints_indexes: np.ndarray
 
 
 def child_directions(cut_type: str, k: int):
@@ -280,16 +288,24 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
     if not use_disjunctive_cuts:
         raise NotImplementedError("use_disjunctive_cuts = false (McCormick path) is out of scope (SURVEY.md section 2)")
     if add_Shor_valid_inequalities:
+        if warm_start:
+            raise ValueError("warm_start needs the persistent engine; Shor rows run on the batched engine, which starts every node cold")
         if not 0.0 <= add_Shor_valid_inequalities_fraction <= 1.0:                                            # OMC.jl:256-263
             raise ValueError(f"Argument `add_Shor_valid_inequalities_fraction` = {add_Shor_valid_inequalities_fraction} out of bounds [0.0, 1.0].")
-        if add_Shor_valid_inequalities_iterative:
-            # OMC.jl:670-676, 956-982, 2495-2540: the minors grow from parent to child, i.e. every node has its own row structure;
-            # the engine shares one structure per problem (omc_problem_set_shor)
-            raise NotImplementedError("add_Shor_valid_inequalities_iterative = true is out of scope (DESIGN.md section 8)")
     else:
         add_Shor_valid_inequalities_fraction = None                                                           # OMC.jl:264-266
-    max_update_Shor_indices_probability = min_update_Shor_indices_probability = None                         # OMC.jl:325-330
-    update_Shor_indices_probability_decay_rate = update_Shor_indices_n_minors = None
+    if add_Shor_valid_inequalities and add_Shor_valid_inequalities_iterative:                                 # OMC.jl:296-324
+        if not 0.0 <= max_update_Shor_indices_probability <= 1.0:
+            raise ValueError(f"Argument `max_update_Shor_indices_probability` = {max_update_Shor_indices_probability} out of bounds [0.0, 1.0].")
+        if not 0.0 < min_update_Shor_indices_probability < 1.0:
+            raise ValueError(f"Argument `min_update_Shor_indices_probability` = {min_update_Shor_indices_probability} out of bounds (0.0, 1.0).")
+        if not 1.0 < update_Shor_indices_probability_decay_rate:
+            raise ValueError(f"Argument `update_Shor_indices_probability_decay_rate` = {update_Shor_indices_probability_decay_rate} out of bounds (1.0, ∞).")
+        if not 1.0 <= update_Shor_indices_n_minors:
+            raise ValueError(f"Argument `update_Shor_indices_n_minors` = {update_Shor_indices_n_minors} out of bounds [1.0, ∞).")
+    else:
+        max_update_Shor_indices_probability = min_update_Shor_indices_probability = None                     # OMC.jl:325-330
+        update_Shor_indices_probability_decay_rate = update_Shor_indices_n_minors = None
     if disjunctive_cuts_type not in ("linear", "linear2", "linear3"):
         raise ValueError('Invalid input for disjunctive cuts type.\nDisjunctive cuts type must be either "linear" or '
                          f'"linear2" or "linear3";\n{disjunctive_cuts_type} supplied instead.')         # OMC.jl:218-224
@@ -326,15 +342,22 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
     if add_Shor_valid_inequalities:
         # OMC.jl:646-669: all 2 x 2 minors with the listed numbers of observed entries, a random fraction of them, and an RSOC row
         # on every coordinate no kept minor covers
-        from .engine import shor_constraint_indexes as _shor_idx
+        from .engine import shor_constraint_indexes as _shor_idx, generate_violated_Shor_minors as _violated
         minors, soc = _shor_idx(problem, list(Shor_valid_inequalities_noisy_rank1_num_entries_present), with_soc=True)
-        if add_Shor_valid_inequalities_fraction < 1.0:
+        shor_candidates = minors                     # all minors of the pattern: depends on the mask only (OMC.jl:2621-2624)
+        if add_Shor_valid_inequalities_iterative:
+            # OMC.jl:670-675: no minors at the root, an RSOC row on every coordinate (column-major order of Iterators.product)
+            minors = np.zeros((0, 4), np.int32)
+            soc = np.array([(i, j) for j in range(m) for i in range(n)], np.int32)
+        elif add_Shor_valid_inequalities_fraction < 1.0:
             minors = minors[rng.random(len(minors)) < add_Shor_valid_inequalities_fraction]                   # randsubseq
             cov = np.zeros((n, m), bool)
             cov[minors[:, 0], minors[:, 2]] = cov[minors[:, 0], minors[:, 3]] = True
             cov[minors[:, 1], minors[:, 2]] = cov[minors[:, 1], minors[:, 3]] = True
             soc = np.argwhere(~cov).astype(np.int32)
+        root_shor = BBNodeShorInfo(minors, soc)
         problem.set_shor(minors, soc)
+        shor_loaded = [root_shor]                    # the structure currently attached to the problem
         instance_shor = dict(constraints_indexes=minors, SOC_constraints_indexes=soc)
     solve_time_altmin = solve_time_relaxation = 0.0
     dict_solve_times_altmin, dict_num_iterations_altmin, dict_solve_times_relaxation = [], [], []
@@ -367,7 +390,7 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
                 "Y": U_initial @ U_initial.T, "U": U_initial, "X": X_initial}
     objective_initial = o4[0]
 
-    root = BBNode(node_id=1, parent_id=0, LB=-np.inf, depth=0)
+    root = BBNode(node_id=1, parent_id=0, LB=-np.inf, depth=0, Shor_info=root_shor if add_Shor_valid_inequalities else None)
     tree = BBTree(nodes={1: root}, node_ids=[1], counter=1, last_updated_counter=1, nodes_explored=0, nodes_remaining=1,
                   best_upper_bound=objective_initial, best_lower_bound=-np.inf, now_gap=np.inf,
                   lower_bounds=JuliaPriorityQueue([(1, np.inf)]))
@@ -419,8 +442,23 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
             if warm_start:
                 save = [free_states.pop() if free_states else -1 for _ in live]
                 pool_exhausted += sum(1 for sid in save if sid < 0)
-            res = problem.relax_batch([nd.disjunctive_cuts for nd in live], opts,
-                                      warm_ids=[nd.warm_id for nd in live] if warm_start else None, save_ids=save)
+            if add_Shor_valid_inequalities and add_Shor_valid_inequalities_iterative:
+                # the engine holds ONE Shor row structure per problem: nodes are relaxed in groups that share their BBNodeShorInfo
+                # (all children of a split do, OMC.jl:2532-2539), the structure is swapped between groups (omc_problem_set_shor)
+                res = [None] * len(live)
+                groups = {}
+                for q, nd in enumerate(live):
+                    groups.setdefault(id(nd.Shor_info), []).append(q)
+                for qs in groups.values():
+                    info = live[qs[0]].Shor_info
+                    if shor_loaded[0] is not info:
+                        problem.set_shor(info.constraints_indexes, info.SOC_constraints_indexes)
+                        shor_loaded[0] = info
+                    for q, r in zip(qs, problem.relax_batch([live[q].disjunctive_cuts for q in qs], opts)):
+                        res[q] = r
+            else:
+                res = problem.relax_batch([nd.disjunctive_cuts for nd in live], opts,
+                                          warm_ids=[nd.warm_id for nd in live] if warm_start else None, save_ids=save)
             for q, (nd, r) in enumerate(zip(live, res)):
                 r["save_id"] = save[q] if save else -1
                 results[nd.node_id] = r
@@ -514,6 +552,26 @@ def matrix_completion_branchandbound(k: int, A: np.ndarray, indices: np.ndarray,
                                                      tree.counter, objective_relax, warm_id=sid)
                 if sid >= 0:
                     state_refs[sid] = len(kids)
+                if add_Shor_valid_inequalities:
+                    info = current_node.Shor_info
+                    if add_Shor_valid_inequalities_iterative:
+                        # OMC.jl:956-969: the deeper the node, the rarer the update; OMC.jl:2495-2518: the n_minors most violated
+                        # minors of X join the node's list, their coordinates leave the RSOC list; all children share the result
+                        lim = np.log(max_update_Shor_indices_probability / min_update_Shor_indices_probability) / np.log(update_Shor_indices_probability_decay_rate)
+                        prob = (min_update_Shor_indices_probability if current_node.depth > lim
+                                else max_update_Shor_indices_probability / update_Shor_indices_probability_decay_rate ** current_node.depth)
+                        if rng.random() < prob:
+                            _, new_minors = _violated(problem, relax_result["X"][None], shor_candidates, info.constraints_indexes,
+                                                      int(update_Shor_indices_n_minors))
+                            allm = np.concatenate([info.constraints_indexes, new_minors]).astype(np.int32)      # union: new ones are not in the old list
+                            cov = np.zeros((n, m), bool)
+                            cov[allm[:, 0], allm[:, 2]] = cov[allm[:, 0], allm[:, 3]] = True
+                            cov[allm[:, 1], allm[:, 2]] = cov[allm[:, 1], allm[:, 3]] = True
+                            old_soc = info.SOC_constraints_indexes
+                            info = BBNodeShorInfo(allm, old_soc[~cov[old_soc[:, 0], old_soc[:, 1]]])                 # setdiff keeps the order
+                            cnt["Shor_indices_updates"] = cnt.get("Shor_indices_updates", 0) + 1
+                    for kd in kids:
+                        kd.Shor_info = info
                 add_nodes_to_tree(tree, kids, objective_relax)
             elif warm_start and relax_result is not None and relax_result.get("save_id", -1) >= 0:
                 free_states.append(relax_result["save_id"])

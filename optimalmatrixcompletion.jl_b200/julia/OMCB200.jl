@@ -252,8 +252,8 @@ function generate_violated_Shor_minors(p::Problem, X::Array{Float64, 3}, candida
     cap = max(1, min(n_minors, size(cand, 2)))
     tuples = zeros(Int32, 4, cap); scores = zeros(cap); cnt = Ref{Int64}(0)
     check(ccall((:omc_shor_score_minors, LIB), Int32,
-                (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Int32}, Int64, Ptr{Int32}, Int64, Ref{Int64}, Ptr{Int32}, Ptr{Float64}),
-                p.handle, Xs, size(cand, 2), cand, size(excl, 2), excl, n_minors, cnt, tuples, scores))
+                (Ptr{Cvoid}, Ptr{Float64}, Int32, Int64, Ptr{Int32}, Int64, Ptr{Int32}, Int64, Ref{Int64}, Ptr{Int32}, Ptr{Float64}),
+                p.handle, Xs, size(X, 1), size(cand, 2), cand, size(excl, 2), excl, n_minors, cnt, tuples, scores))
     return [(scores[q], ntuple(e -> Int(tuples[e, q]) + 1, 4)) for q in 1:cnt[]]
 end
 

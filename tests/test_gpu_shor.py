@@ -170,3 +170,34 @@ def test_violated_shor_minors_match_the_reference_expression(omc):
     keep = np.array([tuple(t) not in exs for t in cand.tolist()])
     order = sorted(np.flatnonzero(keep).tolist(), key=lambda q: (score[q], tuple(cand[q].tolist())), reverse=True)[:100]
     assert np.array_equal(tp, cand[order]) and np.array_equal(sc, score[order])
+
+
+def test_branchandbound_with_iterative_shor_rows(omc):
+    """add_Shor_valid_inequalities_iterative = true (OMC.jl:670-675, 956-982, 2495-2540): the root carries no minors and an RSOC
+    row on every coordinate; splits add the most violated minors to the children's shared list (generate_violated_Shor_minors on
+    the GPU); nodes are relaxed in groups that share a row structure.  A short run: bounds stay ordered, the lists stay
+    consistent (no duplicate minor, RSOC coordinates = the uncovered ones), the incumbent is the one the plain run finds."""
+    from oracle.datagen import generate_matrix_completion_data
+    k, n, m = 1, 8, 9
+    A, mask = generate_matrix_completion_data(k, n, m, 30, 2)
+    kw = dict(node_selection="bestfirst", disjunctive_cuts_type="linear", disjunctive_cuts_breakpoints="smallest_1_eigvec",
+              gap=1e-4, max_steps=14, use_max_steps=True, time_limit=120, frontier_batch=4,
+              relax_opts=omc.default_opts(eps_abs=1e-6, eps_rel=1e-6, max_iter=20000))
+    s0, _, i0 = omc.matrix_completion_branchandbound(k, A, mask, 20.0, **kw)
+    s1, _, i1 = omc.matrix_completion_branchandbound(k, A, mask, 20.0, add_Shor_valid_inequalities=True,
+                                                     add_Shor_valid_inequalities_iterative=True, update_Shor_indices_n_minors=20, **kw)
+    assert abs(s1["objective"] - s0["objective"]) <= 1e-3 * abs(s0["objective"])
+    assert i1["tree"].best_lower_bound <= i1["tree"].best_upper_bound * (1 + 1e-6)
+    assert i1["tree"].best_lower_bound >= i0["run_log"][0][3] * (1 - 1e-4)        # at least the plain root bound
+    assert len(i1["Shor_info"]["constraints_indexes"]) == 0 and len(i1["Shor_info"]["SOC_constraints_indexes"]) == n * m
+    assert i1["run_details"]["add_Shor_valid_inequalities_iterative"] is True
+    assert i1["run_details"]["nodes_relax_feasible_split"] >= 1 and i1["run_details"].get("Shor_indices_updates", 0) >= 1
+    open_infos = {id(nd.Shor_info): nd.Shor_info for nd in i1["open_nodes"]}
+    assert len(open_infos) >= 1
+    for info in open_infos.values():
+        mn, sc = info.constraints_indexes, info.SOC_constraints_indexes
+        cov = np.zeros((n, m), bool)
+        for (a1, a2, b1, b2) in mn:
+            cov[a1, b1] = cov[a1, b2] = cov[a2, b1] = cov[a2, b2] = True
+        assert len(mn) % 20 == 0 and len(np.unique(mn, axis=0)) == len(mn)
+        assert not cov[sc[:, 0], sc[:, 1]].any() and cov.sum() + len(sc) == n * m
