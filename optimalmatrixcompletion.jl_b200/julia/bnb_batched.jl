@@ -29,8 +29,28 @@ function bnb_batched_loop!(tree, solution, printlist, instance, counters, proble
                            node_selection, bestfirst_depthfirst_cutoff, gap, disjunctive_cuts_type, disjunctive_cuts_breakpoints,
                            altmin_flag, max_altmin_probability, min_altmin_probability, altmin_probability_decay_rate,
                            use_max_steps, max_steps, time_limit, update_step, verbosity, start_time, root_only,
-                           frontier_batch::Int = 1, use_cutoff::Bool = true, relax_opts = OMCB200.default_opts())
+                           frontier_batch::Int = 1, use_cutoff::Bool = true, relax_opts = OMCB200.default_opts(),
+                           # Shor valid inequalities (the reference's own keyword arguments, OMC.jl:152-159); `rng` as in the caller
+                           add_Shor_valid_inequalities::Bool = false, add_Shor_valid_inequalities_iterative::Bool = false,
+                           Shor_valid_inequalities_noisy_rank1_num_entries_present::Vector{Int} = [1, 2, 3, 4],
+                           max_update_Shor_indices_probability = 1.0, min_update_Shor_indices_probability = 0.1,
+                           update_Shor_indices_probability_decay_rate = 1.1, update_Shor_indices_n_minors::Int = 100)
     nev = disjunctive_cuts_breakpoints == "smallest_1_eigvec" ? 1 : 2
+    # Shor rows: the engine keeps ONE row structure per problem (OMCB200.set_shor!).  Non-iterative mode: the root's BBNodeShorInfo,
+    # attached once.  Iterative mode: nodes are relaxed in groups that share their Shor_info object (all children of a split do,
+    # OMC.jl:2532-2539) and the structure is swapped between groups.                                                    host.py: "relax grouping"
+    shor_loaded = nothing
+    shor_candidates = NTuple{4, Int}[]
+    if add_Shor_valid_inequalities
+        if add_Shor_valid_inequalities_iterative     # the candidate list depends on the mask only: once per run (OMC.jl:2621-2624)
+            shor_candidates = OMCB200.shor_constraint_indexes(problem, Shor_valid_inequalities_noisy_rank1_num_entries_present)[1]
+        end
+        root_info = tree.nodes[first(keys(tree.nodes))].Shor_info       # built by the caller exactly as OMC.jl:646-676
+        OMCB200.set_shor!(problem, root_info.constraints_indexes, root_info.SOC_constraints_indexes)
+        shor_loaded = root_info
+    end
+    relax_group(nds) = add_Shor_valid_inequalities ? OMCB200.relax_batch_shor(problem, nds; opts = relax_opts) :
+                                                     OMCB200.relax_batch(problem, nds; opts = relax_opts)
     while (tree.now_gap > gap && !(use_max_steps && (tree.counter ≥ max_steps)) && time() - start_time ≤ time_limit)   # host.py:357
         length(tree.nodes) == 0 && break                                                                              # host.py:359
         # ---- pop up to frontier_batch nodes (OMC.jl:709-719)                                                          host.py:363-369
@@ -47,9 +67,26 @@ function bnb_batched_loop!(tree, solution, printlist, instance, counters, proble
         if !isempty(live)                                                                                              # host.py:372-382
             relax_opts.cutoff = use_cutoff ? tree.best_upper_bound : Inf
             relax_opts.time_limit_s = max(1.0, time_limit - (time() - start_time))
-            res = OMCB200.relax_batch(problem, live; opts = relax_opts)     # ONE engine call: B x matrix_completion_SDP_relaxation
-            for (nd, r) in zip(live, res)
-                results[nd.node_id] = r
+            if add_Shor_valid_inequalities && add_Shor_valid_inequalities_iterative
+                groups = Dict{UInt, Vector{Int}}()                         # nodes that share one Shor_info object
+                for (q, nd) in enumerate(live)
+                    push!(get!(groups, objectid(nd.Shor_info), Int[]), q)
+                end
+                for qs in values(groups)
+                    info = live[qs[1]].Shor_info
+                    if shor_loaded !== info
+                        OMCB200.set_shor!(problem, info.constraints_indexes, info.SOC_constraints_indexes)
+                        shor_loaded = info
+                    end
+                    for (q, r) in zip(qs, relax_group(live[qs]))
+                        results[live[q].node_id] = r
+                    end
+                end
+            else
+                res = relax_group(live)                                     # ONE engine call: B x matrix_completion_SDP_relaxation
+                for (nd, r) in zip(live, res)
+                    results[nd.node_id] = r
+                end
             end
         end
         # separation oracle for the whole batch in one launch (OMC.jl:814, 2466-2477)                                   host.py:391-397
@@ -157,6 +194,26 @@ function bnb_batched_loop!(tree, solution, printlist, instance, counters, proble
                 children = create_matrix_cut_child_nodes_with_breakpoint(
                     current_node, disjunctive_cuts_type, eig[current_node.node_id][1], relax_result["U"],
                     tree.counter, objective_relax)
+                if add_Shor_valid_inequalities
+                    info = current_node.Shor_info
+                    if add_Shor_valid_inequalities_iterative                                                           # OMC.jl:956-969
+                        lim = log(update_Shor_indices_probability_decay_rate, max_update_Shor_indices_probability / min_update_Shor_indices_probability)
+                        update_probability = current_node.depth > lim ? min_update_Shor_indices_probability :
+                                             max_update_Shor_indices_probability / (update_Shor_indices_probability_decay_rate ^ current_node.depth)
+                        if rand() < update_probability                                                                 # OMC.jl:2495-2518
+                            n, m = size(A)
+                            minors = OMCB200.generate_violated_Shor_minors(problem, reshape(relax_result["X"], (1, n, m)), shor_candidates,
+                                                                           info.constraints_indexes, update_Shor_indices_n_minors)
+                            Shor_constraints_indexes = union(info.constraints_indexes, [mn[2] for mn in minors])
+                            covered = unique(vcat([[(i1, j1), (i1, j2), (i2, j1), (i2, j2)] for (i1, i2, j1, j2) in Shor_constraints_indexes]...))
+                            info = BBNodeShorInfo(constraints_indexes = Shor_constraints_indexes,
+                                                  SOC_constraints_indexes = setdiff(info.SOC_constraints_indexes, covered))
+                        end
+                    end
+                    for child in children
+                        child.Shor_info = info
+                    end
+                end
                 add_nodes_to_tree!(tree, children, objective_relax, current_node.node_id)
             end
             prune_dominated_nodes!(tree)                                                                               # OMC.jl:1036
