@@ -872,10 +872,9 @@ __global__ void __launch_bounds__(128) k_prod(BigArgs a, int which) {
 //          pass 2: C = sum partA; R -= Z C; partB = R_tile' R_tile.         enough", see oracle/bigblock.py)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
-  constexpr int RLD = PM + 4;          // 36: conflict-free FP64 DMMA fragment loads
-  __shared__ double Hs[PM * RLD];
-  __shared__ double Zs[TS * RLD];
-  __shared__ double Rs[TS * RLD];
+  __shared__ double Hs[PM * ZLD];
+  __shared__ double Zs[TS * ZLD];
+  __shared__ double Rs[TS * ZLD];
   __shared__ double red[32];
   const Layout& L = a.L;
   const int b = blockIdx.z;
@@ -896,7 +895,7 @@ __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
       const double* part = S + ((pass & 1) ? L.partB[b] : L.partA[b]);
       for (int t = 0; t < L.nt[b]; ++t) s += part[(size_t)t * PM * PM + e];
     }
-    Hs[ai * RLD + bi] = s;
+    Hs[ai * ZLD + bi] = s;
     h2 += s * s;
     if (pass == 0 && blockIdx.x == 0) S[L.H[b] + e] = s;
   }
@@ -904,8 +903,8 @@ __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
   for (int e = tid; e < TS * PM; e += 256) {
     const int row = e / PM, col = e % PM;
     const bool ok = r0 + row < N;
-    Zs[row * RLD + col] = ok ? S[L.Z[b] + (size_t)(r0 + row) * PM + col] : 0.0;
-    Rs[row * RLD + col] = ok ? src[(size_t)(r0 + row) * PM + col] : 0.0;
+    Zs[row * ZLD + col] = ok ? S[L.Z[b] + (size_t)(r0 + row) * PM + col] : 0.0;
+    Rs[row * ZLD + col] = ok ? src[(size_t)(r0 + row) * PM + col] : 0.0;
   }
   __syncthreads();
   // pass 0: the last panel column carries a fresh pseudo-random probe instead of its residual, so that the trial space
@@ -916,29 +915,25 @@ __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
     h2 = block_sum(h2, red);
     amp = 1e-3 * sqrt(h2 / (double)N);
   }
-  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
   {
-    // R tile (64 x 32) = Rs - Zs Hs on the FP64 tensor pipe: warp w owns rows 8 w .. 8 w + 7; lane (g, t4) holds, per 8-column
-    // tile nt, the entries (row 8 w + g, columns 8 nt + 2 t4, + 1)
-    const int row = warp * 8 + g;
-    double acc[PM / 8][2];
+    constexpr int CPT = TS * PM / 256;      // outputs per thread (8): one row, CPT consecutive columns
+    const int row = tid / (PM / CPT), cb = (tid % (PM / CPT)) * CPT;
+    double acc[CPT];
 #pragma unroll
-    for (int nt = 0; nt < PM / 8; ++nt) { acc[nt][0] = Rs[row * RLD + nt * 8 + 2 * t4]; acc[nt][1] = Rs[row * RLD + nt * 8 + 2 * t4 + 1]; }
+    for (int q = 0; q < CPT; ++q) acc[q] = Rs[row * ZLD + cb + q];
+#pragma unroll 4
+    for (int c = 0; c < PM; ++c) {
+      const double z = Zs[row * ZLD + c];
 #pragma unroll
-    for (int kk = 0; kk < PM / 4; ++kk) {
-      const double az = -Zs[row * RLD + kk * 4 + t4];
-#pragma unroll
-      for (int nt = 0; nt < PM / 8; ++nt) dmma884(acc[nt][0], acc[nt][1], az, Hs[(kk * 4 + t4) * RLD + nt * 8 + g], acc[nt][0], acc[nt][1]);
+      for (int q = 0; q < CPT; ++q) acc[q] = fma(-z, Hs[c * ZLD + cb + q], acc[q]);
     }
     if (pass == 0) {
       const int pc = L.p[b] - 1;
       if (pc > 0) {
 #pragma unroll
-        for (int nt = 0; nt < PM / 8; ++nt)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (nt * 8 + 2 * t4 + h == pc)
-              acc[nt][h] = amp * hash_unit((unsigned long long)(r0 + row), (unsigned long long)(a.it * 64 + a.step * 4 + b), 12345ull);
+        for (int q = 0; q < CPT; ++q)
+          if (cb + q == pc)
+            acc[q] = amp * hash_unit((unsigned long long)(r0 + row), (unsigned long long)(a.it * 64 + a.step * 4 + b), 12345ull);
       }
       // residual window: only the residuals of the positive Ritz pairs and of the first `window` guard columns (and the
       // probe) enter the trial space; the Rayleigh-Ritz still runs over ALL of Z, so no Ritz value ever gets worse.  The
@@ -948,41 +943,31 @@ __global__ void __launch_bounds__(256) k_resid(BigArgs a, int pass) {
         for (int c = 0; c < L.p[b]; ++c) rprev += (S[L.th[b] + c] > 0.0) ? 1 : 0;
         const int na = rprev + a.o.window;
 #pragma unroll
-        for (int nt = 0; nt < PM / 8; ++nt)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int col = nt * 8 + 2 * t4 + h;
-            if (col >= na && col != pc) acc[nt][h] = 0.0;
-          }
+        for (int q = 0; q < CPT; ++q)
+          if (cb + q >= na && cb + q != pc) acc[q] = 0.0;
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int nt = 0; nt < PM / 8; ++nt) {
-      const int col = nt * 8 + 2 * t4;
-      Rs[row * RLD + col] = acc[nt][0]; Rs[row * RLD + col + 1] = acc[nt][1];
-      if (r0 + row < N) *reinterpret_cast<double2*>(S + L.R[b] + (size_t)(r0 + row) * PM + col) = make_double2(acc[nt][0], acc[nt][1]);
+    for (int q = 0; q < CPT; ++q) {
+      Rs[row * ZLD + cb + q] = acc[q];
+      if (r0 + row < N) S[L.R[b] + (size_t)(r0 + row) * PM + cb + q] = acc[q];
     }
   }
   __syncthreads();
   {
-    // partial Gram matrix of this row tile, Lm' Rs (32 x 32, K = 64 rows), on the FP64 tensor pipe: warp w owns the 8-row tile
-    // w >> 1 and the two 8-column tiles 2 (w & 1), 2 (w & 1) + 1.  (Lm = Rs gives a bitwise symmetric result: entry (i, j) and
-    // entry (j, i) accumulate the same products in the same order.)
     const double* Lm = (pass == 2) ? Rs : Zs;
     double* part = S + ((pass & 1) ? L.partA[b] : L.partB[b]) + (size_t)blockIdx.x * PM * PM;
+    // 2 x 2 outputs per thread (16 x 16 threads cover PM x PM = 32 x 32): one shared-memory load per FMA instead of two
     static_assert(PM == 32, "Gram tiling assumes PM = 32");
-    const int mt = warp >> 1, nb = (warp & 1) * 2;
-    double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
-#pragma unroll
-    for (int kk = 0; kk < TS / 4; ++kk) {
-      const double af = Lm[(kk * 4 + t4) * RLD + mt * 8 + g];
-      dmma884(c0[0], c0[1], af, Rs[(kk * 4 + t4) * RLD + nb * 8 + g], c0[0], c0[1]);
-      dmma884(c1[0], c1[1], af, Rs[(kk * 4 + t4) * RLD + (nb + 1) * 8 + g], c1[0], c1[1]);
+    const int ai = (tid >> 4) * 2, bi = (tid & 15) * 2;
+    double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < TS; ++r) {
+      const double l0 = Lm[r * ZLD + ai], l1 = Lm[r * ZLD + ai + 1], r0v = Rs[r * ZLD + bi], r1v = Rs[r * ZLD + bi + 1];
+      s00 = fma(l0, r0v, s00); s01 = fma(l0, r1v, s01); s10 = fma(l1, r0v, s10); s11 = fma(l1, r1v, s11);
     }
-    const int ai = mt * 8 + g;
-    *reinterpret_cast<double2*>(part + ai * PM + nb * 8 + 2 * t4) = make_double2(c0[0], c0[1]);
-    *reinterpret_cast<double2*>(part + ai * PM + (nb + 1) * 8 + 2 * t4) = make_double2(c1[0], c1[1]);
+    part[ai * PM + bi] = s00; part[ai * PM + bi + 1] = s01; part[(ai + 1) * PM + bi] = s10; part[(ai + 1) * PM + bi + 1] = s11;
   }
 }
 
@@ -1343,13 +1328,12 @@ __global__ void __launch_bounds__(256, 3) k_rr(BigArgs a) {
 }
 
 // k_update: Z <- Z Qtop + R Qbot, W <- W Qtop + W2 Qbot (rows of one tile, in place).
-constexpr int ULD = PM + 4;     // 36 = 4 mod 16: conflict-free DMMA fragment loads (as VLD / PLD in k_prod)
-constexpr size_t UPD_SMEM = ((size_t)JN * ULD + 2 * TS * ULD) * sizeof(double);
+constexpr size_t UPD_SMEM = ((size_t)JN * ZLD + 2 * TS * ZLD) * sizeof(double);
 __global__ void __launch_bounds__(256) k_update(BigArgs a) {
   extern __shared__ __align__(16) double sm[];
-  double* Qs = sm;                   // [JN][ULD]   Q' = [Q1; Q2] (2 PM x PM)
-  double* Zs = Qs + JN * ULD;        // [TS][ULD]
-  double* Rs = Zs + TS * ULD;
+  double* Qs = sm;                   // [JN][ZLD]
+  double* Zs = Qs + JN * ZLD;        // [TS][ZLD]
+  double* Rs = Zs + TS * ZLD;
   const Layout& L = a.L;
   const int b = blockIdx.z;
   if ((int)blockIdx.x >= L.nt[b]) return;
@@ -1359,8 +1343,7 @@ __global__ void __launch_bounds__(256) k_update(BigArgs a) {
   if (a.step > 0 && NI[I_Q + b] != a.step + 1) return;
   double* S = node_ptr(a, slot);
   const int N = L.N[b], tid = threadIdx.x, r0 = blockIdx.x * TS;
-  const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
-  for (int e = tid; e < JN * PM; e += 256) Qs[(e / PM) * ULD + (e % PM)] = S[L.Q[b] + e];
+  for (int e = tid; e < JN * PM; e += 256) Qs[(e / PM) * ZLD + (e % PM)] = S[L.Q[b] + e];
   for (int pass = 0; pass < 2; ++pass) {
     double* A0 = S + (pass ? L.W[b] : L.Z[b]);
     const double* A1 = S + (pass ? L.W2[b] : L.R[b]);
@@ -1368,29 +1351,24 @@ __global__ void __launch_bounds__(256) k_update(BigArgs a) {
     for (int e = tid; e < TS * PM; e += 256) {
       const int row = e / PM, col = e % PM;
       const bool ok = r0 + row < N;
-      Zs[row * ULD + col] = ok ? A0[(size_t)(r0 + row) * PM + col] : 0.0;
-      Rs[row * ULD + col] = ok ? A1[(size_t)(r0 + row) * PM + col] : 0.0;
+      Zs[row * ZLD + col] = ok ? A0[(size_t)(r0 + row) * PM + col] : 0.0;
+      Rs[row * ZLD + col] = ok ? A1[(size_t)(r0 + row) * PM + col] : 0.0;
     }
     __syncthreads();
-    // [64 x 32] = [Zs | Rs] (64 x 64) . Q' (64 x 32) on the FP64 tensor pipe: warp w owns rows 8 w .. 8 w + 7, all four 8-column tiles
-    double c[PM / 8][2];
+    constexpr int CPT = TS * PM / 256;
+    const int row = tid / (PM / CPT), cb = (tid % (PM / CPT)) * CPT;
+    double acc[CPT];
 #pragma unroll
-    for (int nt = 0; nt < PM / 8; ++nt) c[nt][0] = c[nt][1] = 0.0;
-    const int arow = (warp * 8 + g) * ULD;
+    for (int q = 0; q < CPT; ++q) acc[q] = 0.0;
+#pragma unroll 4
+    for (int c = 0; c < PM; ++c) {
+      const double z = Zs[row * ZLD + c], r = Rs[row * ZLD + c];
 #pragma unroll
-    for (int kk = 0; kk < PM / 4; ++kk) {
-      const double az = Zs[arow + kk * 4 + t4], ar = Rs[arow + kk * 4 + t4];
-#pragma unroll
-      for (int nt = 0; nt < PM / 8; ++nt) {
-        dmma884(c[nt][0], c[nt][1], az, Qs[(kk * 4 + t4) * ULD + nt * 8 + g], c[nt][0], c[nt][1]);
-        dmma884(c[nt][0], c[nt][1], ar, Qs[(PM + kk * 4 + t4) * ULD + nt * 8 + g], c[nt][0], c[nt][1]);
-      }
+      for (int q = 0; q < CPT; ++q) acc[q] = fma(z, Qs[c * ZLD + cb + q], fma(r, Qs[(PM + c) * ZLD + cb + q], acc[q]));
     }
-    const int orow = r0 + warp * 8 + g;
-    if (orow < N) {
+    if (r0 + row < N) {
 #pragma unroll
-      for (int nt = 0; nt < PM / 8; ++nt)
-        *reinterpret_cast<double2*>(A0 + (size_t)orow * PM + nt * 8 + 2 * t4) = make_double2(c[nt][0], c[nt][1]);
+      for (int q = 0; q < CPT; ++q) A0[(size_t)(r0 + row) * PM + cb + q] = acc[q];
     }
   }
 }
