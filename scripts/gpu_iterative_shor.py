@@ -1,3 +1,5 @@
+"""GPU diagnostic: branch-and-bound with and without the iterative Shor mode on four small instances (nodes explored, splits,
+Shor index updates, final gap); time-boxed at 120 s per run."""
 import sys, os
 sys.path.insert(0, '/root/repo')
 import numpy as np
